@@ -1,0 +1,691 @@
+/*
+ * ref_lapack.c -- CPU restatement of the reference LAPACK routines on the one-sided factorization
+ * hot path (LU / Cholesky / Householder QR) and the few aux routines they need.
+ * TEST INFRASTRUCTURE ONLY (see oracle.h).  Each function cites the /root/reference file:line it
+ * follows; operation order is the reference's (build with -ffp-contract=off).
+ */
+#include "oracle.h"
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define A_(i, j) a[(size_t)(i) + (size_t)(j) * lda]
+#define B_(i, j) b[(size_t)(i) + (size_t)(j) * ldb]
+#define C_(i, j) c[(size_t)(i) + (size_t)(j) * ldc]
+#define V_(i, j) v[(size_t)(i) + (size_t)(j) * ldv]
+#define T_(i, j) t[(size_t)(i) + (size_t)(j) * ldt]
+#define W_(i, j) work[(size_t)(i) + (size_t)(j) * ldwork]
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* INSTALL/dlamch.f:99-122 for IEEE binary64: eps = 2^-53 (rounding), sfmin = tiny.            */
+double ora_dlamch(char cmach)
+{
+    if (ora_lsame(cmach, 'E')) return DBL_EPSILON * 0.5;
+    if (ora_lsame(cmach, 'S')) return DBL_MIN;              /* 1/huge < tiny, so sfmin = tiny */
+    if (ora_lsame(cmach, 'B')) return 2.0;
+    if (ora_lsame(cmach, 'P')) return DBL_EPSILON * 0.5 * 2.0;
+    if (ora_lsame(cmach, 'N')) return 53.0;
+    if (ora_lsame(cmach, 'R')) return 1.0;
+    if (ora_lsame(cmach, 'M')) return -1021.0;
+    if (ora_lsame(cmach, 'U')) return DBL_MIN;
+    if (ora_lsame(cmach, 'L')) return 1024.0;
+    if (ora_lsame(cmach, 'O')) return DBL_MAX;
+    return 0.0;
+}
+
+/* SRC/ilaenv.f:289-302,374-380 (NB) and :623-630 (NX); overridable like TESTING/LIN/xlaenv.f:101. */
+static int g_nb_getrf = 64, g_nb_potrf = 64, g_nb_geqrf = 32, g_nx_geqrf = 128;
+void ora_set_nb(int nb_getrf, int nb_potrf, int nb_geqrf, int nx_geqrf)
+{
+    g_nb_getrf = nb_getrf; g_nb_potrf = nb_potrf; g_nb_geqrf = nb_geqrf; g_nx_geqrf = nx_geqrf;
+}
+int ora_ilaenv_nb(const char *name)
+{
+    if (!strcmp(name, "DGETRF")) return g_nb_getrf;
+    if (!strcmp(name, "DPOTRF")) return g_nb_potrf;
+    if (!strcmp(name, "DGEQRF") || !strcmp(name, "DORGQR")) return g_nb_geqrf;
+    return 1;
+}
+
+/* SRC/dlapy2.f:96-112 */
+double ora_dlapy2(double x, double y)
+{
+    int xnan = (x != x), ynan = (y != y);
+    double r = 0.0;
+    if (xnan) r = x;
+    if (ynan) r = y;
+    if (!(xnan || ynan)) {
+        double xa = fabs(x), ya = fabs(y);
+        double w = xa > ya ? xa : ya, z = xa < ya ? xa : ya;
+        if (z == 0.0 || w > DBL_MAX) r = w;
+        else { double q = z / w; r = w * sqrt(1.0 + q * q); }
+    }
+    return r;
+}
+
+/* SRC/dlaruv.f:401-447.  The MM(i,:) table rows are the base-4096 digits of a**i mod 2**48 with
+ * a = 33952834046453 (row 1 = 494,322,2508,2549), so x(i) = (seed * a**i mod 2**48) / 2**48 and
+ * the seed leaves as seed * a**n.  The digit-wise float sum at dlaruv.f:417-418 is exact in
+ * binary64 (48 significant bits), so the "== 1.0" retry at :420-433 can never trigger here. */
+void ora_dlaruv(int iseed[4], int n, double *x)
+{
+    const unsigned long long MASK = (1ULL << 48) - 1, AMUL = 33952834046453ULL;
+    if (n < 1) return;
+    if (n > 128) n = 128;
+    unsigned long long s = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
+                           ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
+    unsigned long long p = s;
+    for (int i = 0; i < n; ++i) {
+        p = (p * AMUL) & MASK;
+        x[i] = (double)p * (1.0 / 281474976710656.0);
+    }
+    iseed[0] = (int)((p >> 36) & 4095); iseed[1] = (int)((p >> 24) & 4095);
+    iseed[2] = (int)((p >> 12) & 4095); iseed[3] = (int)(p & 4095);
+}
+
+/* SRC/dlarnv.f:140-170; idist 1: U(0,1), 2: U(-1,1), 3: N(0,1). */
+void ora_dlarnv(int idist, int iseed[4], long n, double *x)
+{
+    const double twopi = 6.28318530717958647692528676655900576839;
+    double u[128];
+    for (long iv = 0; iv < n; iv += 64) {
+        int il = (int)((n - iv) < 64 ? (n - iv) : 64);
+        int il2 = (idist == 3) ? 2 * il : il;
+        ora_dlaruv(iseed, il2, u);
+        if (idist == 1) for (int i = 0; i < il; ++i) x[iv + i] = u[i];
+        else if (idist == 2) for (int i = 0; i < il; ++i) x[iv + i] = 2.0 * u[i] - 1.0;
+        else if (idist == 3)
+            for (int i = 0; i < il; ++i) x[iv + i] = sqrt(-2.0 * log(u[2 * i])) * cos(twopi * u[2 * i + 1]);
+    }
+}
+
+/* SRC/dlange.f:144-190 ('M', '1'/'O', 'I'; NaN-propagating max via DISNAN). */
+double ora_dlange(char norm, int m, int n, const double *a, int lda)
+{
+    double value = 0.0;
+    if (imin(m, n) == 0) return 0.0;
+    if (ora_lsame(norm, 'M')) {
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < m; ++i) { double t = fabs(A_(i, j)); if (value < t || t != t) value = t; }
+    } else if (ora_lsame(norm, 'O') || norm == '1') {
+        for (int j = 0; j < n; ++j) {
+            double sum = 0.0;
+            for (int i = 0; i < m; ++i) sum = sum + fabs(A_(i, j));
+            if (value < sum || sum != sum) value = sum;
+        }
+    } else if (ora_lsame(norm, 'I')) {
+        double *w = (double *)calloc((size_t)m, sizeof(double));
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < m; ++i) w[i] = w[i] + fabs(A_(i, j));
+        for (int i = 0; i < m; ++i) { double t = w[i]; if (value < t || t != t) value = t; }
+        free(w);
+    } else {   /* 'F': plain two-pass scaled form (not on the checker path) */
+        double scale = 0.0, ssq = 1.0;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < m; ++i) {
+                double t = fabs(A_(i, j));
+                if (t != 0.0) {
+                    if (scale < t) { ssq = 1.0 + ssq * (scale / t) * (scale / t); scale = t; }
+                    else ssq = ssq + (t / scale) * (t / scale);
+                }
+            }
+        value = scale * sqrt(ssq);
+    }
+    return value;
+}
+
+/* SRC/dlansy.f:150-199 ('M', and '1'='O'='I' for a symmetric matrix). */
+double ora_dlansy(char norm, char uplo, int n, const double *a, int lda)
+{
+    double value = 0.0;
+    if (n == 0) return 0.0;
+    int upper = ora_lsame(uplo, 'U');
+    if (ora_lsame(norm, 'M')) {
+        for (int j = 0; j < n; ++j) {
+            int i0 = upper ? 0 : j, i1 = upper ? j + 1 : n;
+            for (int i = i0; i < i1; ++i) { double t = fabs(A_(i, j)); if (value < t || t != t) value = t; }
+        }
+        return value;
+    }
+    double *w = (double *)calloc((size_t)n, sizeof(double));
+    if (upper) {
+        for (int j = 0; j < n; ++j) {
+            double sum = 0.0;
+            for (int i = 0; i < j; ++i) { double t = fabs(A_(i, j)); sum = sum + t; w[i] = w[i] + t; }
+            w[j] = sum + fabs(A_(j, j));
+        }
+        for (int i = 0; i < n; ++i) { double sum = w[i]; if (value < sum || sum != sum) value = sum; }
+    } else {
+        for (int j = 0; j < n; ++j) {
+            double sum = w[j] + fabs(A_(j, j));
+            for (int i = j + 1; i < n; ++i) { double t = fabs(A_(i, j)); sum = sum + t; w[i] = w[i] + t; }
+            if (value < sum || sum != sum) value = sum;
+        }
+    }
+    free(w);
+    return value;
+}
+
+/* SRC/dlacpy.f */
+void ora_dlacpy(char uplo, int m, int n, const double *a, int lda, double *b, int ldb)
+{
+    if (ora_lsame(uplo, 'U')) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < imin(j + 1, m); ++i) B_(i, j) = A_(i, j);
+    } else if (ora_lsame(uplo, 'L')) {
+        for (int j = 0; j < n; ++j) for (int i = j; i < m; ++i) B_(i, j) = A_(i, j);
+    } else {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) B_(i, j) = A_(i, j);
+    }
+}
+
+/* SRC/dlaset.f: off-diagonals := alpha, diagonal := beta */
+void ora_dlaset(char uplo, int m, int n, double alpha, double beta, double *a, int lda)
+{
+    if (ora_lsame(uplo, 'U')) {
+        for (int j = 1; j < n; ++j) for (int i = 0; i < imin(j, m); ++i) A_(i, j) = alpha;
+    } else if (ora_lsame(uplo, 'L')) {
+        for (int j = 0; j < imin(m, n); ++j) for (int i = j + 1; i < m; ++i) A_(i, j) = alpha;
+    } else {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) A_(i, j) = alpha;
+    }
+    for (int i = 0; i < imin(m, n); ++i) A_(i, i) = beta;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* LU                                                                                          */
+
+/* SRC/dlaswp.f:138-183.  k1,k2 1-based, ipiv entries 1-based; 32-column strips then remainder. */
+void ora_dlaswp(int n, double *a, int lda, int k1, int k2, const int *ipiv, int incx)
+{
+    int ix0, i1, i2, inc;
+    if (incx > 0) { ix0 = k1; i1 = k1; i2 = k2; inc = 1; }
+    else if (incx < 0) { ix0 = k1 + (k1 - k2) * incx; i1 = k2; i2 = k1; inc = -1; }
+    else return;
+    int n32 = (n / 32) * 32;
+    for (int j = 0; j < n32; j += 32) {
+        int ix = ix0;
+        for (int i = i1; inc > 0 ? i <= i2 : i >= i2; i += inc, ix += incx) {
+            int ip = ipiv[ix - 1];
+            if (ip != i)
+                for (int k = j; k < j + 32; ++k) {
+                    double temp = A_(i - 1, k); A_(i - 1, k) = A_(ip - 1, k); A_(ip - 1, k) = temp;
+                }
+        }
+    }
+    if (n32 != n) {
+        int ix = ix0;
+        for (int i = i1; inc > 0 ? i <= i2 : i >= i2; i += inc, ix += incx) {
+            int ip = ipiv[ix - 1];
+            if (ip != i)
+                for (int k = n32; k < n; ++k) {
+                    double temp = A_(i - 1, k); A_(i - 1, k) = A_(ip - 1, k); A_(ip - 1, k) = temp;
+                }
+        }
+    }
+}
+
+/* SRC/dgetrf2.f:170-265 (recursive panel LU). */
+void ora_dgetrf2(int m, int n, double *a, int lda, int *ipiv, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    if (*info != 0) return;
+    if (m == 0 || n == 0) return;
+    if (m == 1) {                                           /* :170-177 */
+        ipiv[0] = 1;
+        if (A_(0, 0) == 0.0) *info = 1;
+    } else if (n == 1) {                                    /* :179-214 */
+        double sfmin = ora_dlamch('S');
+        int i = ora_idamax(m, a, 1);
+        ipiv[0] = i;
+        if (A_(i - 1, 0) != 0.0) {
+            if (i != 1) { double temp = A_(0, 0); A_(0, 0) = A_(i - 1, 0); A_(i - 1, 0) = temp; }
+            if (fabs(A_(0, 0)) >= sfmin) ora_dscal(m - 1, 1.0 / A_(0, 0), &A_(1, 0), 1);
+            else for (int r = 1; r < m; ++r) A_(r, 0) = A_(r, 0) / A_(0, 0);
+        } else *info = 1;
+    } else {                                                /* :216-263 */
+        int n1 = imin(m, n) / 2, n2 = n - n1, iinfo;
+        ora_dgetrf2(m, n1, a, lda, ipiv, &iinfo);
+        if (*info == 0 && iinfo > 0) *info = iinfo;
+        ora_dlaswp(n2, &A_(0, n1), lda, 1, n1, ipiv, 1);
+        ora_dtrsm('L', 'L', 'N', 'U', n1, n2, 1.0, a, lda, &A_(0, n1), lda);
+        ora_dgemm('N', 'N', m - n1, n2, n1, -1.0, &A_(n1, 0), lda, &A_(0, n1), lda, 1.0, &A_(n1, n1), lda);
+        ora_dgetrf2(m - n1, n2, &A_(n1, n1), lda, ipiv + n1, &iinfo);
+        if (*info == 0 && iinfo > 0) *info = iinfo + n1;
+        for (int i = n1; i < imin(m, n); ++i) ipiv[i] = ipiv[i] + n1;
+        ora_dlaswp(n1, a, lda, n1 + 1, imin(m, n), ipiv, 1);
+    }
+}
+
+/* SRC/dgetrf.f:144-219 (right-looking blocked LU, NB from ILAENV). */
+void ora_dgetrf(int m, int n, double *a, int lda, int *ipiv, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    if (*info != 0) return;
+    if (m == 0 || n == 0) return;
+    int nb = ora_ilaenv_nb("DGETRF"), mn = imin(m, n);
+    if (nb <= 1 || nb >= mn) { ora_dgetrf2(m, n, a, lda, ipiv, info); return; }
+    for (int j = 0; j < mn; j += nb) {                      /* j is 0-based; reference J = j+1 */
+        int jb = imin(mn - j, nb), iinfo;
+        ora_dgetrf2(m - j, jb, &A_(j, j), lda, ipiv + j, &iinfo);
+        if (*info == 0 && iinfo > 0) *info = iinfo + j;
+        for (int i = j; i < imin(m, j + jb); ++i) ipiv[i] = j + ipiv[i];
+        ora_dlaswp(j, a, lda, j + 1, j + jb, ipiv, 1);
+        if (j + jb < n) {
+            ora_dlaswp(n - j - jb, &A_(0, j + jb), lda, j + 1, j + jb, ipiv, 1);
+            ora_dtrsm('L', 'L', 'N', 'U', jb, n - j - jb, 1.0, &A_(j, j), lda, &A_(j, j + jb), lda);
+            if (j + jb < m)
+                ora_dgemm('N', 'N', m - j - jb, n - j - jb, jb, -1.0, &A_(j + jb, j), lda, &A_(j, j + jb), lda,
+                          1.0, &A_(j + jb, j + jb), lda);
+        }
+    }
+}
+
+/* SRC/dgetrs.f:158-218 */
+void ora_dgetrs(char trans, int n, int nrhs, const double *a, int lda, const int *ipiv, double *b, int ldb,
+                int *info)
+{
+    *info = 0;
+    int notran = ora_lsame(trans, 'N');
+    if (!notran && !ora_lsame(trans, 'T') && !ora_lsame(trans, 'C')) *info = -1;
+    else if (n < 0) *info = -2;
+    else if (nrhs < 0) *info = -3;
+    else if (lda < imax(1, n)) *info = -5;
+    else if (ldb < imax(1, n)) *info = -8;
+    if (*info != 0) return;
+    if (n == 0 || nrhs == 0) return;
+    if (notran) {
+        ora_dlaswp(nrhs, b, ldb, 1, n, ipiv, 1);
+        ora_dtrsm('L', 'L', 'N', 'U', n, nrhs, 1.0, a, lda, b, ldb);
+        ora_dtrsm('L', 'U', 'N', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+    } else {
+        ora_dtrsm('L', 'U', 'T', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+        ora_dtrsm('L', 'L', 'T', 'U', n, nrhs, 1.0, a, lda, b, ldb);
+        ora_dlaswp(nrhs, b, ldb, 1, n, ipiv, -1);
+    }
+}
+
+/* SRC/dgesv.f:148-172 */
+void ora_dgesv(int n, int nrhs, double *a, int lda, int *ipiv, double *b, int ldb, int *info)
+{
+    *info = 0;
+    if (n < 0) *info = -1; else if (nrhs < 0) *info = -2; else if (lda < imax(1, n)) *info = -4;
+    else if (ldb < imax(1, n)) *info = -7;
+    if (*info != 0) return;
+    ora_dgetrf(n, n, a, lda, ipiv, info);
+    if (*info == 0) ora_dgetrs('N', n, nrhs, a, lda, ipiv, b, ldb, info);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Cholesky                                                                                    */
+
+/* SRC/dpotrf2.f:165-230 */
+void ora_dpotrf2(char uplo, int n, double *a, int lda, int *info)
+{
+    *info = 0;
+    int upper = ora_lsame(uplo, 'U');
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1; else if (n < 0) *info = -2;
+    else if (lda < imax(1, n)) *info = -4;
+    if (*info != 0) return;
+    if (n == 0) return;
+    if (n == 1) {
+        if (A_(0, 0) <= 0.0 || A_(0, 0) != A_(0, 0)) { *info = 1; return; }
+        A_(0, 0) = sqrt(A_(0, 0));
+    } else {
+        int n1 = n / 2, n2 = n - n1, iinfo;
+        ora_dpotrf2(uplo, n1, a, lda, &iinfo);
+        if (iinfo != 0) { *info = iinfo; return; }
+        if (upper) {
+            ora_dtrsm('L', 'U', 'T', 'N', n1, n2, 1.0, a, lda, &A_(0, n1), lda);
+            ora_dsyrk(uplo, 'T', n2, n1, -1.0, &A_(0, n1), lda, 1.0, &A_(n1, n1), lda);
+        } else {
+            ora_dtrsm('R', 'L', 'T', 'N', n2, n1, 1.0, a, lda, &A_(n1, 0), lda);
+            ora_dsyrk(uplo, 'N', n2, n1, -1.0, &A_(n1, 0), lda, 1.0, &A_(n1, n1), lda);
+        }
+        ora_dpotrf2(uplo, n2, &A_(n1, n1), lda, &iinfo);
+        if (iinfo != 0) { *info = iinfo + n1; return; }
+    }
+}
+
+/* SRC/dpotrf.f:145-240 (left-looking by block column). */
+void ora_dpotrf(char uplo, int n, double *a, int lda, int *info)
+{
+    *info = 0;
+    int upper = ora_lsame(uplo, 'U');
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1; else if (n < 0) *info = -2;
+    else if (lda < imax(1, n)) *info = -4;
+    if (*info != 0) return;
+    if (n == 0) return;
+    int nb = ora_ilaenv_nb("DPOTRF");
+    if (nb <= 1 || nb >= n) { ora_dpotrf2(uplo, n, a, lda, info); return; }
+    for (int j = 0; j < n; j += nb) {
+        int jb = imin(nb, n - j);
+        if (upper) {
+            ora_dsyrk('U', 'T', jb, j, -1.0, &A_(0, j), lda, 1.0, &A_(j, j), lda);
+            ora_dpotrf2('U', jb, &A_(j, j), lda, info);
+            if (*info != 0) { *info = *info + j; return; }
+            if (j + jb < n) {
+                ora_dgemm('T', 'N', jb, n - j - jb, j, -1.0, &A_(0, j), lda, &A_(0, j + jb), lda, 1.0,
+                          &A_(j, j + jb), lda);
+                ora_dtrsm('L', 'U', 'T', 'N', jb, n - j - jb, 1.0, &A_(j, j), lda, &A_(j, j + jb), lda);
+            }
+        } else {
+            ora_dsyrk('L', 'N', jb, j, -1.0, &A_(j, 0), lda, 1.0, &A_(j, j), lda);
+            ora_dpotrf2('L', jb, &A_(j, j), lda, info);
+            if (*info != 0) { *info = *info + j; return; }
+            if (j + jb < n) {
+                ora_dgemm('N', 'T', n - j - jb, jb, j, -1.0, &A_(j + jb, 0), lda, &A_(j, 0), lda, 1.0,
+                          &A_(j + jb, j), lda);
+                ora_dtrsm('R', 'L', 'T', 'N', n - j - jb, jb, 1.0, &A_(j, j), lda, &A_(j + jb, j), lda);
+            }
+        }
+    }
+}
+
+/* SRC/dpotrs.f:147-196 */
+void ora_dpotrs(char uplo, int n, int nrhs, const double *a, int lda, double *b, int ldb, int *info)
+{
+    *info = 0;
+    int upper = ora_lsame(uplo, 'U');
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1; else if (n < 0) *info = -2; else if (nrhs < 0) *info = -3;
+    else if (lda < imax(1, n)) *info = -5; else if (ldb < imax(1, n)) *info = -7;
+    if (*info != 0) return;
+    if (n == 0 || nrhs == 0) return;
+    if (upper) {
+        ora_dtrsm('L', 'U', 'T', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+        ora_dtrsm('L', 'U', 'N', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+    } else {
+        ora_dtrsm('L', 'L', 'N', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+        ora_dtrsm('L', 'L', 'T', 'N', n, nrhs, 1.0, a, lda, b, ldb);
+    }
+}
+
+/* SRC/dposv.f:160-183 */
+void ora_dposv(char uplo, int n, int nrhs, double *a, int lda, double *b, int ldb, int *info)
+{
+    *info = 0;
+    if (!ora_lsame(uplo, 'U') && !ora_lsame(uplo, 'L')) *info = -1; else if (n < 0) *info = -2;
+    else if (nrhs < 0) *info = -3; else if (lda < imax(1, n)) *info = -5; else if (ldb < imax(1, n)) *info = -7;
+    if (*info != 0) return;
+    ora_dpotrf(uplo, n, a, lda, info);
+    if (*info == 0) ora_dpotrs(uplo, n, nrhs, a, lda, b, ldb, info);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Householder QR                                                                              */
+
+/* SRC/dlarfg.f:140-186 */
+void ora_dlarfg(int n, double *alpha, double *x, int incx, double *tau)
+{
+    if (n <= 1) { *tau = 0.0; return; }
+    double xnorm = ora_dnrm2(n - 1, x, incx);
+    if (xnorm == 0.0) { *tau = 0.0; return; }
+    double beta = -copysign(ora_dlapy2(*alpha, xnorm), *alpha);
+    double safmin = ora_dlamch('S') / ora_dlamch('E');
+    int knt = 0;
+    if (fabs(beta) < safmin) {
+        double rsafmn = 1.0 / safmin;
+        do {
+            knt = knt + 1;
+            ora_dscal(n - 1, rsafmn, x, incx);
+            beta = beta * rsafmn;
+            *alpha = *alpha * rsafmn;
+        } while (fabs(beta) < safmin && knt < 20);
+        xnorm = ora_dnrm2(n - 1, x, incx);
+        beta = -copysign(ora_dlapy2(*alpha, xnorm), *alpha);
+    }
+    *tau = (beta - *alpha) / beta;
+    ora_dscal(n - 1, 1.0 / (*alpha - beta), x, incx);
+    for (int j = 0; j < knt; ++j) beta = beta * safmin;
+    *alpha = beta;
+}
+
+/* SRC/iladlc.f:101-112 -- last non-zero column (1-based count). */
+int ora_iladlc(int m, int n, const double *a, int lda)
+{
+    if (n == 0) return n;
+    if (A_(0, n - 1) != 0.0 || A_(m - 1, n - 1) != 0.0) return n;
+    for (int j = n; j >= 1; --j)
+        for (int i = 0; i < m; ++i)
+            if (A_(i, j - 1) != 0.0) return j;
+    return 0;
+}
+
+/* SRC/iladlr.f:101-114 -- last non-zero row (1-based count). */
+int ora_iladlr(int m, int n, const double *a, int lda)
+{
+    if (m == 0) return m;
+    if (A_(m - 1, 0) != 0.0 || A_(m - 1, n - 1) != 0.0) return m;
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+        int i = m;
+        while (i >= 1 && A_(imax(i, 1) - 1, j) == 0.0) i = i - 1;
+        r = imax(r, i);
+    }
+    return r;
+}
+
+/* SRC/dlarf1f.f:192-290 -- apply H = I - tau v v**T with v(1)=1 implicit (v[0] is NOT read). */
+void ora_dlarf1f(char side, int m, int n, const double *v, int incv, double tau, double *c, int ldc,
+                 double *work)
+{
+    int applyleft = ora_lsame(side, 'L');
+    int lastv = 1, lastc = 0;
+    ptrdiff_t i = 0;                                         /* 0-based position in v of element LASTV */
+    if (tau != 0.0) {
+        lastv = applyleft ? m : n;
+        i = incv > 0 ? (ptrdiff_t)(lastv - 1) * incv : 0;
+        while (lastv > 1 && v[i] == 0.0) { lastv = lastv - 1; i = i - incv; }
+        lastc = applyleft ? ora_iladlc(lastv, n, c, ldc) : ora_iladlr(m, lastv, c, ldc);
+        if (incv > 0) i = incv;                             /* -> V(2) */
+    }
+    if (lastc == 0) return;
+    if (applyleft) {
+        if (lastv == 1) {
+            ora_dscal(lastc, 1.0 - tau, c, ldc);
+        } else {
+            ora_dgemv('T', lastv - 1, lastc, 1.0, &C_(1, 0), ldc, &v[i], incv, 0.0, work, 1);
+            ora_daxpy(lastc, 1.0, c, ldc, work, 1);
+            ora_daxpy(lastc, -tau, work, 1, c, ldc);
+            ora_dger(lastv - 1, lastc, -tau, &v[i], incv, work, 1, &C_(1, 0), ldc);
+        }
+    } else {
+        if (lastv == 1) {
+            ora_dscal(lastc, 1.0 - tau, c, 1);
+        } else {
+            ora_dgemv('N', lastc, lastv - 1, 1.0, &C_(0, 1), ldc, &v[i], incv, 0.0, work, 1);
+            ora_daxpy(lastc, 1.0, c, 1, work, 1);
+            ora_daxpy(lastc, -tau, work, 1, c, 1);
+            ora_dger(lastc, lastv - 1, -tau, work, 1, &v[i], incv, &C_(0, 1), ldc);
+        }
+    }
+}
+
+/* SRC/dgeqr2.f:150-184 */
+void ora_dgeqr2(int m, int n, double *a, int lda, double *tau, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    if (*info != 0) return;
+    int k = imin(m, n);
+    for (int i = 0; i < k; ++i) {
+        ora_dlarfg(m - i, &A_(i, i), &A_(imin(i + 1, m - 1), i), 1, &tau[i]);
+        if (i < n - 1) ora_dlarf1f('L', m - i, n - i - 1, &A_(i, i), 1, tau[i], &A_(i, i + 1), lda, work);
+    }
+}
+
+/* SRC/dlarft_lvl2.f:199-258 -- DIRECT='F', STOREV='C' only (the QR case). */
+void ora_dlarft_lvl2(char direct, char storev, int n, int k, const double *v, int ldv, const double *tau,
+                     double *t, int ldt)
+{
+    (void)direct; (void)storev;
+    if (n == 0) return;
+    int prevlastv = n;                                      /* 1-based like the reference */
+    for (int i = 1; i <= k; ++i) {
+        prevlastv = imax(i, prevlastv);
+        if (tau[i - 1] == 0.0) {
+            for (int j = 1; j <= i; ++j) T_(j - 1, i - 1) = 0.0;
+        } else {
+            int lastv;
+            for (lastv = n; lastv >= i + 1; --lastv)
+                if (V_(lastv - 1, i - 1) != 0.0) break;
+            for (int j = 1; j <= i - 1; ++j) T_(j - 1, i - 1) = -tau[i - 1] * V_(i - 1, j - 1);
+            int j = imin(lastv, prevlastv);
+            ora_dgemv('T', j - i, i - 1, -tau[i - 1], &V_(i, 0), ldv, &V_(i, i - 1), 1, 1.0, &T_(0, i - 1), 1);
+            ora_dtrmv('U', 'N', 'N', i - 1, t, ldt, &T_(0, i - 1), 1);
+            T_(i - 1, i - 1) = tau[i - 1];
+            if (i > 1) prevlastv = imax(prevlastv, lastv); else prevlastv = lastv;
+        }
+    }
+}
+
+/* SRC/dlarft.f:207-349 -- recursive compact-WY T, QR case (DIRECT='F', STOREV='C');
+ * crossover NX = 64 (SRC/ilaenv.f:679-682). */
+void ora_dlarft(char direct, char storev, int n, int k, const double *v, int ldv, const double *tau,
+                double *t, int ldt)
+{
+    if (n == 0 || k == 0) return;
+    if (n == 1 || k == 1) { T_(0, 0) = tau[0]; return; }
+    const int nx = 64;
+    if (k < nx) { ora_dlarft_lvl2(direct, storev, n, k, v, ldv, tau, t, ldt); return; }
+    int l = k / 2;
+    ora_dlarft(direct, storev, n, l, v, ldv, tau, t, ldt);
+    ora_dlarft(direct, storev, n - l, k - l, &V_(l, l), ldv, tau + l, &T_(l, l), ldt);
+    for (int j = 0; j < l; ++j)
+        for (int i = 0; i < k - l; ++i) T_(j, l + i) = V_(l + i, j);
+    ora_dtrmm('R', 'L', 'N', 'U', l, k - l, 1.0, &V_(l, l), ldv, &T_(0, l), ldt);
+    ora_dgemm('T', 'N', l, k - l, n - k, 1.0, &V_(k, 0), ldv, &V_(k, l), ldv, 1.0, &T_(0, l), ldt);
+    ora_dtrmm('L', 'U', 'N', 'N', l, k - l, -1.0, t, ldt, &T_(0, l), ldt);
+    ora_dtrmm('R', 'U', 'N', 'N', l, k - l, 1.0, &T_(l, l), ldt, &T_(0, l), ldt);
+}
+
+/* SRC/dlarfb.f:231-345 -- DIRECT='F', STOREV='C'; SIDE L or R; TRANS N or T. */
+void ora_dlarfb(char side, char trans, char direct, char storev, int m, int n, int k, const double *v, int ldv,
+                const double *t, int ldt, double *c, int ldc, double *work, int ldwork)
+{
+    (void)direct; (void)storev;
+    if (m <= 0 || n <= 0) return;
+    char transt = ora_lsame(trans, 'N') ? 'T' : 'N';
+    if (ora_lsame(side, 'L')) {
+        /* W := C**T V = (C1**T V1 + C2**T V2) : dlarfb.f:257-275 */
+        for (int j = 0; j < k; ++j) ora_dcopy(n, &C_(j, 0), ldc, &W_(0, j), 1);
+        ora_dtrmm('R', 'L', 'N', 'U', n, k, 1.0, v, ldv, work, ldwork);
+        if (m > k) ora_dgemm('T', 'N', n, k, m - k, 1.0, &C_(k, 0), ldc, &V_(k, 0), ldv, 1.0, work, ldwork);
+        ora_dtrmm('R', 'U', transt, 'N', n, k, 1.0, t, ldt, work, ldwork);
+        if (m > k) ora_dgemm('N', 'T', m - k, n, k, -1.0, &V_(k, 0), ldv, work, ldwork, 1.0, &C_(k, 0), ldc);
+        ora_dtrmm('R', 'L', 'T', 'U', n, k, 1.0, v, ldv, work, ldwork);
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < n; ++i) C_(j, i) = C_(j, i) - W_(i, j);
+    } else {
+        /* W := C V : dlarfb.f:307-345 */
+        for (int j = 0; j < k; ++j) ora_dcopy(m, &C_(0, j), 1, &W_(0, j), 1);
+        ora_dtrmm('R', 'L', 'N', 'U', m, k, 1.0, v, ldv, work, ldwork);
+        if (n > k) ora_dgemm('N', 'N', m, k, n - k, 1.0, &C_(0, k), ldc, &V_(k, 0), ldv, 1.0, work, ldwork);
+        ora_dtrmm('R', 'U', trans, 'N', m, k, 1.0, t, ldt, work, ldwork);
+        if (n > k) ora_dgemm('N', 'T', m, n - k, k, -1.0, work, ldwork, &V_(k, 0), ldv, 1.0, &C_(0, k), ldc);
+        ora_dtrmm('R', 'L', 'T', 'U', m, k, 1.0, v, ldv, work, ldwork);
+        for (int j = 0; j < k; ++j)
+            for (int i = 0; i < m; ++i) C_(i, j) = C_(i, j) - W_(i, j);
+    }
+}
+
+/* SRC/dgeqrf.f:180-278.  work must hold max(1,n)*nb doubles (lwork is honoured like the reference). */
+void ora_dgeqrf(int m, int n, double *a, int lda, double *tau, double *work, int lwork, int *info)
+{
+    int k = imin(m, n);
+    *info = 0;
+    int nb = ora_ilaenv_nb("DGEQRF");
+    int lquery = (lwork == -1);
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    else if (!lquery) { if (lwork <= 0 || (m > 0 && lwork < imax(1, n))) *info = -7; }
+    if (*info != 0) return;
+    if (lquery) { work[0] = (k == 0) ? 1.0 : (double)n * nb; return; }
+    if (k == 0) { work[0] = 1.0; return; }
+    int nbmin = 2, nx = 0, iws = n, ldwork = n, i = 0, iinfo;
+    if (nb > 1 && nb < k) {
+        nx = imax(0, g_nx_geqrf);
+        if (nx < k) {
+            ldwork = n;
+            iws = ldwork * nb;
+            if (lwork < iws) { nb = lwork / ldwork; nbmin = 2; }
+        }
+    }
+    if (nb >= nbmin && nb < k && nx < k) {
+        for (i = 0; i < k - nx; i += nb) {
+            int ib = imin(k - i, nb);
+            ora_dgeqr2(m - i, ib, &A_(i, i), lda, &tau[i], work, &iinfo);
+            if (i + ib < n) {
+                ora_dlarft('F', 'C', m - i, ib, &A_(i, i), lda, &tau[i], work, ldwork);
+                ora_dlarfb('L', 'T', 'F', 'C', m - i, n - i - ib, ib, &A_(i, i), lda, work, ldwork,
+                           &A_(i, i + ib), lda, work + ib, ldwork);
+            }
+        }
+    } else i = 0;
+    if (i < k) ora_dgeqr2(m - i, n - i, &A_(i, i), lda, &tau[i], work, &iinfo);
+    work[0] = (double)iws;
+}
+
+/* SRC/dorg2r.f:130-168 */
+void ora_dorg2r(int m, int n, int k, double *a, int lda, const double *tau, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0 || n > m) *info = -2; else if (k < 0 || k > n) *info = -3;
+    else if (lda < imax(1, m)) *info = -5;
+    if (*info != 0) return;
+    if (n <= 0) return;
+    for (int j = k; j < n; ++j) {
+        for (int l = 0; l < m; ++l) A_(l, j) = 0.0;
+        A_(j, j) = 1.0;
+    }
+    for (int i = k - 1; i >= 0; --i) {
+        if (i < n - 1) ora_dlarf1f('L', m - i, n - i - 1, &A_(i, i), 1, tau[i], &A_(i, i + 1), lda, work);
+        if (i < m - 1) ora_dscal(m - i - 1, -tau[i], &A_(i + 1, i), 1);
+        A_(i, i) = 1.0 - tau[i];
+        for (int l = 0; l < i; ++l) A_(l, i) = 0.0;
+    }
+}
+
+/* SRC/dorgqr.f:160-277 (NB=32, NX=128 from ilaenv.f for xORGQR; work >= n*nb). */
+void ora_dorgqr(int m, int n, int k, double *a, int lda, const double *tau, double *work, int lwork, int *info)
+{
+    *info = 0;
+    int nb = ora_ilaenv_nb("DORGQR");
+    int lquery = (lwork == -1);
+    if (m < 0) *info = -1; else if (n < 0 || n > m) *info = -2; else if (k < 0 || k > n) *info = -3;
+    else if (lda < imax(1, m)) *info = -5; else if (lwork < imax(1, n) && !lquery) *info = -8;
+    if (*info != 0) return;
+    if (lquery) { work[0] = (double)(imax(1, n) * nb); return; }
+    if (n <= 0) { work[0] = 1.0; return; }
+    int nbmin = 2, nx = 0, iws = n, ldwork = n, ki = 0, kk, iinfo;
+    if (nb > 1 && nb < k) {
+        nx = imax(0, g_nx_geqrf);
+        if (nx < k) {
+            ldwork = n;
+            iws = ldwork * nb;
+            if (lwork < iws) { nb = lwork / ldwork; nbmin = 2; }
+        }
+    }
+    if (nb >= nbmin && nb < k && nx < k) {
+        ki = ((k - nx - 1) / nb) * nb;
+        kk = imin(k, ki + nb);
+        for (int j = kk; j < n; ++j) for (int i = 0; i < kk; ++i) A_(i, j) = 0.0;
+    } else kk = 0;
+    if (kk < n) ora_dorg2r(m - kk, n - kk, k - kk, &A_(kk, kk), lda, tau + kk, work, &iinfo);
+    if (kk > 0) {
+        for (int i = ki; i >= 0; i -= nb) {                 /* i 0-based; reference I = i+1 */
+            int ib = imin(nb, k - i);
+            if (i + ib < n) {
+                ora_dlarft('F', 'C', m - i, ib, &A_(i, i), lda, tau + i, work, ldwork);
+                ora_dlarfb('L', 'N', 'F', 'C', m - i, n - i - ib, ib, &A_(i, i), lda, work, ldwork,
+                           &A_(i, i + ib), lda, work + ib, ldwork);
+            }
+            ora_dorg2r(m - i, ib, ib, &A_(i, i), lda, tau + i, work, &iinfo);
+            for (int j = i; j < i + ib; ++j) for (int l = 0; l < i; ++l) A_(l, j) = 0.0;
+        }
+    }
+    work[0] = (double)iws;
+}

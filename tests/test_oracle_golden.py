@@ -1,0 +1,220 @@
+"""Pins the CPU oracle (oracle/) against the committed netlib-3.12.0 golden vectors
+(tests/golden/make_golden.py) and the DLARNV known answer from SURVEY.md section 7.
+
+Tolerances: IPIV / INFO / RNG bit-exact; factor entries 1e-12 relative (the golden side ran on
+OpenBLAS BLAS, a different summation order than the reference BLAS triple loops the oracle restates).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+SEED = (1988, 1989, 1990, 1991)
+RTOL = 1e-12
+
+
+def relerr(x, y):
+    d = np.max(np.abs(x - y)) if x.size else 0.0
+    s = max(1.0, np.max(np.abs(y))) if y.size else 1.0
+    return d / s
+
+
+def test_dlarnv_known_answer():
+    x, seed = O.dlarnv(2, SEED, 5)
+    assert list(x) == [-0.5217827788720584, -0.08059010722889326, -0.46509858502694357,
+                       0.07496184221979973, -0.745637131925811]
+    assert seed == [520, 3830, 1597, 2307]
+
+
+@pytest.mark.parametrize("idist", [1, 2, 3])
+def test_dlarnv_stream(golden, idist):
+    x, seed = O.dlarnv(idist, SEED, 300)
+    ref = golden[f"larnv{idist}_x"]
+    if idist == 3:   # log/cos come from different libm builds
+        assert np.allclose(x, ref, rtol=1e-14, atol=1e-15)
+    else:
+        assert np.array_equal(x, ref)
+    assert seed == list(golden[f"larnv{idist}_seed"])
+
+
+@pytest.mark.parametrize("tag", ["tall", "sq", "wide", "one", "col", "sing"])
+def test_dgetrf2(golden, tag):
+    a = np.array(golden[f"getrf2_{tag}_a"], order="F")
+    if tag != "sing":
+        regen, _ = O.random_matrix(*a.shape, SEED)
+        assert np.array_equal(regen, a)      # generator parity with the golden inputs
+    ipiv, info = O.dgetrf2(a)
+    assert info == int(golden[f"getrf2_{tag}_info"])
+    assert np.array_equal(ipiv, golden[f"getrf2_{tag}_ipiv"])
+    assert relerr(a, golden[f"getrf2_{tag}_lu"]) < RTOL
+
+
+@pytest.mark.parametrize("nb", [1, 3, 20, 64])
+def test_dgetrf_blocked_equals_recursive_pivots(golden, nb):
+    a = np.array(golden["getrf2_tall_a"], order="F")
+    O.set_nb(getrf=nb)
+    try:
+        ipiv, info = O.dgetrf(a)
+    finally:
+        O.set_nb()
+    assert info == 0
+    assert np.array_equal(ipiv, golden["getrf2_tall_ipiv"])
+    assert relerr(a, golden["getrf2_tall_lu"]) < RTOL
+
+
+@pytest.mark.parametrize("uplo", ["L", "U"])
+def test_dpotrf2(golden, uplo):
+    a = np.array(golden[f"potrf2_{uplo}_a"], order="F")
+    a0 = a.copy(order="F")
+    info = O.dpotrf2(uplo, a)
+    assert info == int(golden[f"potrf2_{uplo}_info"]) == 0
+    tri = np.tril if uplo == "L" else np.triu
+    assert relerr(tri(a), tri(golden[f"potrf2_{uplo}_f"])) < RTOL
+    other = (lambda x: np.triu(x, 1)) if uplo == "L" else (lambda x: np.tril(x, -1))
+    assert np.array_equal(other(a), other(a0))          # opposite triangle untouched
+    for nb in (1, 3, 20):
+        b = a0.copy(order="F")
+        O.set_nb(potrf=nb)
+        try:
+            assert O.dpotrf(uplo, b) == 0
+        finally:
+            O.set_nb()
+        assert relerr(tri(b), tri(golden[f"potrf2_{uplo}_f"])) < RTOL
+
+
+def test_dpotrf2_not_spd(golden):
+    a = np.array(golden["potrf2_bad_a"], order="F")
+    assert O.dpotrf2("L", a) == int(golden["potrf2_bad_info"]) == 11
+    b = np.array(golden["potrf2_bad_a"], order="F")
+    O.set_nb(potrf=4)
+    try:
+        assert O.dpotrf("L", b) == 11
+    finally:
+        O.set_nb()
+
+
+def test_dpotrs(golden):
+    f = np.array(golden["potrf2_L_f"], order="F")
+    x = np.array(golden["potrs_b"], order="F")
+    assert O.dpotrs("L", f, x) == 0
+    assert relerr(x, golden["potrs_x"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["", "tiny_"])
+def test_dlarfg(golden, tag):
+    v = np.array(golden[f"larfg_{tag}in"])
+    x = v[1:].copy()
+    beta, tau = O.dlarfg(float(v[0]), x)
+    assert abs(beta - golden[f"larfg_{tag}beta"]) <= 4e-16 * abs(golden[f"larfg_{tag}beta"])
+    assert abs(tau - golden[f"larfg_{tag}tau"]) <= 1e-15
+    assert relerr(x, golden[f"larfg_{tag}v"]) < 1e-14
+
+
+@pytest.mark.parametrize("tag", ["tall", "sq", "wide"])
+def test_dgeqr2(golden, tag):
+    a = np.array(golden[f"geqrf_{tag}_a"], order="F")
+    tau, info = O.dgeqr2(a)
+    assert info == 0
+    assert relerr(a, golden[f"geqr2_{tag}_qr"]) < RTOL
+    assert relerr(tau, golden[f"geqr2_{tag}_tau"]) < RTOL
+
+
+@pytest.mark.parametrize("tag", ["tall", "sq", "wide", "big"])
+def test_dgeqrf(golden, tag):
+    a = np.array(golden[f"geqrf_{tag}_a"], order="F")
+    m, n = a.shape
+    tau, info, w1 = O.dgeqrf(a)
+    assert info == 0
+    assert relerr(a, golden[f"geqrf_{tag}_qr"]) < RTOL
+    assert relerr(tau, golden[f"geqrf_{tag}_tau"]) < RTOL
+    if tag == "big":
+        assert w1 == n * 32        # k=150 > NX=128: the blocked DLARFT/DLARFB path ran (IWS = N*NB)
+    res = O.dqrt01(np.array(golden[f"geqrf_{tag}_a"], order="F"), a, tau)
+    assert res[0] < O.THRESH and res[1] < O.THRESH
+
+
+def test_dgeqrf_small_blocks(golden):
+    """Force the blocked path (NB=8, NX=0) like TESTING/LIN does through xlaenv."""
+    a = np.array(golden["geqrf_tall_a"], order="F")
+    O.set_nb(geqrf=8, nx=0)
+    try:
+        tau, info, _ = O.dgeqrf(a)
+    finally:
+        O.set_nb()
+    assert relerr(a, golden["geqrf_tall_qr"]) < RTOL
+    assert relerr(tau, golden["geqrf_tall_tau"]) < RTOL
+
+
+def test_dlarft_dlarfb_dorgqr(golden):
+    qr = np.array(golden["geqrf_tall_qr"], order="F")
+    tau = np.array(golden["geqrf_tall_tau"])
+    t = O.dlarft(qr, tau)
+    assert relerr(np.triu(t), golden["larft_t"]) < RTOL
+    for trans in ("T", "N"):
+        c = np.array(golden["larfb_c_in"], order="F")
+        O.dlarfb("L", trans, qr, t, c)
+        assert relerr(c, golden[f"larfb_L{trans}_c"]) < RTOL
+    m, k = qr.shape
+    q = np.zeros((m, m), order="F")
+    q[:, :k] = np.tril(qr, -1)[:, :k]
+    assert O.dorgqr(q, tau, k) == 0
+    assert relerr(q, golden["orgqr_q"]) < RTOL
+    assert np.max(np.abs(q.T @ q - np.eye(m))) < 1e-13
+
+
+def test_dlarft_recursive_branch():
+    """k >= 64 takes the recursive Level-3 branch of dlarft.f:308-349; compare with the Level-2 one."""
+    a, _ = O.random_matrix(150, 80, SEED)
+    tau, info = O.dgeqr2(a)
+    t_rec = O.dlarft(a, tau)
+    t_l2 = O.fmat(80, 80)
+    import ctypes as C
+    O.lib().ora_dlarft_lvl2(C.c_char(b"F"), C.c_char(b"C"), 150, 80, O._d(a), 150, O._d(tau), O._d(t_l2), 80)
+    assert relerr(np.triu(t_rec), np.triu(t_l2)) < 1e-13
+
+
+def test_checkers_flag_bad_factorizations(golden):
+    a = np.array(golden["getrf2_sq_a"], order="F")
+    lu = np.array(golden["getrf2_sq_lu"], order="F")
+    ipiv = np.array(golden["getrf2_sq_ipiv"])
+    assert O.dget01(a, lu, ipiv) < 1.0
+    lu[5, 7] += 1e-6
+    assert O.dget01(a, lu, ipiv) > O.THRESH
+    s = np.array(golden["potrf2_L_a"], order="F")
+    f = np.array(golden["potrf2_L_f"], order="F")
+    assert O.dpot01("L", s, f) < 1.0
+    assert O.dpot01("U", s, np.array(golden["potrf2_U_f"], order="F")) < 1.0
+    f[20, 3] += 1e-6
+    assert O.dpot01("L", s, f) > O.THRESH
+
+
+def test_dgesv_solution_and_residuals():
+    n = 200
+    a, seed = O.random_matrix(n, n, SEED)
+    xact, _ = O.random_matrix(n, 2, seed)
+    b = np.asfortranarray(a @ xact)
+    lu = a.copy(order="F")
+    x = b.copy(order="F")
+    ipiv, info = O.dgesv(lu, x)
+    assert info == 0
+    assert O.dget01(a, lu, ipiv) < O.THRESH
+    assert O.dget02("N", a, x, b) < O.THRESH
+    rcond = 1.0 / np.linalg.cond(a, 1)
+    assert O.dget04(x, xact, rcond) < O.THRESH
+    xt = b.copy(order="F")
+    assert O.dgetrs("T", lu, ipiv, xt) == 0
+    assert O.dget02("T", a, xt, b) < O.THRESH
+
+
+def test_dposv_solution_and_residuals():
+    n = 150
+    s, seed = O.spd_matrix(n, SEED)
+    xact, _ = O.random_matrix(n, 3, seed)
+    b = np.asfortranarray(s @ xact)
+    for uplo in ("L", "U"):
+        f = s.copy(order="F")
+        x = b.copy(order="F")
+        assert O.dposv(uplo, f, x) == 0
+        assert O.dpot01(uplo, s, f) < O.THRESH
+        assert O.dpot02(uplo, s, x, b) < O.THRESH
+        assert np.max(np.abs(x - xact)) / np.max(np.abs(xact)) < 1e-12
