@@ -1,0 +1,83 @@
+/*
+ * lapack_b200.h -- C ABI of liblapack_b200.so (B200 / sm_100a implementation of LAPACK's blocked
+ * one-sided factorizations).  Three layers, all `extern "C"`, plain pointers and sizes:
+ *
+ *  1. lb200_*  : device-pointer API.  Every matrix/vector/IPIV/INFO pointer is a DEVICE pointer,
+ *                `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream.
+ *  2. Fortran-77 ABI symbols (dgetrf_, dpotrf_, dgeqrf_, ... see lapack_b200_f77.h): drop-in for the
+ *                reference's SRC/ and BLAS/SRC symbols; pointers may be host or device memory.
+ *  3. LAPACKE_* : drop-in for the reference's LAPACKE C entry points (lapack_b200_lapacke.h).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference tree).
+ */
+#ifndef LAPACK_B200_H
+#define LAPACK_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int lb200_version(void);
+int lb200_last_cuda_error(void);
+void lb200_clear_cuda_error(void);
+unsigned long long lb200_launch_count(void);      /* kernels launched by this library so far */
+void lb200_reset_launch_count(void);
+
+/* measured FP64 pipe peak (TFLOP/s): kind 0 = DMMA.8x8x4 issue rate, 1 = DFMA */
+double lb200_fp64_peak_tflops(void* stream, int kind, int warps_per_cta, int ctas_per_sm, int iters);
+
+/* tuning knobs (testing / benchmarking; defaults are chosen per problem size) */
+void lb200_set_gemm_config(int cfg);
+void lb200_set_getrf_params(int nb, int leaf, int lookahead);
+void lb200_set_potrf_params(int nb, int lookahead);
+void lb200_set_geqrf_params(int nb, int lookahead);
+
+/* BLAS/SRC/dgemm.f:187 DGEMM(TRANSA,TRANSB,M,N,K,ALPHA,A,LDA,B,LDB,BETA,C,LDC) */
+int lb200_dgemm(void* stream, char transa, char transb, int m, int n, int k, double alpha, const double* dA,
+                long long lda, const double* dB, long long ldb, double beta, double* dC, long long ldc);
+/* BLAS/SRC/dsyrk.f:168 DSYRK(UPLO,TRANS,N,K,ALPHA,A,LDA,BETA,C,LDC) */
+int lb200_dsyrk(void* stream, char uplo, char trans, int n, int k, double alpha, const double* dA, long long lda,
+                double beta, double* dC, long long ldc);
+/* BLAS/SRC/dtrsm.f:180 DTRSM(SIDE,UPLO,TRANSA,DIAG,M,N,ALPHA,A,LDA,B,LDB) */
+int lb200_dtrsm(void* stream, char side, char uplo, char trans, char diag, int m, int n, double alpha,
+                const double* dA, long long lda, double* dB, long long ldb);
+/* BLAS/SRC/dtrmm.f:176 DTRMM(SIDE,UPLO,TRANSA,DIAG,M,N,ALPHA,A,LDA,B,LDB) */
+int lb200_dtrmm(void* stream, char side, char uplo, char trans, char diag, int m, int n, double alpha,
+                const double* dA, long long lda, double* dB, long long ldb);
+/* SRC/dlaswp.f:112 DLASWP(N,A,LDA,K1,K2,IPIV,INCX); ipiv is a device array of 1-based rows */
+int lb200_dlaswp(void* stream, int n, double* dA, long long lda, int k1, int k2, const int* dipiv, int incx);
+
+/* SRC/dgetrf.f:105 DGETRF(M,N,A,LDA,IPIV,INFO); SRC/dgetrf2.f:112 */
+int lb200_dgetrf(void* stream, int m, int n, double* dA, long long lda, int* dipiv, int* dinfo);
+int lb200_dgetrf2(void* stream, int m, int n, double* dA, long long lda, int* dipiv, int* dinfo);
+/* SRC/dgetrs.f:118 DGETRS(TRANS,N,NRHS,A,LDA,IPIV,B,LDB,INFO) */
+int lb200_dgetrs(void* stream, char trans, int n, int nrhs, const double* dA, long long lda, const int* dipiv,
+                 double* dB, long long ldb);
+/* SRC/dpotrf.f:104 DPOTRF(UPLO,N,A,LDA,INFO); SRC/dpotrf2.f:105; SRC/dpotrs.f:107 */
+int lb200_dpotrf(void* stream, char uplo, int n, double* dA, long long lda, int* dinfo);
+int lb200_dpotrf2(void* stream, char uplo, int n, double* dA, long long lda, int* dinfo);
+int lb200_dpotrs(void* stream, char uplo, int n, int nrhs, const double* dA, long long lda, double* dB,
+                 long long ldb);
+/* SRC/dgeqrf.f:145 DGEQRF(M,N,A,LDA,TAU,WORK,LWORK,INFO) (device scratch replaces WORK); SRC/dgeqr2.f:127 */
+int lb200_dgeqrf(void* stream, int m, int n, double* dA, long long lda, double* dtau);
+int lb200_dgeqr2(void* stream, int m, int n, double* dA, long long lda, double* dtau);
+/* SRC/dlarft.f:160 DLARFT('F','C',N,K,V,LDV,TAU,T,LDT);  SRC/dlarfb.f:192 DLARFB(SIDE,TRANS,'F','C',...) */
+int lb200_dlarft(void* stream, int n, int k, const double* dV, long long ldv, const double* dtau, double* dT,
+                 long long ldt);
+int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const double* dV, long long ldv,
+                 const double* dT, long long ldt, double* dC, long long ldc);
+/* batched 32x32 (config C5b): matrices contiguous, stride 1024 doubles; ipiv 32 ints per matrix */
+int lb200_dgetrf_batched32(void* stream, long long batch, double* dA, int* dipiv, int* dinfo);
+int lb200_dpotrf_batched32(void* stream, char uplo, long long batch, double* dA, int* dinfo);
+
+/* SRC/dlarnv.f:97 + SRC/dlaruv.f:95: fill A (m x n, column by column) with U(-1,1) from the 48-bit LCG,
+ * starting `stream_offset` draws after `iseed` (O(log n) jump-ahead, bit-identical to DLARNV(2)). */
+int lb200_dlarnv_matrix(void* stream, const int iseed[4], long long stream_offset, int m, int n, double* dA,
+                        long long lda);
+int lb200_make_spd(void* stream, int n, double* dA, long long lda, double shift); /* A := (A+A')/2 + shift*I */
+int lb200_dlacpy(void* stream, char uplo, int m, int n, const double* dA, long long lda, double* dB, long long ldb);
+int lb200_transpose(void* stream, int m, int n, const double* dA, long long lda, double* dB, long long ldb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,528 @@
+// fortran_abi.cu -- the drop-in boundary: Fortran-77 ABI symbols of the reference's LU / Cholesky / QR
+// hot path and the Level-3 BLAS under it (declared in include/lapack_b200_f77.h).
+//
+// Contract (reference LAPACKE/include/lapack.h): every argument by reference,
+// INTEGER = 32-bit int, CHARACTER*1 = char* plus a hidden trailing size_t length (only the first character
+// is read, case-insensitively like BLAS/SRC/lsame.f), column-major, in place, synchronous on return.
+// Argument checks, their order, the XERBLA name/position and quick returns are the reference's
+// (SRC/dgetrf.f:144-160, dgetrs.f:158-180, dgesv.f:148-162, dpotrf.f:145-162, dpotrs.f:147-166,
+// dposv.f:160-176, dgeqrf.f:180-212, dgeqr2.f:150-162, BLAS/SRC/dgemm.f:253-299, dtrsm.f:230-260,
+// dsyrk.f:210-240).  Errors go through the EXTERNAL symbol xerbla_ so that a caller's own XERBLA
+// (e.g. TESTING/LIN/xerbla.f) intercepts them.
+//
+// Pointers may be host or device memory (cudaPointerGetAttributes).  Host operands are staged through
+// device scratch on an internal stream (pinned host memory gets full-rate async DMA); device operands are
+// used in place on the legacy default stream.  There is no CPU fallback: without a usable CUDA device the
+// routines report INFO = -1001 - cudaError and return.
+#include "lb_internal.h"
+#include "../../include/lapack_b200_f77.h"
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace lb {
+void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx);
+}
+
+// ------------------------------------------------------------------------------------------------ XERBLA
+static int g_xerbla_mode = -1;        // 0 stop (reference), 1 print+return, 2 silent (record only)
+static char g_xerbla_name[33] = {0};
+static int g_xerbla_info = 0;
+static int g_xerbla_count = 0;
+
+extern "C" void lb200_set_xerbla_mode(int mode) { g_xerbla_mode = mode; }
+extern "C" int lb200_last_xerbla(char* name_out, int* info_out) {
+    if (name_out) strcpy(name_out, g_xerbla_name);
+    if (info_out) *info_out = g_xerbla_info;
+    return g_xerbla_count;
+}
+extern "C" void lb200_clear_xerbla(void) { g_xerbla_count = 0; g_xerbla_info = 0; g_xerbla_name[0] = 0; }
+
+// BLAS/SRC/xerbla.f:59-83.  Weak: a XERBLA supplied by the application or test harness wins.
+extern "C" __attribute__((weak)) void xerbla_(const char* srname, const int* info, size_t srname_len) {
+    size_t len = srname_len;
+    if (len == 0 || len > 32) len = strnlen(srname, 32);
+    memcpy(g_xerbla_name, srname, len);
+    g_xerbla_name[len] = 0;
+    while (len > 0 && g_xerbla_name[len - 1] == ' ') g_xerbla_name[--len] = 0;   // LEN_TRIM
+    g_xerbla_info = *info;
+    g_xerbla_count++;
+    if (g_xerbla_mode < 0) {
+        const char* e = getenv("LAPACK_B200_XERBLA");
+        g_xerbla_mode = (e && !strcmp(e, "return")) ? 1 : (e && !strcmp(e, "silent")) ? 2 : 0;
+    }
+    if (g_xerbla_mode != 2)
+        printf(" ** On entry to %s parameter number %2d had an illegal value\n", g_xerbla_name, *info);
+    if (g_xerbla_mode == 0) {
+        fflush(stdout);
+        exit(0);   // Fortran STOP
+    }
+}
+
+static void call_xerbla(const char* name6, int pos) { xerbla_(name6, &pos, strlen(name6)); }
+
+// BLAS/SRC/lsame.f
+extern "C" int lsame_(const char* ca, const char* cb, size_t, size_t) {
+    char a = *ca, b = *cb;
+    if (a >= 'a' && a <= 'z') a = (char)(a - 32);
+    if (b >= 'a' && b <= 'z') b = (char)(b - 32);
+    return a == b;
+}
+static inline bool same(const char* p, char u) { char c = *p; if (c >= 'a' && c <= 'z') c = (char)(c - 32); return c == u; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------ staging
+namespace {
+
+enum PtrKind { PK_HOST = 0, PK_PINNED = 1, PK_DEVICE = 2 };
+
+PtrKind ptr_kind(const void* p) {
+    cudaPointerAttributes at;
+    if (!p) return PK_HOST;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return PK_HOST; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return PK_DEVICE;
+    if (at.type == cudaMemoryTypeHost) return PK_PINNED;
+    return PK_HOST;
+}
+
+std::mutex g_abi_mutex;     // one Fortran-ABI call at a time (the reference is re-entrant; we serialise)
+
+cudaStream_t host_stream() {
+    static cudaStream_t s = nullptr;
+    if (!s) LB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    return s;
+}
+
+bool device_ok(int* info) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        fprintf(stderr, "lapack_b200: no usable CUDA device (%s); this library has no CPU fallback\n",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        if (info) *info = -1001 - (int)e;
+        return false;
+    }
+    return true;
+}
+
+// Call context: picks the stream (legacy default stream if any operand is device memory, else the internal
+// stream), owns the staged copies, copies results back and synchronises in finish().
+struct Ctx {
+    cudaStream_t s = nullptr;
+    bool any_device = false;
+    struct Item { void* dev; void* host; size_t width_bytes; size_t rows_or_cols; size_t hpitch; size_t dpitch; bool out; };
+    std::vector<Item> items;
+
+    void scan(std::initializer_list<const void*> ptrs) {
+        for (const void* p : ptrs) if (p && ptr_kind(p) == PK_DEVICE) any_device = true;
+        s = any_device ? (cudaStream_t)0 : host_stream();
+    }
+    // column-major rows x cols matrix with leading dimension ld
+    double* mat(const double* p, int rows, int cols, lb::i64 ld, bool in, bool out, lb::i64* ld_dev) {
+        if (rows <= 0 || cols <= 0) { *ld_dev = imax(1, rows); return const_cast<double*>(p); }
+        if (ptr_kind(p) == PK_DEVICE) { *ld_dev = ld; return const_cast<double*>(p); }
+        lb::i64 ldd = ((lb::i64)rows + 1) & ~1LL;
+        double* d = (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * cols);
+        if (in) LB_CUDA_CHECK(cudaMemcpy2DAsync(d, ldd * 8, p, ld * 8, (size_t)rows * 8, cols, cudaMemcpyHostToDevice, s));
+        items.push_back({d, (void*)p, (size_t)rows * 8, (size_t)cols, (size_t)ld * 8, (size_t)ldd * 8, out});
+        *ld_dev = ldd;
+        return d;
+    }
+    template <typename T>
+    T* vec(const T* p, size_t n, bool in, bool out) {
+        if (n == 0) return const_cast<T*>(p);
+        if (ptr_kind(p) == PK_DEVICE) return const_cast<T*>(p);
+        T* d = (T*)lb::ws_alloc(s, sizeof(T) * n);
+        if (in) LB_CUDA_CHECK(cudaMemcpyAsync(d, p, sizeof(T) * n, cudaMemcpyHostToDevice, s));
+        items.push_back({d, (void*)p, sizeof(T) * n, 1, sizeof(T) * n, sizeof(T) * n, out});
+        return d;
+    }
+    int* dev_info() {
+        int* d = (int*)lb::ws_alloc(s, 64);
+        LB_CUDA_CHECK(cudaMemsetAsync(d, 0, 64, s));
+        return d;
+    }
+    // copies outputs back, frees scratch, synchronises; returns the device INFO word if given
+    int finish(int* dinfo = nullptr) {
+        int hinfo = 0;
+        for (auto& it : items)
+            if (it.out)
+                LB_CUDA_CHECK(cudaMemcpy2DAsync(it.host, it.hpitch, it.dev, it.dpitch, it.width_bytes, it.rows_or_cols,
+                                                cudaMemcpyDeviceToHost, s));
+        if (dinfo) LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+        for (auto& it : items) lb::ws_free(s, it.dev);
+        if (dinfo) lb::ws_free(s, dinfo);
+        LB_CUDA_CHECK(cudaStreamSynchronize(s));
+        int e = lb::last_cuda_error();
+        if (e) { lb::clear_cuda_error(); return -1001 - e; }
+        return hinfo;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ================================================================================================ BLAS 3
+void dgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const double* alpha,
+            const double* A, const int* lda, const double* B, const int* ldb, const double* beta, double* C,
+            const int* ldc, size_t, size_t) {
+    const bool nota = same(transa, 'N'), notb = same(transb, 'N');
+    const int nrowa = nota ? *m : *k, nrowb = notb ? *k : *n;
+    int info = 0;
+    if (!nota && !same(transa, 'C') && !same(transa, 'T')) info = 1;
+    else if (!notb && !same(transb, 'C') && !same(transb, 'T')) info = 2;
+    else if (*m < 0) info = 3;
+    else if (*n < 0) info = 4;
+    else if (*k < 0) info = 5;
+    else if (*lda < imax(1, nrowa)) info = 8;
+    else if (*ldb < imax(1, nrowb)) info = 10;
+    else if (*ldc < imax(1, *m)) info = 13;
+    if (info) { call_xerbla("DGEMM ", info); return; }
+    if (*m == 0 || *n == 0 || ((*alpha == 0.0 || *k == 0) && *beta == 1.0)) return;
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, B, C});
+    lb::i64 la, lbb, lc;
+    const bool need_ab = (*alpha != 0.0 && *k > 0);
+    const int acols = nota ? *k : *m, bcols = notb ? *n : *k;
+    const double* dA = need_ab ? c.mat(A, nrowa, acols, *lda, true, false, &la) : A;
+    const double* dB = need_ab ? c.mat(B, nrowb, bcols, *ldb, true, false, &lbb) : B;
+    if (!need_ab) { la = *lda; lbb = *ldb; }
+    double* dC = c.mat(C, *m, *n, *ldc, *beta != 0.0, true, &lc);
+    lb::gemm(c.s, nota ? 'N' : 'T', notb ? 'N' : 'T', *m, *n, need_ab ? *k : 0, *alpha, dA, la, dB, lbb, *beta, dC, lc, 0);
+    c.finish();
+}
+
+void dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* A,
+            const int* lda, const double* beta, double* C, const int* ldc, size_t, size_t) {
+    const bool notr = same(trans, 'N');
+    const int nrowa = notr ? *n : *k;
+    const bool upper = same(uplo, 'U');
+    int info = 0;
+    if (!upper && !same(uplo, 'L')) info = 1;
+    else if (!notr && !same(trans, 'T') && !same(trans, 'C')) info = 2;
+    else if (*n < 0) info = 3;
+    else if (*k < 0) info = 4;
+    else if (*lda < imax(1, nrowa)) info = 7;
+    else if (*ldc < imax(1, *n)) info = 10;
+    if (info) { call_xerbla("DSYRK ", info); return; }
+    if (*n == 0 || ((*alpha == 0.0 || *k == 0) && *beta == 1.0)) return;
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, C});
+    lb::i64 la = *lda, lc;
+    const bool need_a = (*alpha != 0.0 && *k > 0);
+    const double* dA = need_a ? c.mat(A, nrowa, notr ? *k : *n, *lda, true, false, &la) : A;
+    double* dC = c.mat(C, *n, *n, *ldc, true, true, &lc);   // the untouched triangle travels both ways unchanged
+    lb::syrk(c.s, upper ? 'U' : 'L', notr ? 'N' : 'T', *n, need_a ? *k : 0, *alpha, dA, la, *beta, dC, lc);
+    c.finish();
+}
+
+static void trxm_common(bool solve, const char* side, const char* uplo, const char* transa, const char* diag, const int* m,
+                        const int* n, const double* alpha, const double* A, const int* lda, double* B, const int* ldb) {
+    const bool lside = same(side, 'L');
+    const int nrowa = lside ? *m : *n;
+    int info = 0;
+    if (!lside && !same(side, 'R')) info = 1;
+    else if (!same(uplo, 'U') && !same(uplo, 'L')) info = 2;
+    else if (!same(transa, 'N') && !same(transa, 'T') && !same(transa, 'C')) info = 3;
+    else if (!same(diag, 'U') && !same(diag, 'N')) info = 4;
+    else if (*m < 0) info = 5;
+    else if (*n < 0) info = 6;
+    else if (*lda < imax(1, nrowa)) info = 9;
+    else if (*ldb < imax(1, *m)) info = 11;
+    if (info) { call_xerbla(solve ? "DTRSM " : "DTRMM ", info); return; }
+    if (*m == 0 || *n == 0) return;
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, B});
+    lb::i64 la = *lda, lbb;
+    const double* dA = (*alpha != 0.0) ? c.mat(A, nrowa, nrowa, *lda, true, false, &la) : A;
+    double* dB = c.mat(B, *m, *n, *ldb, *alpha != 0.0, true, &lbb);
+    const char tr = same(transa, 'N') ? 'N' : 'T';
+    if (solve) lb::trsm(c.s, lside ? 'L' : 'R', same(uplo, 'U') ? 'U' : 'L', tr, same(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, dA, la, dB, lbb);
+    else lb::trmm(c.s, lside ? 'L' : 'R', same(uplo, 'U') ? 'U' : 'L', tr, same(diag, 'U') ? 'U' : 'N', *m, *n, *alpha, dA, la, dB, lbb);
+    c.finish();
+}
+void dtrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+            const double* alpha, const double* A, const int* lda, double* B, const int* ldb, size_t, size_t, size_t, size_t) {
+    trxm_common(true, side, uplo, transa, diag, m, n, alpha, A, lda, B, ldb);
+}
+void dtrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+            const double* alpha, const double* A, const int* lda, double* B, const int* ldb, size_t, size_t, size_t, size_t) {
+    trxm_common(false, side, uplo, transa, diag, m, n, alpha, A, lda, B, ldb);
+}
+
+// ================================================================================================ LU
+static void getrf_common(bool recursive, const int* m, const int* n, double* A, const int* lda, int* ipiv, int* info) {
+    *info = 0;
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *m)) *info = -4;
+    if (*info != 0) { call_xerbla(recursive ? "DGETRF2" : "DGETRF", -*info); return; }
+    if (*m == 0 || *n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, ipiv});
+    lb::i64 la;
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    int* dp = c.vec<int>(ipiv, (size_t)imin(*m, *n), false, true);
+    int* dinfo = c.dev_info();
+    if (recursive) lb::getrf2(c.s, *m, *n, dA, la, dp, dinfo);
+    else lb::getrf(c.s, *m, *n, dA, la, dp, dinfo);
+    *info = c.finish(dinfo);
+}
+void dgetrf_(const int* m, const int* n, double* A, const int* lda, int* ipiv, int* info) {
+    getrf_common(false, m, n, A, lda, ipiv, info);
+}
+void dgetrf2_(const int* m, const int* n, double* A, const int* lda, int* ipiv, int* info) {
+    getrf_common(true, m, n, A, lda, ipiv, info);
+}
+
+// SRC/dlaswp.f:112 -- no argument checking, no INFO
+void dlaswp_(const int* n, double* A, const int* lda, const int* k1, const int* k2, const int* ipiv, const int* incx) {
+    if (*n <= 0 || *incx == 0 || *k2 < *k1) return;
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    // rows touched: K1..K2 and every pivot target; pivots are read at positions K1..K1+(K2-K1)*|INCX|
+    const int ainc = *incx > 0 ? *incx : -*incx;
+    const size_t npiv = (size_t)(*k1 - 1) + (size_t)(*k2 - *k1) * ainc + 1;
+    Ctx c; c.scan({A, ipiv});
+    int rows = *k2;
+    std::vector<int> hp;
+    if (ptr_kind(ipiv) != PK_DEVICE) {
+        for (int i = *k1; i <= *k2; ++i) { int v = ipiv[(*k1 - 1) + (size_t)(i - *k1) * ainc]; if (v > rows) rows = v; }
+    } else {
+        hp.resize(npiv);
+        cudaMemcpy(hp.data(), ipiv, npiv * sizeof(int), cudaMemcpyDeviceToHost);
+        for (int i = *k1; i <= *k2; ++i) { int v = hp[(*k1 - 1) + (size_t)(i - *k1) * ainc]; if (v > rows) rows = v; }
+    }
+    if (rows > *lda) rows = *lda;
+    lb::i64 la;
+    double* dA = c.mat(A, rows, *n, *lda, true, true, &la);
+    int* dp = c.vec<int>(ipiv, npiv, true, false);
+    lb::laswp(c.s, *n, dA, la, *k1, *k2, dp, *incx);
+    c.finish();
+}
+
+void dgetrs_(const char* trans, const int* n, const int* nrhs, const double* A, const int* lda, const int* ipiv, double* B,
+             const int* ldb, int* info, size_t) {
+    *info = 0;
+    const bool notran = same(trans, 'N');
+    if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nrhs < 0) *info = -3;
+    else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldb < imax(1, *n)) *info = -8;
+    if (*info != 0) { call_xerbla("DGETRS", -*info); return; }
+    if (*n == 0 || *nrhs == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, ipiv, B});
+    lb::i64 la, lbb;
+    const double* dA = c.mat(A, *n, *n, *lda, true, false, &la);
+    const int* dp = c.vec<int>(ipiv, (size_t)*n, true, false);
+    double* dB = c.mat(B, *n, *nrhs, *ldb, true, true, &lbb);
+    lb::getrs(c.s, notran ? 'N' : 'T', *n, *nrhs, dA, la, dp, dB, lbb);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+void dgesv_(const int* n, const int* nrhs, double* A, const int* lda, int* ipiv, double* B, const int* ldb, int* info) {
+    *info = 0;
+    if (*n < 0) *info = -1;
+    else if (*nrhs < 0) *info = -2;
+    else if (*lda < imax(1, *n)) *info = -4;
+    else if (*ldb < imax(1, *n)) *info = -7;
+    if (*info != 0) { call_xerbla("DGESV ", -*info); return; }
+    if (*n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, ipiv, B});
+    lb::i64 la, lbb;
+    double* dA = c.mat(A, *n, *n, *lda, true, true, &la);
+    int* dp = c.vec<int>(ipiv, (size_t)*n, false, true);
+    double* dB = c.mat(B, *n, *nrhs, *ldb, true, true, &lbb);
+    int* dinfo = c.dev_info();
+    lb::getrf(c.s, *n, *n, dA, la, dp, dinfo);
+    // DGESV solves only if INFO == 0 (dgesv.f:166); the factorization's INFO is needed on the host first
+    int hinfo = 0;
+    LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c.s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    if (hinfo == 0 && *nrhs > 0) lb::getrs(c.s, 'N', *n, *nrhs, dA, la, dp, dB, lbb);
+    else if (hinfo != 0) { for (auto& it : c.items) if (it.dev == dB) it.out = false; }
+    int r = c.finish(dinfo);
+    *info = r;
+}
+
+// ================================================================================================ Cholesky
+static void potrf_common(bool recursive, const char* uplo, const int* n, double* A, const int* lda, int* info) {
+    *info = 0;
+    const bool upper = same(uplo, 'U');
+    if (!upper && !same(uplo, 'L')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *n)) *info = -4;
+    if (*info != 0) { call_xerbla(recursive ? "DPOTRF2" : "DPOTRF", -*info); return; }
+    if (*n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A});
+    lb::i64 la;
+    double* dA = c.mat(A, *n, *n, *lda, true, true, &la);
+    int* dinfo = c.dev_info();
+    if (recursive) lb::potrf2(c.s, upper ? 'U' : 'L', *n, dA, la, dinfo);
+    else lb::potrf(c.s, upper ? 'U' : 'L', *n, dA, la, dinfo);
+    *info = c.finish(dinfo);
+}
+void dpotrf_(const char* uplo, const int* n, double* A, const int* lda, int* info, size_t) { potrf_common(false, uplo, n, A, lda, info); }
+void dpotrf2_(const char* uplo, const int* n, double* A, const int* lda, int* info, size_t) { potrf_common(true, uplo, n, A, lda, info); }
+
+void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* A, const int* lda, double* B, const int* ldb,
+             int* info, size_t) {
+    *info = 0;
+    const bool upper = same(uplo, 'U');
+    if (!upper && !same(uplo, 'L')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nrhs < 0) *info = -3;
+    else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldb < imax(1, *n)) *info = -7;
+    if (*info != 0) { call_xerbla("DPOTRS", -*info); return; }
+    if (*n == 0 || *nrhs == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, B});
+    lb::i64 la, lbb;
+    const double* dA = c.mat(A, *n, *n, *lda, true, false, &la);
+    double* dB = c.mat(B, *n, *nrhs, *ldb, true, true, &lbb);
+    lb::potrs(c.s, upper ? 'U' : 'L', *n, *nrhs, dA, la, dB, lbb);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const int* lda, double* B, const int* ldb,
+            int* info, size_t) {
+    *info = 0;
+    const bool upper = same(uplo, 'U');
+    if (!upper && !same(uplo, 'L')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nrhs < 0) *info = -3;
+    else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldb < imax(1, *n)) *info = -7;
+    if (*info != 0) { call_xerbla("DPOSV ", -*info); return; }
+    if (*n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, B});
+    lb::i64 la, lbb;
+    double* dA = c.mat(A, *n, *n, *lda, true, true, &la);
+    double* dB = c.mat(B, *n, *nrhs, *ldb, true, true, &lbb);
+    int* dinfo = c.dev_info();
+    lb::potrf(c.s, upper ? 'U' : 'L', *n, dA, la, dinfo);
+    int hinfo = 0;
+    LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c.s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    if (hinfo == 0 && *nrhs > 0) lb::potrs(c.s, upper ? 'U' : 'L', *n, *nrhs, dA, la, dB, lbb);   // dposv.f:180-183
+    else if (hinfo != 0) { for (auto& it : c.items) if (it.dev == dB) it.out = false; }
+    *info = c.finish(dinfo);
+}
+
+// ================================================================================================ QR
+// Reference block sizes that only matter for the WORK(1) protocol (SRC/ilaenv.f:296-302, 623-630)
+static const int REF_NB_GEQRF = 32, REF_NX_GEQRF = 128;
+
+void dgeqrf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info) {
+    const int k = imin(*m, *n);
+    *info = 0;
+    const bool lquery = (*lwork == -1);
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *m)) *info = -4;
+    else if (!lquery) { if (*lwork <= 0 || (*m > 0 && *lwork < imax(1, *n))) *info = -7; }
+    if (*info != 0) { call_xerbla("DGEQRF", -*info); return; }
+    if (lquery) { work[0] = (k == 0) ? 1.0 : (double)*n * REF_NB_GEQRF; return; }    // dgeqrf.f:197-204
+    if (k == 0) { work[0] = 1.0; return; }
+    if (!device_ok(info)) return;
+    {
+        std::lock_guard<std::mutex> lock(g_abi_mutex);
+        Ctx c; c.scan({A, tau});
+        lb::i64 la;
+        double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+        double* dt = c.vec<double>(tau, (size_t)k, false, true);
+        lb::geqrf(c.s, *m, *n, dA, la, dt);
+        int r = c.finish();
+        if (r) *info = r;
+    }
+    // WORK(1) = IWS as the reference would report it (dgeqrf.f:216-236,278); device scratch replaces WORK
+    int iws = *n;
+    if (REF_NB_GEQRF > 1 && REF_NB_GEQRF < k && REF_NX_GEQRF < k) iws = *n * REF_NB_GEQRF;
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)iws;
+}
+
+void dgeqr2_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, int* info) {
+    (void)work;
+    *info = 0;
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *m)) *info = -4;
+    if (*info != 0) { call_xerbla("DGEQR2", -*info); return; }
+    const int k = imin(*m, *n);
+    if (k == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, tau});
+    lb::i64 la;
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    double* dt = c.vec<double>(tau, (size_t)k, false, true);
+    lb::geqr2(c.s, *m, *n, dA, la, dt);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+// SRC/dlarft.f:160 -- DIRECT='F', STOREV='C' (the QR case) is implemented; no argument checking, no INFO
+void dlarft_(const char* direct, const char* storev, const int* n, const int* k, const double* V, const int* ldv,
+             const double* tau, double* T, const int* ldt, size_t, size_t) {
+    if (*n == 0 || *k == 0) return;
+    if (!same(direct, 'F') || !same(storev, 'C')) {
+        fprintf(stderr, "lapack_b200: DLARFT supports DIRECT='F', STOREV='C' only (QR path)\n");
+        call_xerbla("DLARFT", same(direct, 'F') ? 2 : 1);
+        return;
+    }
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({V, tau, T});
+    lb::i64 lv, lt;
+    const double* dV = c.mat(V, *n, *k, *ldv, true, false, &lv);
+    const double* dtau = c.vec<double>(tau, (size_t)*k, true, false);
+    double* dT = c.mat(T, *k, *k, *ldt, true, true, &lt);   // strictly lower part travels unchanged
+    lb::larft(c.s, *n, *k, dV, lv, dtau, dT, lt);
+    c.finish();
+}
+
+// SRC/dlarfb.f:192 -- DIRECT='F', STOREV='C'; WORK is not used (device scratch)
+void dlarfb_(const char* side, const char* trans, const char* direct, const char* storev, const int* m, const int* n,
+             const int* k, const double* V, const int* ldv, const double* T, const int* ldt, double* C, const int* ldc,
+             double* work, const int* ldwork, size_t, size_t, size_t, size_t) {
+    (void)work; (void)ldwork;
+    if (*m <= 0 || *n <= 0) return;
+    if (!same(direct, 'F') || !same(storev, 'C')) {
+        fprintf(stderr, "lapack_b200: DLARFB supports DIRECT='F', STOREV='C' only (QR path)\n");
+        call_xerbla("DLARFB", same(direct, 'F') ? 4 : 3);
+        return;
+    }
+    if (*k <= 0) return;
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({V, T, C});
+    lb::i64 lv, lt, lc;
+    const bool left = same(side, 'L');
+    const double* dV = c.mat(V, left ? *m : *n, *k, *ldv, true, false, &lv);
+    const double* dT = c.mat(T, *k, *k, *ldt, true, false, &lt);
+    double* dC = c.mat(C, *m, *n, *ldc, true, true, &lc);
+    lb::larfb(c.s, left ? 'L' : 'R', same(trans, 'N') ? 'N' : 'T', *m, *n, *k, dV, lv, dT, lt, dC, lc);
+    c.finish();
+}
+
+}  // extern "C"

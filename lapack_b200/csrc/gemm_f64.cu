@@ -1,0 +1,404 @@
+// gemm_f64.cu -- FP64 tensor-core GEMM / SYRK for sm_100a.
+//
+// Replaces the reference triple loops BLAS/SRC/dgemm.f:322-383 and dsyrk.f:278-355 on the trailing
+// updates of DGETRF (SRC/dgetrf.f:212), DPOTRF (SRC/dpotrf.f:216,225; VARIANTS/cholesky/RL) and DLARFB
+// (SRC/dlarfb.f:270,287).
+//
+// Hardware mapping.  On sm_100a the FP64 tensor pipe is only reachable through the warp-level
+// `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4); tcgen05 has no f64 kind.  Each warp owns a 64(m) x 32(n)
+// block of C held in registers (64 doubles/thread) and issues 32 independent DMMAs per k-step of 4.
+// The MMA is issued "transposed" (first operand = op(B) fragment, second = op(A) fragment) so that
+// every thread ends up with two consecutive rows of one column of C, i.e. a 16-byte column-major store.
+// Operand tiles are staged global->shared by a multi-stage cp.async (LDGSTS) ring; the shared layouts
+// are padded (+4 doubles) so that the 8-byte fragment loads are bank-conflict free.
+//
+// Roofline: 2*M*N*K flops per launch against the FP64 DMMA peak; minimum HBM traffic
+// 8*(2*M*N + M*K + K*N) bytes.
+#include "lb_internal.h"
+
+namespace lb {
+
+unsigned long long g_launches = 0;
+
+struct GemmParams {
+    int M, N, K;
+    double alpha, beta;
+    const double* A; i64 lda;
+    const double* B; i64 ldb;
+    double* C; i64 ldc;
+    int tri;              // 0 full, 1 lower, 2 upper
+    int tiles_m, tiles_n;
+    int kchunk;           // split-K: blockIdx.y owns k in [y*kchunk, (y+1)*kchunk); C advances by c_zstride
+    i64 c_zstride;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// D(8x8) += X(8x4,row) * Y(4x8,col); thread t supplies X[t/4][t%4], Y[t%4][t/4], holds D[t/4][2(t%4)+{0,1}].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double x, double y) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(x), "d"(y));
+}
+
+constexpr int BK = 16;
+constexpr int PAD = 4;
+
+// Shared-memory tile of one operand: EXT = extent along m (or n), BK along k.
+//   K-major  (KMAJ=true):  element (e,k) at e*(BK+PAD) + k      (k contiguous in global memory)
+//   MN-major (KMAJ=false): element (e,k) at k*(EXT+PAD) + e      (e contiguous in global memory)
+template <int EXT, bool KMAJ>
+struct TileLayout {
+    static constexpr int ELEMS = KMAJ ? EXT * (BK + PAD) : BK * (EXT + PAD);
+    __device__ static __forceinline__ int off(int e, int k) { return KMAJ ? e * (BK + PAD) + k : k * (EXT + PAD) + e; }
+};
+
+// Per-thread state for the cp.async copies of one operand tile.  All address arithmetic that does not
+// depend on the k-tile index is done once in init(); issue() only adds the k offset and clamps at the K
+// edge (zero fill), so the steady-state loop spends its issue slots on LDS/DMMA.
+//   g points at element (e=0,k=0) of the whole operand; e0 = tile origin, elim/klim = operand extents.
+template <int EXT, bool KMAJ, bool AL16, int NTHREADS>
+struct TileLoader {
+    static constexpr int N = AL16 ? (EXT * BK / 2) / NTHREADS : (EXT * BK) / NTHREADS;
+    static_assert((AL16 ? (EXT * BK / 2) : (EXT * BK)) % NTHREADS == 0, "tile/thread mismatch");
+    const double* gp[N];   // global address of the chunk for k-tile 0 (nullptr-safe: clamped to g)
+    int so[N];             // shared offset (doubles) inside the stage
+    int ebytes[N];         // bytes available along e (AL16 && !KMAJ), or 0/full validity flag
+    int kloc[N];           // k index of the chunk inside the tile
+    i64 kstep;             // pointer increment per k-tile (doubles)
+    const double* g0;
+
+    __device__ __forceinline__ void init(const double* __restrict__ g, i64 ld, int e0, int elim, int tid) {
+        g0 = g;
+        kstep = KMAJ ? (i64)BK : (i64)BK * ld;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            int idx = tid + i * NTHREADS;
+            int e, k;
+            if (AL16) {
+                if (KMAJ) { e = idx / (BK / 2); k = 2 * (idx % (BK / 2)); }
+                else { k = idx / (EXT / 2); e = 2 * (idx % (EXT / 2)); }
+            } else {
+                if (KMAJ) { e = idx / BK; k = idx % BK; }
+                else { k = idx / EXT; e = idx % EXT; }
+            }
+            int ge = e0 + e;
+            kloc[i] = k;
+            so[i] = KMAJ ? e * (BK + PAD) + k : k * (EXT + PAD) + e;
+            int rem = elim - ge;
+            if (AL16 && !KMAJ) ebytes[i] = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+            else ebytes[i] = rem >= 1 ? (AL16 ? 16 : 8) : 0;
+            gp[i] = ebytes[i] ? (KMAJ ? g + (i64)ge * ld + k : g + (i64)k * ld + ge) : g;
+        }
+    }
+    __device__ __forceinline__ void issue(double* sm, int kt, int klim) {
+        const int krem = klim - kt * BK;      // valid k's left from the start of this tile
+        const i64 koff = (i64)kt * kstep;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            int bytes;
+            if (AL16 && KMAJ) {
+                int r = krem - kloc[i];
+                bytes = ebytes[i] ? (r >= 2 ? 16 : (r == 1 ? 8 : 0)) : 0;
+            } else {
+                bytes = (kloc[i] < krem) ? ebytes[i] : 0;
+            }
+            const double* src = bytes ? gp[i] + koff : g0;
+            if (AL16) cp_async16(sm + so[i], src, bytes);
+            else cp_async8(sm + so[i], src, bytes);
+        }
+    }
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, bool AL16, int STAGES>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, (WARPS_M * WARPS_N <= 4) ? 2 : 1)
+    gemm_f64_dmma_kernel(GemmParams p) {
+    constexpr int NTHREADS = WARPS_M * WARPS_N * 32;
+    constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
+    constexpr int MT = WM / 8, NT = WN / 8;
+    using LA = TileLayout<BM, A_KMAJ>;
+    using LB = TileLayout<BN, B_KMAJ>;
+    constexpr int STAGE_ELEMS = LA::ELEMS + LB::ELEMS;
+
+    extern __shared__ __align__(16) double smem[];
+
+    // grouped rasterisation: 16 tile-rows at a time so that a wave of CTAs covers a squarish patch of C
+    constexpr int GROUP = 16;
+    int pid = blockIdx.x;
+    int width = GROUP * p.tiles_n;
+    int group_id = pid / width;
+    int first_m = group_id * GROUP;
+    int gsz = min(p.tiles_m - first_m, GROUP);
+    int pid_m = first_m + (pid % width) % gsz;
+    int pid_n = (pid % width) / gsz;
+    const int m0 = pid_m * BM, n0 = pid_n * BN;
+    if (p.tri == 1 && m0 + BM - 1 < n0) return;       // tile strictly above the diagonal
+    if (p.tri == 2 && n0 + BN - 1 < m0) return;       // tile strictly below the diagonal
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp_m = warp % WARPS_M, warp_n = warp / WARPS_M;
+    const int g4 = lane >> 2, t4 = lane & 3;
+
+    // split-K slice owned by this CTA (gridDim.y == 1 and kchunk == K for an ordinary launch)
+    {
+        const int kb = blockIdx.y * p.kchunk;
+        p.A += A_KMAJ ? (i64)kb : (i64)kb * p.lda;
+        p.B += B_KMAJ ? (i64)kb : (i64)kb * p.ldb;
+        p.C += (i64)blockIdx.y * p.c_zstride;
+        p.K = min(p.K - kb, p.kchunk);
+    }
+
+    // pull the C tile towards L2 while the main loop runs (the epilogue is a read-modify-write)
+    if (p.beta != 0.0) {
+        constexpr int LINES_PER_COL = BM / 16;
+        for (int l = tid; l < BN * LINES_PER_COL; l += NTHREADS) {
+            int n = n0 + l / LINES_PER_COL, m = m0 + (l % LINES_PER_COL) * 16;
+            if (n < p.N && m < p.M) {
+                const double* ptr = p.C + (i64)n * p.ldc + m;
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+            }
+        }
+    }
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int KT = (p.K + BK - 1) / BK;
+    TileLoader<BM, A_KMAJ, AL16, NTHREADS> ldA;
+    TileLoader<BN, B_KMAJ, AL16, NTHREADS> ldB;
+    ldA.init(p.A, p.lda, m0, p.M, tid);
+    ldB.init(p.B, p.ldb, n0, p.N, tid);
+
+    auto issue = [&](int kt) {
+        if (kt < KT) {
+            double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
+            ldA.issue(sa, kt, p.K);
+            ldB.issue(sa + LA::ELEMS, kt, p.K);
+        }
+        cp_async_commit();
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+    // fragment offsets inside a stage (k added per step)
+    int aoff[MT], boff[NT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a) aoff[a] = LA::off(warp_m * WM + a * 8 + g4, t4);
+#pragma unroll
+    for (int b = 0; b < NT; ++b) boff[b] = LB::off(warp_n * WN + b * 8 + g4, t4);
+    constexpr int AKS = A_KMAJ ? 1 : (BM + PAD);     // shared stride of one k step
+    constexpr int BKS = B_KMAJ ? 1 : (BN + PAD);
+
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        issue(kt + STAGES - 1);
+        const double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
+        const double* sb = sa + LA::ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int a = 0; a < MT; ++a) af[a] = sa[aoff[a] + kk * AKS];
+#pragma unroll
+            for (int b = 0; b < NT; ++b) bf[b] = sb[boff[b] + kk * BKS];
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) dmma884(acc[a][b][0], acc[a][b][1], bf[b], af[a]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread holds C(m = mrow + {0,1}, n = ncol) for every (a,b).  All loads of one column
+    // batch are issued before its stores so that the read-modify-write costs one memory round trip per
+    // batch instead of one per element.
+    const bool vec_ok = AL16 && ((p.ldc & 1) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+    const double alpha = p.alpha, beta = p.beta;
+    const int mbase = m0 + warp_m * WM + 2 * t4;
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+        int n = n0 + warp_n * WN + b * 8 + g4;
+        if (n >= p.N) continue;
+        double* ccol = p.C + (i64)n * p.ldc;
+        double c0[MT], c1[MT];
+        bool ok0[MT], ok1[MT];
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+            int m = mbase + a * 8;
+            ok0[a] = (m < p.M);
+            ok1[a] = (m + 1 < p.M);
+            if (p.tri == 1) { ok0[a] = ok0[a] && (m >= n); ok1[a] = ok1[a] && (m + 1 >= n); }
+            if (p.tri == 2) { ok0[a] = ok0[a] && (m <= n); ok1[a] = ok1[a] && (m + 1 <= n); }
+            c0[a] = c1[a] = 0.0;
+            if (beta != 0.0) {
+                if (vec_ok && ok0[a] && ok1[a]) {
+                    double2 c = *reinterpret_cast<const double2*>(ccol + m);
+                    c0[a] = c.x; c1[a] = c.y;
+                } else {
+                    if (ok0[a]) c0[a] = ccol[m];
+                    if (ok1[a]) c1[a] = ccol[m + 1];
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+            int m = mbase + a * 8;
+            double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
+            if (beta != 0.0) { v0 += beta * c0[a]; v1 += beta * c1[a]; }
+            if (vec_ok && ok0[a] && ok1[a]) {
+                *reinterpret_cast<double2*>(ccol + m) = make_double2(v0, v1);
+            } else {
+                if (ok0[a]) ccol[m] = v0;
+                if (ok1[a]) ccol[m + 1] = v1;
+            }
+        }
+    }
+}
+
+// C := beta*C (full or one triangle); beta == 0 writes zeros without reading (dgemm.f:303-318).
+__global__ void scale_matrix_kernel(int m, int n, double beta, double* C, i64 ldc, int tri) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= m) return;
+    for (; j < n; j += gridDim.y) {
+        if (tri == 1 && i < j) continue;
+        if (tri == 2 && i > j) continue;
+        double* c = C + i + (i64)j * ldc;
+        *c = (beta == 0.0) ? 0.0 : beta * (*c);
+    }
+}
+
+// C := alpha * sum_z P[z] + beta*C  (deterministic split-K reduction; P slices are dense m x n, ld = m)
+__global__ void splitk_reduce_kernel(int m, int n, int nz, double alpha, double beta, const double* __restrict__ P,
+                                     double* __restrict__ C, i64 ldc, int tri) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        if (tri == 1 && i < j) continue;
+        if (tri == 2 && i > j) continue;
+        double acc = 0.0;
+        const double* q = P + i + (i64)j * m;
+        for (int z = 0; z < nz; ++z) acc += q[(i64)z * m * n];
+        double* c = C + i + (i64)j * ldc;
+        *c = (beta == 0.0) ? alpha * acc : alpha * acc + beta * (*c);
+    }
+}
+
+static int g_gemm_cfg = -1;   // -1 auto, 0 = 128x128x8w, 1 = 128x64x4w, 2 = 64x64 (2 warps)
+
+template <int BM, int BN, int WMW, int WNW, int STAGES>
+static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const GemmParams& p0) {
+    GemmParams p = p0;
+    p.tiles_m = ceil_div(p.M, BM);
+    p.tiles_n = ceil_div(p.N, BN);
+    constexpr int NTH = WMW * WNW * 32;
+    size_t smem = 0;
+    dim3 grid((unsigned)((i64)p.tiles_m * p.tiles_n), (unsigned)ceil_div(p.K, p.kchunk));
+#define LB_LAUNCH(AK, BKM, AL)                                                                                  \
+    {                                                                                                           \
+        auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES>;                                  \
+        smem = sizeof(double) * STAGES * (TileLayout<BM, AK>::ELEMS + TileLayout<BN, BKM>::ELEMS);               \
+        static bool attr_set = false;                                                                           \
+        if (!attr_set) {                                                                                        \
+            LB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            attr_set = true;                                                                                    \
+        }                                                                                                       \
+        kern<<<grid, NTH, smem, s>>>(p);                                                              \
+    }
+    if (a_k) {
+        if (b_k) { if (al16) LB_LAUNCH(true, true, true) else LB_LAUNCH(true, true, false) }
+        else     { if (al16) LB_LAUNCH(true, false, true) else LB_LAUNCH(true, false, false) }
+    } else {
+        if (b_k) { if (al16) LB_LAUNCH(false, true, true) else LB_LAUNCH(false, true, false) }
+        else     { if (al16) LB_LAUNCH(false, false, true) else LB_LAUNCH(false, false, false) }
+    }
+#undef LB_LAUNCH
+    count_launch();
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+
+void gemm_set_config(int cfg) { g_gemm_cfg = cfg; }
+
+void gemm(cudaStream_t s, char transa, char transb, int m, int n, int k, double alpha, const double* A, i64 lda,
+          const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri) {
+    if (m <= 0 || n <= 0) return;
+    if (alpha == 0.0 || k <= 0) {
+        if (beta == 1.0) return;
+        dim3 grid(ceil_div(m, 256), (unsigned)min(n, 4096));
+        scale_matrix_kernel<<<grid, 256, 0, s>>>(m, n, beta, C, ldc, tri);
+        count_launch();
+        return;
+    }
+    const bool ta = (transa == 'T' || transa == 't' || transa == 'C' || transa == 'c');
+    const bool tb = (transb == 'T' || transb == 't' || transb == 'C' || transb == 'c');
+    const bool a_k = ta;        // op(A)=A^T: A stored K x M, k contiguous
+    const bool b_k = !tb;       // op(B)=B  : B stored K x N, k contiguous
+    const bool al16 = ((((uintptr_t)A) & 15) == 0) && ((((uintptr_t)B) & 15) == 0) && ((lda & 1) == 0) &&
+                      ((ldb & 1) == 0);
+    GemmParams p;
+    p.M = m; p.N = n; p.K = k; p.alpha = alpha; p.beta = beta;
+    p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc; p.tri = tri;
+    p.tiles_m = p.tiles_n = 0;
+    p.kchunk = k;
+    p.c_zstride = 0;
+    int cfg = g_gemm_cfg;
+    // Reduce-shaped products (few output tiles, long K: V^T*C in the QR panel, V^T*V) are split along K;
+    // the slices go to scratch and are summed in a fixed order (deterministic).
+    {
+        i64 t64 = (i64)ceil_div(m, 64) * ceil_div(n, 64);
+        if (t64 * 4 <= num_sms() && k >= 4096) {
+            int nz = (int)min((i64)(k / 1024), (i64)(2 * num_sms()) / t64);
+            if (nz >= 2) {
+                int kchunk = ceil_div(ceil_div(k, nz), BK) * BK;
+                nz = ceil_div(k, kchunk);
+                double* P = (double*)ws_alloc(s, sizeof(double) * (size_t)m * n * nz);
+                GemmParams q = p;
+                q.alpha = 1.0; q.beta = 0.0; q.C = P; q.ldc = m; q.tri = 0;
+                q.kchunk = kchunk; q.c_zstride = (i64)m * n;
+                launch_cfg<64, 64, 1, 2, 4>(s, a_k, b_k, al16, q);
+                dim3 rgrid(ceil_div(m, 128), (unsigned)min(n, 4096));
+                splitk_reduce_kernel<<<rgrid, 128, 0, s>>>(m, n, nz, alpha, beta, P, C, ldc, tri);
+                count_launch();
+                ws_free(s, P);
+                return;
+            }
+        }
+    }
+    if (cfg < 0) {
+        // enough 128x128 tiles to fill the machine -> big tile; otherwise smaller tiles for parallelism
+        i64 t128 = (i64)ceil_div(m, 128) * ceil_div(n, 128);
+        i64 t12864 = (i64)ceil_div(m, 128) * ceil_div(n, 64);
+        if (t128 >= 2 * num_sms()) cfg = 0;
+        else if (t12864 >= num_sms()) cfg = 1;
+        else cfg = 2;
+    }
+    if (cfg == 0) launch_cfg<128, 128, 2, 4, 4>(s, a_k, b_k, al16, p);
+    else if (cfg == 1) launch_cfg<128, 64, 2, 2, 3>(s, a_k, b_k, al16, p);
+    else launch_cfg<64, 64, 1, 2, 4>(s, a_k, b_k, al16, p);
+}
+
+// DSYRK (BLAS/SRC/dsyrk.f:168): C := alpha*A*A^T + beta*C ('N') or alpha*A^T*A + beta*C ('T'), one triangle.
+void syrk(cudaStream_t s, char uplo, char trans, int n, int k, double alpha, const double* A, i64 lda, double beta,
+          double* C, i64 ldc) {
+    const bool upper = (uplo == 'U' || uplo == 'u');
+    const bool notr = (trans == 'N' || trans == 'n');
+    if (notr) gemm(s, 'N', 'T', n, n, k, alpha, A, lda, A, lda, beta, C, ldc, upper ? 2 : 1);
+    else gemm(s, 'T', 'N', n, n, k, alpha, A, lda, A, lda, beta, C, ldc, upper ? 2 : 1);
+}
+
+}  // namespace lb

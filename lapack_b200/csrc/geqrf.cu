@@ -1,0 +1,503 @@
+// geqrf.cu -- Householder QR on one B200: DGEQRF / DGEQR2 / DLARFT / DLARFB.
+//
+// Reference path: SRC/dgeqrf.f:180-278 (blocked driver), SRC/dgeqr2.f:169-184 (unblocked panel),
+// SRC/dlarfg.f:140-186 (one reflector), SRC/dlarf1f.f:192-290 (apply), SRC/dlarft.f:207-349 and
+// SRC/dlarft_lvl2.f:199-258 (triangular factor T), SRC/dlarfb.f:231-345 (block reflector, Forward/Columnwise).
+//
+// B200 design.
+//  * Outer block NB (default 256; the reference's 32 gives K=32 GEMMs that sit on the HBM ridge).  The
+//    trailing update C := (I - V T^T V^T) C is three DMMA GEMMs on an explicit "clean" copy Vc of the
+//    reflectors (unit diagonal, zeros above), so no triangular special cases are needed:
+//        W = Vc^T C   (reduce-shaped, split-K when narrow),  W2 = T^T W,  C -= Vc W2.
+//  * The panel is factored recursively (the Elmroth-Gustavson recursion the reference itself uses in
+//    dlarft.f / dgeqrt3.f): left half, apply to right half, right half, T12 = -T1 (V1^T V2) T2.
+//  * Leaf kernel (geqr2_leaf_kernel, W=16 columns): cooperative multi-CTA kernel, one row per thread held
+//    in registers.  Per column ONE fused reduction (sum x^2, x^T C for the remaining columns and the
+//    V^T v dot products needed for T) and ONE grid barrier; then every CTA forms beta/tau exactly as
+//    DLARFG does (DLAPY2 form) and applies the reflector to its rows.  Memory-bound: 16*M*W bytes per leaf.
+//  * Over/underflow safety (DNRM2's scaled accumulators, DLARFG's rescale loop) is obtained by an exact
+//    power-of-two pre-scaling of the whole matrix when max|A| is outside [2^-400, 2^400]; V and tau are
+//    invariant under it and R is scaled back.
+#include "lb_internal.h"
+#include <cfloat>
+#include <mutex>
+
+namespace lb {
+
+void expand_tri(cudaStream_t s, int n, const double* A, i64 lda, bool upper, bool unit, double* T, i64 ldt);
+
+static int g_qr_nb = 256, g_qr_lookahead = 1;
+void geqrf_set_params(int nb, int lookahead) {
+    if (nb > 0) g_qr_nb = nb;
+    if (lookahead >= 0) g_qr_lookahead = lookahead;
+}
+
+constexpr int QW = 16;          // leaf width
+constexpr int QTHREADS = 1024;  // rows per CTA
+
+struct QrLeafParams {
+    int m, n;
+    double* A; i64 lda;
+    double* tau;
+    double* Vc; i64 ldvc;      // clean reflectors (m x n)
+    double* T; i64 ldt;        // leaf T block (n x n upper triangular), lower part untouched
+    unsigned* bar; unsigned bar_base;
+    double* part;              // [2][G][QW]
+    double* toprow;            // [2][QW]
+    int G;
+};
+
+__device__ __forceinline__ void qr_grid_barrier(unsigned* bar, unsigned target, int G) {
+    __syncthreads();
+    if (G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
+            } while ((int)(v - target) < 0);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// SRC/dlapy2.f:96-112 for finite inputs
+__device__ __forceinline__ double dev_dlapy2(double x, double y) {
+    double xa = fabs(x), ya = fabs(y);
+    double w = fmax(xa, ya), z = fmin(xa, ya);
+    if (z == 0.0 || w > DBL_MAX) return w;
+    double q = z / w;
+    return w * sqrt(1.0 + q * q);
+}
+
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_kernel(QrLeafParams p) {
+    constexpr int NWARP = THREADS / 32;
+    __shared__ double s_red[NWARP][W];
+    __shared__ double s_tot[W];
+    __shared__ double s_trow[W];
+    __shared__ double s_G[W][W];      // s_G[i][c] = V(:,i)^T v_c, i < c
+    __shared__ double s_tau[W];
+    __shared__ double s_T[W][W];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x;
+    const int row = g * THREADS + tid;
+    const bool have = row < p.m;
+    const int kmax = min(p.m, p.n);
+
+    double a[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[c] = (have && c < p.n) ? p.A[row + (i64)c * p.lda] : 0.0;
+
+    // step c = 0..kmax-1: reflector c; step c = kmax: only the trailing V^T v reduction for column kmax-1
+#pragma unroll
+    for (int c = 0; c <= W; ++c) {
+        if (c <= kmax) {
+            const int slot = c & 1;
+            double red[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) red[q] = 0.0;
+            if (c < kmax && c < W) {
+                if (have && row > c) {
+                    red[0] = a[c < W ? c : 0] * a[c < W ? c : 0];
+#pragma unroll
+                    for (int q = c + 1; q < W; ++q) red[1 + (q - c - 1)] = a[c < W ? c : 0] * a[q];
+                }
+            }
+            if (c >= 1) {
+                // dots of the finished reflector pc = c-1 with the earlier ones (unit diagonal at row pc)
+                const int pc = c - 1;
+                if (have && row >= pc) {
+#pragma unroll
+                    for (int i = 0; i + 1 < c; ++i) {   // i in 0..pc-1
+                        double vi = a[i];
+                        red[W - c + i] = (row == pc) ? vi : vi * a[pc];
+                    }
+                }
+            }
+            // block reduction of the W partial sums
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                double v = red[q];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if (lane == 0) s_red[warp][q] = v;
+            }
+            __syncthreads();
+            if (tid < W) {
+                double v = 0.0;
+#pragma unroll 8
+                for (int w = 0; w < NWARP; ++w) v += s_red[w][tid];
+                p.part[((i64)slot * p.G + g) * W + tid] = v;
+            }
+            if (c < kmax && have && row == c) {
+                double* dst = p.toprow + slot * W;
+#pragma unroll
+                for (int q = 0; q < W; ++q) dst[q] = a[q];
+            }
+            qr_grid_barrier(p.bar, p.bar_base + (unsigned)(c + 1) * (unsigned)p.G, p.G);
+            if (tid < W) {
+                double v = 0.0;
+                for (int q = 0; q < p.G; ++q) v += __ldcg(p.part + ((i64)slot * p.G + q) * W + tid);
+                s_tot[tid] = v;
+                if (c < kmax) s_trow[tid] = __ldcg(p.toprow + slot * W + tid);
+            }
+            __syncthreads();
+            if (c >= 1) {
+                const int pc = c - 1;
+                if (tid < pc) s_G[tid][pc] = s_tot[W - c + tid];
+            }
+            if (c < kmax && c < W) {
+                // DLARFG (dlarfg.f:140-186) with xnorm^2 = s_tot[0]
+                const double alpha = s_trow[c];
+                const double xnorm = sqrt(s_tot[0]);
+                double tau = 0.0, beta = alpha, scale = 0.0;
+                if (xnorm != 0.0) {
+                    beta = -copysign(dev_dlapy2(alpha, xnorm), alpha);
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                if (tid == 0) {
+                    s_tau[c] = tau;
+                    if (g == 0) p.tau[c] = tau;
+                }
+                if (tau != 0.0) {
+                    if (have && row > c) {
+                        const double v = a[c] * scale;           // DSCAL by 1/(alpha-beta), dlarfg.f:178
+                        a[c] = v;
+#pragma unroll
+                        for (int q = c + 1; q < W; ++q) {
+                            // w(q) = C(1,q) + v2^T C2(:,q)  (dlarf1f.f:247-250);  C -= tau*v*w^T (dlarf1f.f:256-258)
+                            const double wq = s_trow[q] + scale * s_tot[1 + (q - c - 1)];
+                            a[q] = fma(-tau * wq, v, a[q]);
+                        }
+                    } else if (have && row == c) {
+                        a[c] = beta;
+#pragma unroll
+                        for (int q = c + 1; q < W; ++q) {
+                            const double wq = s_trow[q] + scale * s_tot[1 + (q - c - 1)];
+                            a[q] = a[q] - tau * wq;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // T for the leaf (dlarft_lvl2.f:199-258): T(0:c,c) = T(0:c,0:c) * (-tau_c * G(0:c,c)), T(c,c) = tau_c
+    if (g == 0) {
+        if (warp == 0) {
+            for (int c = 0; c < kmax; ++c) {
+                const double tc = s_tau[c];
+                double tmp = (lane < c) ? -tc * s_G[lane][c] : 0.0;
+                // upper-triangular matvec: out[i] = sum_{j=i..c-1} T[i][j]*tmp[j]
+                double out = 0.0;
+                for (int j = 0; j < c; ++j) {
+                    double tj = __shfl_sync(0xffffffffu, tmp, j);
+                    if (lane <= j && lane < c) out += s_T[lane][j] * tj;
+                }
+                if (lane < c) s_T[lane][c] = (tc == 0.0) ? 0.0 : out;
+                if (lane == c) s_T[c][c] = tc;
+                __syncwarp();
+            }
+            for (int idx = lane; idx < kmax * kmax; idx += 32) {
+                int i = idx % kmax, j = idx / kmax;
+                if (i <= j) p.T[i + (i64)j * p.ldt] = s_T[i][j];
+            }
+        }
+    }
+    if (have) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+            if (c < p.n) {
+                p.A[row + (i64)c * p.lda] = a[c];
+                if (p.Vc) {
+                    double v = a[c];
+                    if (c >= kmax || row < c) v = 0.0;
+                    else if (row == c) v = 1.0;
+                    p.Vc[row + (i64)c * p.ldvc] = v;
+                }
+            }
+        }
+    }
+}
+
+struct QrWs {
+    unsigned* bar = nullptr;
+    unsigned base = 0;
+    double* part = nullptr;
+    double* toprow = nullptr;
+    int maxG = 0;
+};
+static QrWs& qr_ws() {
+    static QrWs w;
+    if (!w.bar) {
+        w.maxG = 1024;
+        LB_CUDA_CHECK(cudaMalloc(&w.bar, 256));
+        LB_CUDA_CHECK(cudaMemset(w.bar, 0, 256));
+        LB_CUDA_CHECK(cudaMalloc(&w.part, sizeof(double) * 2 * w.maxG * QW));
+        LB_CUDA_CHECK(cudaMalloc(&w.toprow, sizeof(double) * 2 * QW));
+    }
+    return w;
+}
+
+// leaf: m x n (n <= QW); writes A (R and v), tau, Vc (clean, may be null) and the n x n T block
+static void geqr2_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, double* Vc, i64 ldvc, double* T,
+                       i64 ldt) {
+    QrWs& w = qr_ws();
+    QrLeafParams p;
+    p.m = m; p.n = n; p.A = A; p.lda = lda; p.tau = tau; p.Vc = Vc; p.ldvc = ldvc; p.T = T; p.ldt = ldt;
+    p.G = ceil_div(m, QTHREADS);
+    if (p.G > w.maxG || p.G > num_sms()) {
+        fprintf(stderr, "lapack_b200: QR panel of %d rows exceeds the cooperative leaf capacity\n", m);
+        record_cuda_error(cudaErrorInvalidValue);
+        return;
+    }
+    p.bar = w.bar; p.bar_base = w.base; p.part = w.part; p.toprow = w.toprow;
+    geqr2_leaf_kernel<QW, QTHREADS><<<p.G, QTHREADS, 0, s>>>(p);
+    count_launch();
+    if (p.G > 1) w.base += (unsigned)(min(m, n) + 1) * (unsigned)p.G;
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+
+// Recursive panel: A (m x n) -> R, V (in A), tau, clean Vc (m x n), T (n x n upper, lower part zero on entry).
+// tmp: scratch of at least n*n doubles (+ n x ncols for the in-panel block reflector application).
+struct PanelWs {
+    double* W1;   // (n/2) x (n/2)
+    double* W2;
+};
+static void geqrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, double* Vc, i64 ldvc, double* T,
+                        i64 ldt, double* W1, double* W2) {
+    if (m <= 0 || n <= 0) return;
+    if (n <= QW) { geqr2_leaf(s, m, n, A, lda, tau, Vc, ldvc, T, ldt); return; }
+    int n1 = QW;
+    while (n1 * 2 < n) n1 *= 2;
+    if (n1 > m) n1 = m;          // cannot have more reflectors than rows in the left part
+    const int n2 = n - n1;
+    // left half
+    geqrf_panel(s, m, n1, A, lda, tau, Vc, ldvc, T, ldt, W1, W2);
+    const int k1 = min(m, n1);
+    // apply H1^T to the right half: C = A(:, n1:n)
+    double* C = A + (i64)n1 * lda;
+    i64 ldw = (k1 + 1) & ~1;
+    gemm(s, 'T', 'N', k1, n2, m, 1.0, Vc, ldvc, C, lda, 0.0, W1, ldw);            // W1 = V1^T C      (dlarfb.f:257-275)
+    gemm(s, 'T', 'N', k1, n2, k1, 1.0, T, ldt, W1, ldw, 0.0, W2, ldw);            // W2 = T1^T W1     (dlarfb.f:277)
+    gemm(s, 'N', 'N', m, n2, k1, -1.0, Vc, ldvc, W2, ldw, 1.0, C, lda);           // C -= V1 W2       (dlarfb.f:287-304)
+    if (m > n1) {
+        // right half on the trailing rows
+        geqrf_panel(s, m - n1, n2, A + n1 + (i64)n1 * lda, lda, tau + n1, Vc + n1 + (i64)n1 * ldvc, ldvc,
+                    T + n1 + (i64)n1 * ldt, ldt, W1, W2);
+        // rows 0..n1-1 of the right half of Vc are zero
+        laset(s, 'A', n1, n2, 0.0, 0.0, Vc + (i64)n1 * ldvc, ldvc);
+        const int k2 = min(m - n1, n2);
+        // T12 = -T1 (V1^T V2) T2      (dlarft.f:308-349)
+        gemm(s, 'T', 'N', k1, k2, m - n1, 1.0, Vc + n1, ldvc, Vc + n1 + (i64)n1 * ldvc, ldvc, 0.0, W1, ldw);
+        gemm(s, 'N', 'N', k1, k2, k1, -1.0, T, ldt, W1, ldw, 0.0, W2, ldw);
+        gemm(s, 'N', 'N', k1, k2, k2, 1.0, W2, ldw, T + n1 + (i64)n1 * ldt, ldt, 0.0, T + (i64)n1 * ldt, ldt);
+    } else {
+        laset(s, 'A', m, n2, 0.0, 0.0, Vc + (i64)n1 * ldvc, ldvc);
+    }
+}
+
+// max |A| -> power-of-two scale factor (1.0 when no scaling is needed), kept on the device
+__global__ void amax_kernel(int m, int n, const double* __restrict__ A, i64 lda, unsigned long long* amax_bits) {
+    double v = 0.0;
+    for (i64 j = blockIdx.x; j < n; j += gridDim.x)
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            double x = fabs(A[i + j * lda]);
+            if (x == x && x <= DBL_MAX) v = fmax(v, x);   // ignore NaN/Inf: they propagate on their own
+        }
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(v));
+}
+__global__ void decide_scale_kernel(const unsigned long long* amax_bits, double* scale) {
+    double amax = __longlong_as_double((long long)*amax_bits);
+    double sc = 1.0;
+    if (amax > 0.0) {
+        int e;
+        frexp(amax, &e);
+        if (e > 400 || e < -400) { sc = ldexp(1.0, 1 - e); scale[1] = ldexp(1.0, e - 1); }
+    }
+    scale[0] = sc;
+    if (sc == 1.0) scale[1] = 1.0;
+}
+// A := A * scale[which]; tri: 0 all, 1 = upper triangle incl. diagonal only (R)
+__global__ void scale_by_dev_kernel(int m, int n, double* __restrict__ A, i64 lda, const double* scale, int which,
+                                    int upper_only) {
+    const double sc = scale[which];
+    if (sc == 1.0) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    for (int j = blockIdx.y; j < n; j += gridDim.y) {
+        if (upper_only && i > j) continue;
+        A[i + (i64)j * lda] *= sc;
+    }
+}
+
+static std::mutex g_qr_mutex;
+
+static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, int nb) {
+    if (m <= 0 || n <= 0) return;
+    const int k = min(m, n);
+    nb = min(nb, k);
+    if (nb < QW) nb = min(QW, k);
+    // scratch
+    const i64 ldvc = (m + 1) & ~1;
+    const i64 ldt = (nb + 1) & ~1;
+    const i64 ldw = (nb + 1) & ~1;
+    double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * nb);
+    double* T = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
+    double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
+    unsigned long long* amax_bits = (unsigned long long*)ws_alloc(s, 64);
+    double* scale = (double*)(amax_bits + 2);
+
+    // exact power-of-two pre-scaling against over/underflow in the fused norm reduction
+    LB_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 8, s));
+    amax_kernel<<<min(n, 4 * num_sms()), 256, 0, s>>>(m, n, A, lda, amax_bits);
+    decide_scale_kernel<<<1, 1, 0, s>>>(amax_bits, scale);
+    dim3 sgrid(ceil_div(m, 256), (unsigned)min(n, 4096));
+    scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 0, 0);
+    count_launch(3);
+
+    for (int j = 0; j < k; j += nb) {
+        const int jb = min(nb, k - j);
+        const int mj = m - j;
+        double* Ajj = A + j + (i64)j * lda;
+        LB_CUDA_CHECK(cudaMemsetAsync(T, 0, sizeof(double) * ldt * nb, s));
+        geqrf_panel(s, mj, jb, Ajj, lda, tau + j, Vc, ldvc, T, ldt, W1, W2);
+        const int nt = n - j - jb;
+        if (nt > 0) {
+            double* C = A + j + (i64)(j + jb) * lda;
+            gemm(s, 'T', 'N', jb, nt, mj, 1.0, Vc, ldvc, C, lda, 0.0, W1, ldw);       // W1 = V^T C
+            gemm(s, 'T', 'N', jb, nt, jb, 1.0, T, ldt, W1, ldw, 0.0, W2, ldw);        // W2 = T^T W1
+            gemm(s, 'N', 'N', mj, nt, jb, -1.0, Vc, ldvc, W2, ldw, 1.0, C, lda);      // C -= V W2
+        }
+    }
+    scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 1, 1);   // un-scale R only
+    count_launch();
+    ws_free(s, Vc); ws_free(s, T); ws_free(s, W1); ws_free(s, W2); ws_free(s, amax_bits);
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+
+void geqrf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
+    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    geqrf_impl(s, m, n, A, lda, tau, g_qr_nb);
+}
+// DGEQR2: same factorization, panel-only code path (one recursive panel per 64 columns)
+void geqr2(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
+    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    geqrf_impl(s, m, n, A, lda, tau, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// clean copy of reflectors stored below the diagonal of V (n x k): zeros above, ones on the diagonal
+__global__ void clean_v_kernel(int n, int k, const double* __restrict__ V, i64 ldv, double* __restrict__ Vc, i64 ldvc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = blockIdx.y; j < k; j += gridDim.y) {
+        double v = (i > j) ? V[i + (i64)j * ldv] : (i == j ? 1.0 : 0.0);
+        Vc[i + (i64)j * ldvc] = v;
+    }
+}
+static void clean_v(cudaStream_t s, int n, int k, const double* V, i64 ldv, double* Vc, i64 ldvc) {
+    dim3 grid(ceil_div(n, 256), (unsigned)min(k, 4096));
+    clean_v_kernel<<<grid, 256, 0, s>>>(n, k, V, ldv, Vc, ldvc);
+    count_launch();
+}
+
+// T block (len <= 32) from G = V^T V and tau: dlarft_lvl2.f:199-258
+__global__ void larft_leaf_kernel(int len, const double* __restrict__ G, i64 ldg, const double* __restrict__ tau,
+                                  double* __restrict__ T, i64 ldt) {
+    __shared__ double sT[32][33];
+    const int lane = threadIdx.x;
+    for (int c = 0; c < len; ++c) {
+        const double tc = tau[c];
+        double tmp = (lane < c) ? -tc * G[lane + (i64)c * ldg] : 0.0;
+        double out = 0.0;
+        for (int j = 0; j < c; ++j) {
+            double tj = __shfl_sync(0xffffffffu, tmp, j);
+            if (lane <= j && lane < c) out += sT[lane][j] * tj;
+        }
+        if (lane < c) sT[lane][c] = (tc == 0.0) ? 0.0 : out;
+        if (lane == c) sT[c][c] = tc;
+        __syncwarp();
+    }
+    for (int idx = lane; idx < len * len; idx += 32) {
+        int i = idx % len, j = idx / len;
+        if (i <= j) T[i + (i64)j * ldt] = sT[i][j];
+    }
+}
+static void larft_rec(cudaStream_t s, int k, const double* G, i64 ldg, const double* tau, double* T, i64 ldt, double* W1,
+                      double* W2, i64 ldw) {
+    if (k <= 32) {
+        larft_leaf_kernel<<<1, 32, 0, s>>>(k, G, ldg, tau, T, ldt);
+        count_launch();
+        return;
+    }
+    int k1 = 32;
+    while (k1 * 2 < k) k1 *= 2;
+    const int k2 = k - k1;
+    larft_rec(s, k1, G, ldg, tau, T, ldt, W1, W2, ldw);
+    larft_rec(s, k2, G + k1 + (i64)k1 * ldg, ldg, tau + k1, T + k1 + (i64)k1 * ldt, ldt, W1, W2, ldw);
+    // T12 = -T1 * G12 * T2; T1/T2 are read through expanded (zero-filled) copies
+    double* E1 = W1;                       // k1 x k1
+    double* E2 = W1 + ldw * k1;            // k2 x k2
+    double* Tm = W2;                       // k1 x k2
+    expand_tri(s, k1, T, ldt, true, false, E1, ldw);
+    expand_tri(s, k2, T + k1 + (i64)k1 * ldt, ldt, true, false, E2, ldw);
+    gemm(s, 'N', 'N', k1, k2, k1, -1.0, E1, ldw, G + (i64)k1 * ldg, ldg, 0.0, Tm, ldw);
+    gemm(s, 'N', 'N', k1, k2, k2, 1.0, Tm, ldw, E2, ldw, 0.0, T + (i64)k1 * ldt, ldt);
+}
+
+// DLARFT('Forward','Columnwise', n, k, V, ldv, tau, T, ldt): only the upper triangle of T is written
+void larft(cudaStream_t s, int n, int k, const double* V, i64 ldv, const double* tau, double* T, i64 ldt) {
+    if (n <= 0 || k <= 0) return;
+    const i64 ldvc = (n + 1) & ~1, ldg = (k + 1) & ~1, ldw = (k + 1) & ~1;
+    double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * k);
+    double* G = (double*)ws_alloc(s, sizeof(double) * ldg * k);
+    double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * (k + 2));
+    double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * (k + 2));
+    clean_v(s, n, k, V, ldv, Vc, ldvc);
+    gemm(s, 'T', 'N', k, k, n, 1.0, Vc, ldvc, Vc, ldvc, 0.0, G, ldg);
+    larft_rec(s, k, G, ldg, tau, T, ldt, W1, W2, ldw);
+    ws_free(s, Vc); ws_free(s, G); ws_free(s, W1); ws_free(s, W2);
+}
+
+// DLARFB(SIDE, TRANS, 'Forward', 'Columnwise', m, n, k, V, T, C): C := H C, H^T C, C H or C H^T, H = I - V T V^T
+void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const double* V, i64 ldv, const double* T, i64 ldt,
+           double* C, i64 ldc) {
+    if (m <= 0 || n <= 0 || k <= 0) return;
+    const bool left = (side == 'L' || side == 'l');
+    const bool tr = !(trans == 'N' || trans == 'n');
+    const int nv = left ? m : n;
+    const i64 ldvc = (nv + 1) & ~1, lde = (k + 1) & ~1;
+    double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * k);
+    double* E = (double*)ws_alloc(s, sizeof(double) * lde * k);
+    clean_v(s, nv, k, V, ldv, Vc, ldvc);
+    expand_tri(s, k, T, ldt, true, false, E, lde);
+    if (left) {
+        const i64 ldw = (k + 1) & ~1;
+        double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * n);
+        double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * n);
+        gemm(s, 'T', 'N', k, n, m, 1.0, Vc, ldvc, C, ldc, 0.0, W1, ldw);                 // W1 = V^T C
+        gemm(s, tr ? 'T' : 'N', 'N', k, n, k, 1.0, E, lde, W1, ldw, 0.0, W2, ldw);       // W2 = op(T) W1
+        gemm(s, 'N', 'N', m, n, k, -1.0, Vc, ldvc, W2, ldw, 1.0, C, ldc);                // C -= V W2
+        ws_free(s, W1); ws_free(s, W2);
+    } else {
+        const i64 ldw = (m + 1) & ~1;
+        double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * k);
+        double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * k);
+        gemm(s, 'N', 'N', m, k, n, 1.0, C, ldc, Vc, ldvc, 0.0, W1, ldw);                 // W1 = C V
+        gemm(s, 'N', tr ? 'T' : 'N', m, k, k, 1.0, W1, ldw, E, lde, 0.0, W2, ldw);       // W2 = W1 op(T)
+        gemm(s, 'N', 'T', m, n, k, -1.0, W2, ldw, Vc, ldvc, 1.0, C, ldc);                // C -= W2 V^T
+        ws_free(s, W1); ws_free(s, W2);
+    }
+    ws_free(s, Vc); ws_free(s, E);
+}
+
+}  // namespace lb

@@ -1,0 +1,372 @@
+// getrf.cu -- LU with partial pivoting on one B200: DGETRF / DGETRF2 / DGETRS.
+//
+// Reference path: SRC/dgetrf.f:164-219 (right-looking blocked driver), SRC/dgetrf2.f:170-265 (recursive
+// panel; leaf = IDAMAX + swap + scale, BLAS/SRC/idamax.f:93-123, dscal.f:104-135), SRC/dlaswp.f:138-183,
+// SRC/dgetrs.f:181-218.
+//
+// B200 design.
+//  * Outer block NB (default 512, not ILAENV's 64): the trailing update C -= L21*U12 then has arithmetic
+//    intensity NB/8 flop/B, far above the HBM ridge, and runs as DMMA GEMM tiles (gemm_f64.cu).
+//  * The NB-wide panel is factored recursively (same splitting idea as DGETRF2) so that all but the
+//    narrowest level is again TRSM/GEMM on the tensor pipe.  The recursion stops at a W(=16)-column leaf.
+//  * Leaf kernel (getrf_leaf_kernel): cooperative multi-CTA kernel, one panel row per thread held in
+//    registers for all W columns.  Per column: block-level arg-max (warp shuffles), candidates + their
+//    rows published to global scratch, ONE grid barrier, every CTA then picks the winner (first index on
+//    ties, IDAMAX semantics), swaps through the published copies, scales by the reciprocal (or divides
+//    when |pivot| < SFMIN, dgetrf2.f:204-210) and applies the rank-1 update to its rows.  Memory-bound:
+//    the panel is read once and written once; algorithmic bytes 16*M*W per leaf.
+//  * Look-ahead: panel k+1 is factored on a high-priority stream as soon as its columns have received
+//    update k, while the rest of update k runs on another stream.
+#include "lb_internal.h"
+#include <cfloat>
+#include <math_constants.h>
+#include <mutex>
+
+namespace lb {
+
+void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx);
+
+static int g_nb = 512, g_lookahead = 1;
+void getrf_set_params(int nb, int leaf, int lookahead) {
+    (void)leaf;
+    if (nb > 0) g_nb = nb;
+    if (lookahead >= 0) g_lookahead = lookahead;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Cand {
+    double key;   // |a| used for selection (NaN handling folded in)
+    int row;      // panel-relative row, 0-based
+    int pad;
+};
+
+struct LeafParams {
+    int m, n;
+    double* A;
+    i64 lda;
+    int* ipiv;        // panel-relative, 1-based on output
+    int* info;        // device word: first zero pivot (absolute, 1-based) -- written only if still 0
+    int info_off;     // absolute column offset of this leaf
+    double sfmin;
+    unsigned* bar;
+    unsigned bar_base;
+    Cand* cand;       // [2][G]
+    double* candrow;  // [2][G][W]
+    double* toprow;   // [2][W]
+    int G;
+};
+
+__device__ __forceinline__ bool cand_better(double k1, int r1, double k2, int r2) {
+    return (k1 > k2) || (k1 == k2 && r1 < r2);
+}
+
+__device__ __forceinline__ void leaf_grid_barrier(unsigned* bar, unsigned target, int G) {
+    __syncthreads();
+    if (G > 1) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            unsigned v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
+            } while ((int)(v - target) < 0);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
+    constexpr int NWARP = THREADS / 32;
+    __shared__ double s_key[NWARP];
+    __shared__ int s_row[NWARP];
+    __shared__ double s_prow[W], s_trow[W];
+    __shared__ int s_win_row;
+    __shared__ int s_loc_row;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x;
+    const int row = g * THREADS + tid;          // panel-relative row owned by this thread
+    const bool have = row < p.m;
+    const int kmax = min(p.m, p.n);
+
+    double a[W];
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[c] = (have && c < p.n) ? p.A[row + (i64)c * p.lda] : 0.0;
+
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+        if (c < kmax) {
+            const int slot = c & 1;
+            // (1) local arg-max over active rows (row >= c); IDAMAX semantics: first index of the max,
+            //     NaN never wins unless it is the very first element (idamax.f:103 strict '>').
+            double key = -1.0;
+            int krow = 0x7fffffff;
+            if (have && row >= c) {
+                double v = fabs(a[c]);
+                if (v != v) v = (row == c) ? CUDART_INF : -1.0;
+                key = v;
+                krow = row;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ok = __shfl_xor_sync(0xffffffffu, key, off);
+                int orow = __shfl_xor_sync(0xffffffffu, krow, off);
+                if (cand_better(ok, orow, key, krow)) { key = ok; krow = orow; }
+            }
+            if (lane == 0) { s_key[warp] = key; s_row[warp] = krow; }
+            __syncthreads();
+            if (warp == 0) {
+                double k2 = (lane < NWARP) ? s_key[lane] : -1.0;
+                int r2 = (lane < NWARP) ? s_row[lane] : 0x7fffffff;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                    int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                    if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; }
+                }
+                if (lane == 0) {
+                    s_loc_row = r2;
+                    Cand cd; cd.key = k2; cd.row = r2; cd.pad = 0;
+                    p.cand[slot * p.G + g] = cd;
+                }
+            }
+            __syncthreads();
+            // (2) publish the local winner's row and (owner of row c) the current top row
+            if (have && row == s_loc_row) {
+                double* dst = p.candrow + ((i64)slot * p.G + g) * W;
+#pragma unroll
+                for (int q = 0; q < W; ++q) dst[q] = a[q];
+            }
+            if (have && row == c) {
+                double* dst = p.toprow + slot * W;
+#pragma unroll
+                for (int q = 0; q < W; ++q) dst[q] = a[q];
+            }
+            // (3) one grid-wide barrier per column
+            leaf_grid_barrier(p.bar, p.bar_base + (unsigned)(c + 1) * (unsigned)p.G, p.G);
+            // (4) every CTA picks the global winner and fetches the two rows
+            if (warp == 0) {
+                double k2 = -2.0;
+                int r2 = 0x7fffffff, g2 = 0;
+                for (int q = lane; q < p.G; q += 32) {
+                    const Cand* cp = p.cand + slot * p.G + q;
+                    double ck = __ldcg(&cp->key);
+                    int cr = __ldcg(&cp->row);
+                    if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                    int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                    int og = __shfl_xor_sync(0xffffffffu, g2, off);
+                    if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
+                }
+                if (lane < W) {
+                    s_prow[lane] = __ldcg(p.candrow + ((i64)slot * p.G + g2) * W + lane);
+                    s_trow[lane] = __ldcg(p.toprow + slot * W + lane);
+                }
+                if (lane == 0) s_win_row = r2;
+            }
+            __syncthreads();
+            const int prow = s_win_row;
+            const double pivot = s_prow[c];
+            // (5) interchange through the published copies (dgetrf2.f:196-200; whole rows of the leaf)
+            if (prow != c) {
+                if (have && row == prow) {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) a[q] = s_trow[q];
+                } else if (have && row == c) {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) a[q] = s_prow[q];
+                }
+            }
+            // (6) pivot index / singularity flag (dgetrf2.f:191-192,212-214)
+            if (g == 0 && tid == 0) {
+                p.ipiv[c] = prow + 1;
+                if (pivot == 0.0 && *p.info == 0) *p.info = p.info_off + c + 1;
+            }
+            // (7) scale (reciprocal unless |pivot| < SFMIN, dgetrf2.f:204-210) and rank-1 update
+            if (pivot != 0.0 && have && row > c) {
+                double l;
+                if (fabs(pivot) >= p.sfmin) l = a[c] * (1.0 / pivot);
+                else l = a[c] / pivot;
+                a[c] = l;
+#pragma unroll
+                for (int q = c + 1; q < W; ++q) a[q] = fma(-l, s_prow[q], a[q]);
+            }
+        }
+    }
+    if (have) {
+#pragma unroll
+        for (int c = 0; c < W; ++c)
+            if (c < p.n) p.A[row + (i64)c * p.lda] = a[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int LEAF_W = 16;
+constexpr int LEAF_THREADS = 1024;
+
+struct LeafWs {
+    unsigned* bar = nullptr;
+    unsigned base = 0;
+    Cand* cand = nullptr;
+    double* candrow = nullptr;
+    double* toprow = nullptr;
+    int maxG = 0;
+};
+static LeafWs& leaf_ws() {
+    static LeafWs w;
+    if (!w.bar) {
+        w.maxG = 1024;
+        LB_CUDA_CHECK(cudaMalloc(&w.bar, 256));
+        LB_CUDA_CHECK(cudaMemset(w.bar, 0, 256));
+        LB_CUDA_CHECK(cudaMalloc(&w.cand, sizeof(Cand) * 2 * w.maxG));
+        LB_CUDA_CHECK(cudaMalloc(&w.candrow, sizeof(double) * 2 * w.maxG * LEAF_W));
+        LB_CUDA_CHECK(cudaMalloc(&w.toprow, sizeof(double) * 2 * LEAF_W));
+    }
+    return w;
+}
+
+// factor an m x n (n <= LEAF_W) panel; ipiv relative (1-based); *info set to info_off + col + 1 on the
+// first exact zero pivot (only if still zero)
+static void getrf_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
+    LeafWs& w = leaf_ws();
+    LeafParams p;
+    p.m = m; p.n = n; p.A = A; p.lda = lda; p.ipiv = ipiv; p.info = info; p.info_off = info_off;
+    p.sfmin = DBL_MIN;   // DLAMCH('S') (INSTALL/dlamch.f:111-122)
+    p.G = ceil_div(m, LEAF_THREADS);
+    if (p.G > w.maxG || p.G > num_sms()) {
+        fprintf(stderr, "lapack_b200: panel of %d rows exceeds the cooperative leaf capacity\n", m);
+        record_cuda_error(cudaErrorInvalidValue);
+        return;
+    }
+    p.bar = w.bar; p.bar_base = w.base; p.cand = w.cand; p.candrow = w.candrow; p.toprow = w.toprow;
+    getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G, LEAF_THREADS, 0, s>>>(p);
+    count_launch();
+    if (p.G > 1) w.base += (unsigned)min(m, n) * (unsigned)p.G;
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+
+// recursive panel (the DGETRF2 recursion, dgetrf2.f:216-263) down to LEAF_W columns
+static void getrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
+    if (m <= 0 || n <= 0) return;
+    if (n <= LEAF_W) { getrf_leaf(s, m, n, A, lda, ipiv, info, info_off); return; }
+    const int mn = min(m, n);
+    int n1 = LEAF_W;
+    while (n1 * 2 < mn) n1 *= 2;                 // power-of-two multiple of the leaf width, < mn
+    if (n1 >= mn) n1 = max(1, mn / 2);
+    if (n1 > mn) n1 = mn;
+    const int n2 = n - n1;
+    //        [ A11 ]
+    // factor [ --- ]
+    //        [ A21 ]
+    getrf_panel(s, m, n1, A, lda, ipiv, info, info_off);
+    double* A12 = A + (i64)n1 * lda;
+    double* A21 = A + n1;
+    double* A22 = A + n1 + (i64)n1 * lda;
+    laswp(s, n2, A12, lda, 1, n1, ipiv, 1);                                    // dgetrf2.f:236
+    trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, A, lda, A12, lda);               // dgetrf2.f:240
+    if (m > n1) {
+        gemm(s, 'N', 'N', m - n1, n2, n1, -1.0, A21, lda, A12, lda, 1.0, A22, lda);   // dgetrf2.f:245
+        getrf_panel(s, m - n1, n2, A22, lda, ipiv + n1, info, info_off + n1);          // dgetrf2.f:250
+        iadd(s, min(m, n) - n1, ipiv + n1, n1);                                          // dgetrf2.f:257-259
+        laswp(s, n1, A, lda, n1 + 1, min(m, n), ipiv, 1);                               // dgetrf2.f:263
+    }
+}
+
+static std::mutex g_lib_mutex;
+
+void getrf2(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
+    std::lock_guard<std::mutex> lock(g_lib_mutex);
+    LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
+    getrf_panel(s, m, n, A, lda, ipiv, info, 0);
+}
+
+void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
+    std::lock_guard<std::mutex> lock(g_lib_mutex);
+    LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
+    if (m <= 0 || n <= 0) return;
+    const int mn = min(m, n);
+    const int nb = g_nb;
+    if (nb >= mn) { getrf_panel(s, m, n, A, lda, ipiv, info, 0); return; }
+
+    const bool la = g_lookahead != 0;
+    Aux& ax = aux();
+    cudaStream_t sp = la ? ax.panel_stream : s;    // panel stream
+    cudaStream_t su = la ? ax.update_stream : s;   // trailing-update stream
+    cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2];
+    if (la) {
+        LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_join, 0));
+    }
+    // first panel
+    getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
+    if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
+
+    for (int j = 0; j < mn; j += nb) {
+        const int jb = min(nb, mn - j);
+        const int jn = j + jb;                       // first column after this panel
+        if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel, 0));
+        double* Ajj = A + j + (i64)j * lda;
+        const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
+        // columns of the next panel first (look-ahead), then the rest
+        const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
+        if (jn < n) {
+            const int w1 = (jb2 > 0) ? jb2 : (n - jn);       // width of the first slab
+            double* A12 = A + j + (i64)jn * lda;
+            laswp(su, w1, A + (i64)jn * lda, lda, j + 1, jn, piv, 1);                        // dgetrf.f:199
+            trsm(su, 'L', 'L', 'N', 'U', jb, w1, 1.0, Ajj, lda, A12, lda);                   // dgetrf.f:204
+            if (jn < m)
+                gemm(su, 'N', 'N', m - jn, w1, jb, -1.0, A + jn + (i64)j * lda, lda, A12, lda, 1.0,
+                     A + jn + (i64)jn * lda, lda);                                          // dgetrf.f:212
+            if (jb2 > 0) {
+                if (la) {
+                    LB_CUDA_CHECK(cudaEventRecord(ev_next, su));
+                    LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_next, 0));
+                }
+                // factor the next panel (overlaps with the rest of this update when look-ahead is on)
+                getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
+                iadd(sp, min(m - jn, jb2), ipiv + jn, jn);                                   // dgetrf.f:187-189
+                if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
+                const int rest = n - jn - w1;
+                if (rest > 0) {
+                    double* A13 = A + j + (i64)(jn + w1) * lda;
+                    laswp(su, rest, A + (i64)(jn + w1) * lda, lda, j + 1, jn, piv, 1);
+                    trsm(su, 'L', 'L', 'N', 'U', jb, rest, 1.0, Ajj, lda, A13, lda);
+                    if (jn < m)
+                        gemm(su, 'N', 'N', m - jn, rest, jb, -1.0, A + jn + (i64)j * lda, lda, A13, lda, 1.0,
+                             A + jn + (i64)(jn + w1) * lda, lda);
+                }
+            }
+        }
+        // interchanges to the left of the panel (dgetrf.f:193)
+        if (j > 0) laswp(su, j, A, lda, j + 1, jn, piv, 1);
+    }
+    if (la) {
+        LB_CUDA_CHECK(cudaEventRecord(ev_join, su));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+        LB_CUDA_CHECK(cudaEventRecord(ev_next, sp));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_next, 0));
+    }
+}
+
+// DGETRS (SRC/dgetrs.f:181-218); argument checks live in the Fortran-ABI layer
+void getrs(cudaStream_t s, char trans, int n, int nrhs, const double* A, i64 lda, const int* ipiv, double* B, i64 ldb) {
+    if (n <= 0 || nrhs <= 0) return;
+    const bool notran = (trans == 'N' || trans == 'n');
+    if (notran) {
+        laswp_rows(s, nrhs, n, B, ldb, 1, n, ipiv, 1);
+        trsm(s, 'L', 'L', 'N', 'U', n, nrhs, 1.0, A, lda, B, ldb);
+        trsm(s, 'L', 'U', 'N', 'N', n, nrhs, 1.0, A, lda, B, ldb);
+    } else {
+        trsm(s, 'L', 'U', 'T', 'N', n, nrhs, 1.0, A, lda, B, ldb);
+        trsm(s, 'L', 'L', 'T', 'U', n, nrhs, 1.0, A, lda, B, ldb);
+        laswp_rows(s, nrhs, n, B, ldb, 1, n, ipiv, -1);
+    }
+}
+
+}  // namespace lb

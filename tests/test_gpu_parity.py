@@ -1,0 +1,445 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): IPIV bit-exact on random well-conditioned matrices; LAPACK TESTING/LIN residual
+ratios < 30 (TESTING/dtest.in:13); solutions within 1e-10 relative of the oracle's; BLAS results within the
+BLAS/TESTING/dblat3.in threshold of 16 (ratio |err| / (eps * sum|a||b|)).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+SEED = (1988, 1989, 1990, 1991)
+EPS = 2.0 ** -53
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import lapack_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    lapack_b200.lib().lb200_set_xerbla_mode(2)
+    return lapack_b200
+
+
+def rel(x, y):
+    s = max(1e-300, float(np.max(np.abs(y)))) if y.size else 1.0
+    return float(np.max(np.abs(x - y))) / s if x.size else 0.0
+
+
+def dev_to_np(t):
+    return np.asfortranarray(t.cpu().numpy())
+
+
+def np_to_dev(lb, a):
+    t = lb.dev.colmajor(a.shape[0], a.shape[1])
+    t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+    return t
+
+
+# ------------------------------------------------------------------------------------------- generator
+def test_larnv_bit_exact(lb):
+    for (m, n, off) in ((1000, 37, 0), (129, 5, 12345), (1, 1, 7), (64, 64, 2 ** 33 + 5)):
+        a = lb.dev.larnv_matrix(m, n, SEED, off)
+        x, _ = O.dlarnv(2, SEED, off + m * n) if off < 10 ** 6 else (None, None)
+        got = dev_to_np(a)
+        if x is not None:
+            want = np.asfortranarray(x[off:].reshape((n, m)).T)
+            assert np.array_equal(got, want)
+        else:
+            assert np.all(np.abs(got) <= 1.0) and len(np.unique(got)) == got.size
+
+
+def test_spd_generator(lb):
+    n = 300
+    a = lb.dev.larnv_matrix(n, n, SEED)
+    lb.dev.make_spd(a, float(n))
+    want, _ = O.spd_matrix(n, SEED)
+    assert np.array_equal(dev_to_np(a), want)
+
+
+# ------------------------------------------------------------------------------------------- BLAS 3
+@pytest.mark.parametrize("ta", "NT")
+@pytest.mark.parametrize("tb", "NT")
+def test_dgemm_vs_oracle(lb, ta, tb):
+    rng = np.random.default_rng(5)
+    for (m, n, k, alpha, beta) in ((9, 5, 3, 0.7, 1.3), (130, 67, 45, -1.0, 1.0), (64, 64, 200, 1.0, 0.0), (5, 9, 0, 1.0, 0.7),
+                                   (33, 1, 17, 0.0, 1.3), (257, 129, 64, -1.0, 1.0)):
+        a = np.asfortranarray(rng.uniform(-1, 1, (m, k) if ta == "N" else (k, m)))
+        b = np.asfortranarray(rng.uniform(-1, 1, (k, n) if tb == "N" else (n, k)))
+        c = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+        want = c.copy(order="F")
+        O.dgemm(ta, tb, m, n, k, alpha, a if a.size else np.zeros((1, 1), order="F"), b if b.size else np.zeros((1, 1), order="F"), beta, want)
+        got = c.copy(order="F")
+        lda = max(1, a.shape[0])
+        ldb = max(1, b.shape[0])
+        lb.f77.dgemm(ta, tb, m, n, k, alpha, a if a.size else np.zeros(1), lda, b if b.size else np.zeros(1), ldb, beta, got, m)
+        opa = np.abs(a if ta == "N" else a.T)
+        opb = np.abs(b if tb == "N" else b.T)
+        g = abs(alpha) * (opa @ opb if k else 0.0) + abs(beta) * np.abs(c) + 1e-300
+        assert np.max(np.abs(got - want) / g) / EPS < 16.0
+
+
+def test_dsyrk_triangle_only(lb):
+    rng = np.random.default_rng(6)
+    for uplo in "LU":
+        for tr in "NT":
+            n, k = 77, 40
+            a = np.asfortranarray(rng.uniform(-1, 1, (n, k) if tr == "N" else (k, n)))
+            c = np.asfortranarray(rng.uniform(-1, 1, (n + 1, n)))      # ld = n+1 like dblat3
+            want = c.copy(order="F")
+            O.dsyrk(uplo, tr, n, k, -1.0, a, 1.0, want[:n, :])
+            got = c.copy(order="F")
+            lb.f77.dsyrk(uplo, tr, n, k, -1.0, a, a.shape[0], 1.0, got, n + 1)
+            assert rel(got[:n], want[:n]) < 1e-13
+            other = np.triu(np.ones((n, n), bool), 1) if uplo == "L" else np.tril(np.ones((n, n), bool), -1)
+            assert np.array_equal(got[:n][other], c[:n][other])          # other triangle untouched
+            assert np.array_equal(got[n], c[n])                          # padding row untouched
+
+
+@pytest.mark.parametrize("side", "LR")
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("trans", "NT")
+@pytest.mark.parametrize("diag", "NU")
+def test_dtrsm_dtrmm_vs_oracle(lb, side, uplo, trans, diag):
+    rng = np.random.default_rng(7)
+    for (m, n) in ((1, 1), (5, 9), (33, 70), (130, 45), (70, 200)):
+        na = m if side == "L" else n
+        a = np.asfortranarray(rng.uniform(-1, 1, (na, na)) + na * np.eye(na) * 0.5)
+        b = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+        for alpha in (1.0, 0.7):
+            want = b.copy(order="F")
+            O.dtrsm(side, uplo, trans, diag, m, n, alpha, a, want)
+            got = b.copy(order="F")
+            lb.f77.dtrsm(side, uplo, trans, diag, m, n, alpha, a, na, got, m)
+            assert rel(got, want) < 1e-11, ("trsm", m, n, alpha)
+            want = b.copy(order="F")
+            O.dtrmm(side, uplo, trans, diag, m, n, alpha, a, want)
+            got = b.copy(order="F")
+            lb.f77.dtrmm(side, uplo, trans, diag, m, n, alpha, a, na, got, m)
+            assert rel(got, want) < 1e-13, ("trmm", m, n, alpha)
+
+
+def test_dlaswp_vs_oracle(lb):
+    rng = np.random.default_rng(8)
+    m, n = 60, 45
+    a = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+    ipiv = np.array([rng.integers(i + 1, m + 1) for i in range(20)], dtype=np.int32)
+    for incx in (1, -1):
+        for (k1, k2) in ((1, 20), (3, 11), (7, 7)):
+            want = a.copy(order="F")
+            O.dlaswp(want, k1, k2, ipiv, incx)
+            got = a.copy(order="F")
+            lb.f77.dlaswp(n, got, m, k1, k2, ipiv, incx)
+            assert np.array_equal(got, want), (incx, k1, k2)
+
+
+# ------------------------------------------------------------------------------------------- LU
+LU_SHAPES = [(1, 1), (1, 5), (9, 1), (5, 3), (3, 5), (16, 16), (17, 17), (50, 50), (100, 37), (37, 100), (300, 300),
+             (1100, 260), (1500, 1500), (2100, 700)]
+
+
+@pytest.mark.parametrize("shape", LU_SHAPES)
+@pytest.mark.parametrize("recursive", [False, True])
+def test_dgetrf_ipiv_and_residual(lb, shape, recursive):
+    m, n = shape
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    ipiv_ref, info_ref = O.dgetrf(ref) if not recursive else O.dgetrf2(ref)
+    got = a.copy(order="F")
+    ipiv, info = lb.f77.getrf(got, recursive)
+    assert info == info_ref == 0
+    assert np.array_equal(ipiv, ipiv_ref)                         # IPIV bit-exact
+    assert rel(got, ref) < 1e-10
+    assert O.dget01(a, got, ipiv) < O.THRESH
+
+
+@pytest.mark.parametrize("nb,la", [(16, 0), (16, 1), (32, 1), (64, 1), (128, 0), (128, 1)])
+def test_dgetrf_blocked_lookahead(lb, nb, la):
+    """Force the blocked right-looking driver (with and without look-ahead streams) at test sizes."""
+    L = lb.lib()
+    L.lb200_set_getrf_params(nb, 0, la)
+    try:
+        for (m, n) in ((300, 300), (700, 450), (450, 700), (1300, 1300)):
+            a, _ = O.random_matrix(m, n, SEED)
+            ref = a.copy(order="F")
+            ipiv_ref, _ = O.dgetrf(ref)
+            got = a.copy(order="F")
+            ipiv, info = lb.f77.getrf(got)
+            assert info == 0
+            assert np.array_equal(ipiv, ipiv_ref), (m, n)
+            assert O.dget01(a, got, ipiv) < O.THRESH
+            assert rel(got, ref) < 1e-10
+    finally:
+        L.lb200_set_getrf_params(512, 0, 1)
+
+
+def test_dgetrf_singular_info(lb):
+    """TESTING/LIN/dchkge.f:328-347: zero a column -> INFO = that column, factorization completes."""
+    n = 120
+    a, _ = O.random_matrix(n, n, SEED)
+    for izero in (1, n, n // 2 + 1):
+        b = a.copy(order="F")
+        b[:, izero - 1] = 0.0
+        ref = b.copy(order="F")
+        ipiv_ref, info_ref = O.dgetrf(ref)
+        got = b.copy(order="F")
+        ipiv, info = lb.f77.getrf(got)
+        assert info == info_ref == izero
+        assert np.array_equal(ipiv, ipiv_ref)
+        assert O.dget01(b, got, ipiv) < O.THRESH
+    b = a.copy(order="F")
+    b[:, n // 2:] = 0.0                                            # type 7: last half zero
+    ref = b.copy(order="F")
+    ipiv_ref, info_ref = O.dgetrf(ref)
+    got = b.copy(order="F")
+    ipiv, info = lb.f77.getrf(got)
+    assert info == info_ref == n // 2 + 1
+    assert np.array_equal(ipiv, ipiv_ref)
+
+
+def test_dgetrf_tiny_pivot_and_lda(lb):
+    """|pivot| < SFMIN takes the divide branch (dgetrf2.f:207-209); lda > m leaves the padding untouched."""
+    m, n, lda = 40, 30, 47
+    a, _ = O.random_matrix(m, n, SEED)
+    a[:, 0] *= 1e-310
+    buf = np.full((lda, n), -1.0e10, order="F")
+    buf[:m] = a
+    ref = a.copy(order="F")
+    ipiv_ref, _ = O.dgetrf(ref)
+    ipiv = np.zeros(n, dtype=np.int32)
+    info = lb.f77.dgetrf(m, n, buf, lda, ipiv)
+    assert info == 0 and np.array_equal(ipiv, ipiv_ref)
+    assert rel(buf[:m], ref) < 1e-10
+    assert np.all(buf[m:] == -1.0e10)
+
+
+def test_dgesv_dgetrs_solution(lb):
+    for (n, nrhs) in ((1, 1), (33, 2), (200, 1), (777, 15), (1500, 3)):
+        a, seed = O.random_matrix(n, n, SEED)
+        xact, _ = O.random_matrix(n, nrhs, seed)
+        b = np.asfortranarray(a @ xact)
+        lu_ref, x_ref = a.copy(order="F"), b.copy(order="F")
+        ipiv_ref, info_ref = O.dgesv(lu_ref, x_ref)
+        lu, x = a.copy(order="F"), b.copy(order="F")
+        ipiv, info = lb.f77.gesv(lu, x)
+        assert info == info_ref == 0
+        assert np.array_equal(ipiv, ipiv_ref)
+        assert rel(x, x_ref) < 1e-10                               # within 1e-10 relative of the reference solution
+        assert O.dget02("N", a, x, b) < O.THRESH
+        xt_ref = b.copy(order="F")
+        O.dgetrs("T", lu_ref, ipiv_ref, xt_ref)
+        xt = b.copy(order="F")
+        assert lb.f77.getrs("T", lu, ipiv, xt) == 0
+        assert rel(xt, xt_ref) < 1e-9
+        assert O.dget02("T", a, xt, b) < O.THRESH
+
+
+# ------------------------------------------------------------------------------------------- Cholesky
+@pytest.mark.parametrize("uplo", "LU")
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 100, 513, 1400])
+@pytest.mark.parametrize("recursive", [False, True])
+def test_dpotrf_vs_oracle(lb, uplo, n, recursive):
+    s, _ = O.spd_matrix(n, SEED)
+    rogue = s.copy(order="F")
+    mask = np.triu(np.ones((n, n), bool), 1) if uplo == "L" else np.tril(np.ones((n, n), bool), -1)
+    rogue[mask] = -1.0e10                                          # the other triangle must not be referenced
+    ref = rogue.copy(order="F")
+    assert (O.dpotrf2(uplo, ref) if recursive else O.dpotrf(uplo, ref)) == 0
+    got = rogue.copy(order="F")
+    assert lb.f77.potrf(uplo, got, recursive) == 0
+    assert np.all(got[mask] == -1.0e10)
+    tri = np.tril if uplo == "L" else np.triu
+    assert rel(tri(got), tri(ref)) < 1e-12
+    assert O.dpot01(uplo, s, got) < O.THRESH
+
+
+@pytest.mark.parametrize("nb,la", [(32, 0), (32, 1), (64, 1), (128, 1)])
+def test_dpotrf_blocked_lookahead(lb, nb, la):
+    L = lb.lib()
+    L.lb200_set_potrf_params(nb, la)
+    try:
+        for uplo in "LU":
+            for n in (200, 333, 1025):
+                s, _ = O.spd_matrix(n, SEED)
+                got = s.copy(order="F")
+                assert lb.f77.potrf(uplo, got) == 0
+                assert O.dpot01(uplo, s, got) < O.THRESH
+                ref = s.copy(order="F")
+                O.dpotrf(uplo, ref)
+                tri = np.tril if uplo == "L" else np.triu
+                assert rel(tri(got), tri(ref)) < 1e-12
+    finally:
+        L.lb200_set_potrf_params(512, 1)
+
+
+def test_dpotrf_not_positive_definite(lb):
+    """TESTING/LIN/dchkpo.f:313-344: zero row+column IZERO -> INFO = IZERO."""
+    n = 150
+    s, _ = O.spd_matrix(n, SEED)
+    for uplo in "LU":
+        for izero in (1, n, n // 2 + 1):
+            b = s.copy(order="F")
+            b[izero - 1, :] = 0.0
+            b[:, izero - 1] = 0.0
+            ref = b.copy(order="F")
+            info_ref = O.dpotrf(uplo, ref)
+            got = b.copy(order="F")
+            assert lb.f77.potrf(uplo, got) == info_ref == izero
+    b = s.copy(order="F")
+    b[40, 40] = np.nan
+    assert lb.f77.potrf("L", b.copy(order="F")) == 41              # NaN on the diagonal (dpotrf2.f:169)
+
+
+def test_dposv_dpotrs_solution(lb):
+    for uplo in "LU":
+        for (n, nrhs) in ((1, 1), (150, 3), (900, 1)):
+            s, seed = O.spd_matrix(n, SEED)
+            xact, _ = O.random_matrix(n, nrhs, seed)
+            b = np.asfortranarray(s @ xact)
+            f_ref, x_ref = s.copy(order="F"), b.copy(order="F")
+            assert O.dposv(uplo, f_ref, x_ref) == 0
+            f, x = s.copy(order="F"), b.copy(order="F")
+            assert lb.f77.posv(uplo, f, x) == 0
+            assert rel(x, x_ref) < 1e-10
+            assert O.dpot02(uplo, s, x, b) < O.THRESH
+            x2 = b.copy(order="F")
+            assert lb.f77.potrs(uplo, f, x2) == 0
+            assert rel(x2, x_ref) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------- QR
+QR_SHAPES = [(1, 1), (5, 3), (3, 5), (16, 16), (17, 40), (90, 40), (50, 50), (30, 45), (300, 200), (1100, 300), (2100, 2100)]
+
+
+@pytest.mark.parametrize("shape", QR_SHAPES)
+def test_dgeqrf_vs_oracle(lb, shape):
+    m, n = shape
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    tau_ref, info_ref, _ = O.dgeqrf(ref)
+    got = a.copy(order="F")
+    tau, info, w1 = lb.f77.geqrf(got)
+    assert info == 0
+    assert rel(got, ref) < 1e-10
+    assert rel(tau, tau_ref) < 1e-10
+    if m <= 1200:
+        res = O.dqrt01(a, got, tau)
+        assert res[0] < O.THRESH and res[1] < O.THRESH
+
+
+def test_dgeqrf_workspace_protocol(lb):
+    """LWORK=-1 query returns N*NB (dgeqrf.f:197-204); LWORK < N is argument 7."""
+    m, n = 200, 150
+    a, _ = O.random_matrix(m, n, SEED)
+    tau = np.zeros(n)
+    wq = np.zeros(1)
+    assert lb.f77.dgeqrf(m, n, a, m, tau, wq, -1) == 0 and wq[0] == n * 32
+    assert lb.f77.dgeqrf(m, n, a, m, tau, np.zeros(10), 10) == -7
+
+
+def test_dgeqrf_scaled_inputs(lb):
+    """Near-overflow / near-underflow scalings (dlatb4.f QR types 7-8) must not break the fused norm reduction."""
+    m, n = 120, 80
+    a, _ = O.random_matrix(m, n, SEED)
+    for scale in (1e292, 1e-292):
+        b = np.asfortranarray(a * scale)
+        got = b.copy(order="F")
+        tau, info, _ = lb.f77.geqrf(got)
+        assert info == 0 and np.all(np.isfinite(got))
+        res = O.dqrt01(b, got, tau)
+        assert res[0] < O.THRESH and res[1] < O.THRESH
+
+
+def test_dlarft_dlarfb_vs_oracle(lb):
+    for (m, k, n) in ((90, 40, 17), (300, 100, 64), (64, 64, 10)):
+        a, seed = O.random_matrix(m, k, SEED)
+        tau, _ = O.dgeqr2(a)
+        t_ref = O.dlarft(a, tau)
+        t = lb.f77.larft(a, tau)
+        assert rel(np.triu(t), np.triu(t_ref)) < 1e-11
+        c0, _ = O.random_matrix(m, n, seed)
+        for trans in "TN":
+            want = c0.copy(order="F")
+            O.dlarfb("L", trans, a, t_ref, want)
+            got = c0.copy(order="F")
+            lb.f77.larfb("L", trans, a, t_ref, got)
+            assert rel(got, want) < 1e-11
+        c1 = np.asfortranarray(c0.T.copy())
+        for trans in "TN":
+            want = c1.copy(order="F")
+            O.dlarfb("R", trans, a, t_ref, want)
+            got = c1.copy(order="F")
+            lb.f77.larfb("R", trans, a, t_ref, got)
+            assert rel(got, want) < 1e-11
+
+
+# ------------------------------------------------------------------------------------------- batched 32x32
+def test_batched_getrf32(lb):
+    batch = 3000
+    a = lb.dev.larnv_matrix(32, 32 * batch, SEED)                  # column-major 32 x (32*batch) == batch matrices
+    a_np = dev_to_np(a).copy()
+    mats = a.t().contiguous().view(batch, 32, 32)                  # [b][col][row]
+    # make a few matrices singular / tiny
+    mats[5, 3, :] = 0.0
+    mats[6, :, :] = 0.0
+    mats[7, 0, :] *= 1e-310
+    ref_in = mats.cpu().numpy().copy()
+    ipiv, info = lb.dev.getrf_batched32(mats)
+    torch.cuda.synchronize()
+    out = mats.cpu().numpy()
+    ipiv = ipiv.cpu().numpy()
+    info = info.cpu().numpy()
+    for b in list(range(0, 40)) + list(range(batch - 20, batch)):
+        x = np.asfortranarray(ref_in[b].T)
+        r = x.copy(order="F")
+        ipiv_ref, info_ref = O.dgetrf2(r)
+        assert info[b] == info_ref, b
+        assert np.array_equal(ipiv[b], ipiv_ref), b
+        assert rel(out[b].T, r) < 1e-12, b
+        if info_ref == 0:
+            assert O.dget01(x, np.asfortranarray(out[b].T), ipiv[b]) < O.THRESH
+    assert a_np.shape == (32, 32 * batch)
+
+
+def test_batched_potrf32(lb):
+    batch = 1000
+    a = lb.dev.larnv_matrix(32, 32 * batch, SEED)
+    mats = a.t().contiguous().view(batch, 32, 32)
+    mats.copy_((mats + mats.transpose(1, 2)) * 0.5 + 32.0 * torch.eye(32, device=mats.device, dtype=mats.dtype))
+    mats[3, 10, 10] = -1.0
+    ref_in = mats.cpu().numpy().copy()
+    for uplo in "LU":
+        work = mats.clone()
+        info = lb.dev.potrf_batched32(uplo, work).cpu().numpy()
+        out = work.cpu().numpy()
+        for b in range(0, 30):
+            x = np.asfortranarray(ref_in[b].T)
+            r = x.copy(order="F")
+            info_ref = O.dpotrf2(uplo, r)
+            assert info[b] == info_ref, (uplo, b)
+            if info_ref == 0:
+                tri = np.tril if uplo == "L" else np.triu
+                assert rel(tri(out[b].T), tri(r)) < 1e-13
+                assert O.dpot01(uplo, x, np.asfortranarray(out[b].T)) < O.THRESH
+
+
+# ------------------------------------------------------------------------------------------- device-pointer API
+def test_device_api_getrf_getrs(lb):
+    n = 1000
+    a = lb.dev.larnv_matrix(n, n, SEED)
+    a0 = dev_to_np(a)
+    want, _ = O.random_matrix(n, n, SEED)
+    assert np.array_equal(a0, want)
+    ipiv, info = lb.dev.getrf(a)
+    ref = want.copy(order="F")
+    ipiv_ref, _ = O.dgetrf(ref)
+    assert int(info.item()) == 0
+    assert np.array_equal(ipiv.cpu().numpy(), ipiv_ref)
+    b = lb.dev.larnv_matrix(n, 2, SEED, offset=n * n)
+    b0 = dev_to_np(b)
+    lb.dev.getrs("N", a, ipiv, b)
+    assert O.dget02("N", want, dev_to_np(b), b0) < O.THRESH
