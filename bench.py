@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of lapack_b200 (contract: see the task statement / DESIGN.md section 6).
+
+Metric (BASELINE.json): DGETRF/DPOTRF FP64 TFLOP/s on one B200 at n=32768.
+One "step" = BASELINE configs[1] + configs[2] back to back on synthetic DLARNV(2) inputs:
+    DPOTRF('L') + DPOTRS (1 RHS) of the n x n SPD matrix, then DGETRF of the n x n U(-1,1) matrix.
+`value`  : algorithmic flops of the step / device time, inputs resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same step through the Fortran-77 ABI (dpotrf_/dpotrs_/dgetrf_) with pinned HOST buffers, i.e.
+           H2D + factorization + D2H inside the timed region (wall clock around the synchronous calls).
+`roofline`: the dominant kernel = trailing-update DMMA GEMM; achieved = its algorithmic flops / its measured
+           launch durations (CUDA events on its own stream, recorded inside the timed region by the library).
+`cpu_baseline`: the reference algorithm (oracle port: NB=64 blocked DGETRF + reference BLAS loops), one thread,
+           on a bounded sample (DGESV, BASELINE configs[0] shape scaled to fit ~20 s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 32768] [--impl ours|reference]
+N>1 runs under torchrun: every rank factors its own matrices (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+SEED = (1988, 1989, 1990, 1991)
+EPS = 2.0 ** -53
+
+
+def flops_getrf(n):
+    return 2.0 * n ** 3 / 3 - n ** 2 / 2 + 5.0 * n / 6
+
+
+def flops_potrf(n):
+    return n ** 3 / 3 + n ** 2 / 2 + n / 6
+
+
+def flops_potrs(n, nrhs):
+    return 2.0 * n * n * nrhs
+
+
+def flops_getrs(n, nrhs):
+    return nrhs * (2.0 * n * n - n)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_sample(n, nrhs=1):
+    """One DGESV (DGETRF NB=64 + DGETRS) of the oracle port on an n x n DLARNV matrix; returns (seconds, flops)."""
+    import numpy as np
+    from oracle import oracle as O
+    a, seed = O.random_matrix(n, n, SEED)
+    xact, _ = O.random_matrix(n, nrhs, seed)
+    b = np.asfortranarray(a @ xact)
+    t0 = time.perf_counter()
+    ipiv, info = O.dgesv(a, b)
+    t = time.perf_counter() - t0
+    err = float(np.max(np.abs(b - xact)) / np.max(np.abs(xact)))
+    return t, flops_getrf(n) + flops_getrs(n, nrhs), info, err
+
+
+def pick_cpu_sample(budget_s, steps):
+    """Largest n in a fixed ladder whose estimated total time fits the budget (calibrated on n=768)."""
+    t, fl, _, _ = cpu_reference_sample(768)
+    rate = fl / t
+    for n in (4096, 3072, 2048, 1536, 1024):
+        if (flops_getrf(n) / rate) * steps <= budget_s:
+            return n
+    return 1024
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = args.steps + args.warmup
+    n = pick_cpu_sample(150.0, steps)
+    ts = []
+    fl = 0.0
+    for i in range(steps):
+        t, fl, info, err = cpu_reference_sample(n)
+        if i >= args.warmup:
+            ts.append(t)
+    tmean = sum(ts) / len(ts)
+    val = fl / tmean * 1e-12
+    sample = f"DGESV n={n} nrhs=1: reference DGETRF (NB=64, recursive DGETRF2 panel) + DGETRS on reference BLAS loops (oracle port), 1 thread"
+    line = {
+        "impl": "reference", "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"bounded CPU sample of the n={args.n} factorization workload: " + sample},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference Fortran cannot be compiled in this image (no Fortran compiler); the timed code is the line-faithful C port in oracle/",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- GPU leg
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import lapack_b200 as lb
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- lapack_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    L = lb.lib()
+    L.lb200_profile_gemm.argtypes = [C.c_int]
+    L.lb200_profile_gemm_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    nrhs = 1
+    # ---- synthetic inputs: U(-1,1) from DLARNV(2), seed 1988..1991; SPD = (R+R')/2 + n*I
+    a_lu0 = lb.dev.larnv_matrix(n, n, SEED, device=dev)
+    a_po0 = lb.dev.larnv_matrix(n, n, SEED, device=dev)
+    lb.dev.make_spd(a_po0, float(n))
+    xact = lb.dev.larnv_matrix(n, nrhs, SEED, offset=n * n, device=dev)
+    b_po0 = lb.dev.colmajor(n, nrhs, device=dev)
+    b_po0.copy_(a_po0 @ xact)   # B = S * XACT (like dlarhs.f:319)
+    a_lu = lb.dev.colmajor(n, n, device=dev)
+    a_po = lb.dev.colmajor(n, n, device=dev)
+    b_po = lb.dev.colmajor(n, nrhs, device=dev)
+    step_flops = flops_potrf(n) + flops_potrs(n, nrhs) + flops_getrf(n)
+
+    def step():
+        a_po.copy_(a_po0)
+        b_po.copy_(b_po0)
+        a_lu.copy_(a_lu0)
+        info_po = lb.dev.potrf("L", a_po)
+        lb.dev.potrs("L", a_po, b_po)
+        ipiv, info_lu = lb.dev.getrf(a_lu)
+        return info_po, ipiv, info_lu
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        info_po, ipiv, info_lu = step()
+    barrier()
+    # ---- correctness gates on the warm-up result (GPU-side independent products; checker only)
+    checks = {}
+    if rank == 0 and not args.no_check:
+        Lm = torch.tril(a_po)
+        r = Lm @ Lm.t()
+        r -= a_po0
+        r = torch.tril(r)
+        rn = (r.abs().sum(0) + r.abs().sum(1) - r.diagonal().abs()).max().item()
+        an = torch.tril(a_po0)
+        an1 = (an.abs().sum(0) + an.abs().sum(1) - an.diagonal().abs()).max().item()
+        checks["dpot01_ratio"] = rn / (n * an1 * EPS)
+        checks["posv_rel_err"] = ((b_po - xact).abs().max() / xact.abs().max()).item()
+        del Lm, r, an
+        Lm = torch.tril(a_lu, -1)
+        Lm.diagonal().fill_(1.0)
+        r = Lm @ torch.triu(a_lu)
+        del Lm
+        perm = list(range(n))
+        for i, p in enumerate((ipiv.long() - 1).cpu().tolist()):
+            if p != i:
+                perm[i], perm[p] = perm[p], perm[i]
+        r -= a_lu0[torch.tensor(perm, device=dev)]
+        checks["dget01_ratio"] = r.abs().sum(0).max().item() / (n * a_lu0.abs().sum(0).max().item() * EPS)
+        checks["info"] = [int(info_po.item()), int(info_lu.item())]
+        del r
+        torch.cuda.empty_cache()
+
+    # ---- timed region: device-resident
+    sampler = ClockSampler(local_rank)
+    launches0 = L.lb200_launch_count()
+    L.lb200_profile_gemm(1)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    L.lb200_profile_gemm(0)
+    ms = e0.elapsed_time(e1)
+    launches = int(L.lb200_launch_count() - launches0)
+    gms, gfl, gcnt = C.c_double(0), C.c_double(0), C.c_longlong(0)
+    L.lb200_profile_gemm_read(C.byref(gms), C.byref(gfl), C.byref(gcnt))
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * step_flops * args.steps / (ms * 1e-3) * 1e-12
+
+    # separate single-routine timings (informational)
+    def time_one(fn, restore):
+        restore()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        fn()
+        s1.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) * 1e-3
+    t_lu = time_one(lambda: lb.dev.getrf(a_lu), lambda: a_lu.copy_(a_lu0))
+    t_po = time_one(lambda: lb.dev.potrf("L", a_po), lambda: a_po.copy_(a_po0))
+    peak = max(L.lb200_fp64_peak_tflops(None, 0, 8, 2, 20000) for _ in range(2))
+
+    # ---- e2e: Fortran-77 ABI with pinned host buffers (H2D + compute + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+        h_lu = torch.empty((n, n), dtype=torch.float64).pin_memory()     # row-major (n,n) buffer == column-major n x n, ld = n
+        h_po = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        h_b = torch.empty((nrhs, n), dtype=torch.float64).pin_memory()
+        h_ipiv = np.zeros(n, dtype=np.int32)
+        ts = []
+        for i in range(args.steps + 1):
+            h_lu.copy_(a_lu0.t())       # a_lu0.t() is the contiguous (n,n) storage of the column-major matrix
+            h_po.copy_(a_po0.t())
+            h_b.copy_(b_po0.t())
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            i1 = lb.f77.dpotrf("L", n, h_po.data_ptr(), n)
+            i2 = lb.f77.dpotrs("L", n, nrhs, h_po.data_ptr(), n, h_b.data_ptr(), n)
+            i3 = lb.f77.dgetrf(n, n, h_lu.data_ptr(), n, h_ipiv)
+            dt = time.perf_counter() - t0
+            if i >= 1:
+                ts.append(dt)
+            assert i1 == 0 and i2 == 0 and i3 == 0, (i1, i2, i3)
+        te = torch.tensor([sum(ts) / len(ts)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ipiv_same = bool(np.array_equal(h_ipiv, ipiv.cpu().numpy()))
+        nb = n * n * 8
+        e2e = {"value": world * step_flops / te.item() * 1e-12, "unit": "TFLOP/s", "ms_per_step": te.item() * 1e3,
+               "h2d_bytes_per_step": 2 * nb + n * nrhs * 8, "d2h_bytes_per_step": 2 * nb + n * nrhs * 8 + n * 4,
+               "api": "dpotrf_/dpotrs_/dgetrf_ (Fortran-77 ABI) on pinned host buffers", "ipiv_equals_device_run": ipiv_same}
+        del h_lu, h_po, h_b
+
+    if rank != 0:
+        return
+    # ---- CPU baseline (oracle port, bounded sample), rank 0 only, N=1 only
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        ncpu = pick_cpu_sample(25.0, 1)
+        tc, fc, _, _ = cpu_reference_sample(ncpu)
+        cpu = {"value": fc / tc * 1e-12, "unit": "TFLOP/s", "cores": 1, "kind": "port", "seconds": tc,
+               "sample": f"DGESV n={ncpu} nrhs=1: reference DGETRF (NB=64) + DGETRS on reference BLAS loops (oracle port), 1 of {os.cpu_count()} host cores"}
+    gemm_tf = (gfl.value / (gms.value * 1e-3) * 1e-12) if gms.value > 0 else None
+    line = {
+        "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"per step: DPOTRF('L')+DPOTRS(1 rhs) n={n} SPD (BASELINE configs[1]) then DGETRF n={n} (configs[2]); "
+                               "DLARNV(2) seed 1988-1991; in-place, column-major",
+                   "n": n, "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (no data-path collective)",
+                   "l2": "inputs (8 GiB per matrix) are far larger than the 126 MB L2; restored from HBM copies every step"},
+        "pct_of_fp64_peak": value / world / peak if peak else None,
+        "breakdown": {"dgetrf_tflops": flops_getrf(n) / t_lu * 1e-12, "dgetrf_ms": t_lu * 1e3,
+                      "dpotrf_tflops": flops_potrf(n) / t_po * 1e-12, "dpotrf_ms": t_po * 1e3},
+        "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel / gemm_f64_dmma_kernel (trailing updates)",
+                     "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
+                     "traffic": None, "launches_timed": int(gcnt.value),
+                     "peak_source": "FP64 DMMA.8x8x4 issue-rate peak measured in this run by lb200_fp64_peak_tflops "
+                                    "(MEASURED_PEAKS.json carries HBM and bf16 only)"},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

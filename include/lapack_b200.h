@@ -25,8 +25,14 @@ void lb200_reset_launch_count(void);
 /* measured FP64 pipe peak (TFLOP/s): kind 0 = DMMA.8x8x4 issue rate, 1 = DFMA */
 double lb200_fp64_peak_tflops(void* stream, int kind, int warps_per_cta, int ctas_per_sm, int iters);
 
+/* per-launch CUDA-event timing of the large trailing-update GEMMs (used by bench.py's roofline leg):
+ * enable(1) resets the counters; read() returns the summed durations / algorithmic flops / launch count */
+void lb200_profile_gemm(int enable);
+void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* launches);
+
 /* tuning knobs (testing / benchmarking; defaults are chosen per problem size) */
-void lb200_set_gemm_config(int cfg);
+void lb200_set_gemm_config(int cfg);   /* -1 auto, 0/1/2 force a cp.async tile shape, 3 force the TMA kernel */
+void lb200_set_gemm_tma(int on);       /* 0 disables the TMA fast path (falls back to cp.async) */
 void lb200_set_getrf_params(int nb, int leaf, int lookahead);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);

@@ -17,6 +17,8 @@ NVCC_FLAGS.remove("--use_fast_math=false")   # never fast-math: FP64 parity
 
 def sources(minimal: bool = False):
     if minimal:
+        return ["gemm_f64.cu", "gemm_tma.cu", "runtime.cu", "capi.cu"]
+    if minimal:
         return ["gemm_f64.cu", "runtime.cu", "capi.cu"]
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 

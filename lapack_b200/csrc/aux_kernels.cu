@@ -59,18 +59,108 @@ __global__ void laswp_colsmem_kernel(int rows, double* __restrict__ A, i64 lda, 
     for (int i = threadIdx.x; i < rows; i += blockDim.x) a[i] = scol[i];
 }
 
+// Variant C (default for more than a handful of interchanges): the sequence of transpositions is first
+// composed into a list of independent moves (dst_row <- src_row) by one small CTA, then every column applies
+// that list with all loads in flight at once (gather into shared memory, barrier, scatter).  This removes the
+// dependent load->store->load chain of variant A (about one memory round trip per interchange).
+struct MoveList {
+    int count;
+    int pad;
+    int2 mv[1];   // (dst_row, src_row), 0-based
+};
+
+__global__ void laswp_build_kernel(int np, int k1, int k2, const int* __restrict__ ipiv, int incx, MoveList* out) {
+    extern __shared__ int sm[];
+    int* piv = sm;              // [np]   pivot row (1-based) of the t-th interchange in application order
+    int* slot = sm + np;        // [np]   slot of the pivot row: < np inside the block, >= np outside
+    int* idx = sm + 2 * np;     // [2np]  which original slot currently sits in each slot
+    int* rowof = sm + 4 * np;   // [2np]  global row (1-based) of each slot, 0 = unused
+    __shared__ int s_count;
+    const int ix0 = incx > 0 ? k1 : k1 + (k1 - k2) * incx;
+    for (int t = threadIdx.x; t < np; t += blockDim.x) piv[t] = ipiv[ix0 + t * incx - 1];
+    for (int q = threadIdx.x; q < 2 * np; q += blockDim.x) { idx[q] = q; rowof[q] = (q < np) ? k1 + q : 0; }
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < np; t += blockDim.x) {
+        int ip = piv[t];
+        int sl;
+        if (ip >= k1 && ip <= k2) sl = ip - k1;
+        else {
+            int first = t;
+            for (int u = 0; u < t; ++u)
+                if (piv[u] == ip) { first = u; break; }
+            sl = np + first;
+            if (first == t) rowof[sl] = ip;
+        }
+        slot[t] = sl;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < np; ++t) {
+            int i = incx > 0 ? k1 + t : k2 - t;     // row being interchanged at step t
+            int a = i - k1, b = slot[t];
+            int tmp = idx[a]; idx[a] = idx[b]; idx[b] = tmp;
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * np; q += blockDim.x) {
+        if (rowof[q] != 0 && idx[q] != q) {
+            int pos = atomicAdd(&s_count, 1);
+            out->mv[pos] = make_int2(rowof[q] - 1, rowof[idx[q]] - 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out->count = s_count;
+}
+
+constexpr int LASWP_CW = 4;   // columns per CTA in the apply kernel
+__global__ void __launch_bounds__(256) laswp_apply_kernel(int n, double* __restrict__ A, i64 lda, const MoveList* __restrict__ ml) {
+    extern __shared__ double sval[];
+    const int cnt = ml->count;
+    if (cnt == 0) return;
+    const int c0 = blockIdx.x * LASWP_CW;
+    const int nc = min(LASWP_CW, n - c0);
+    const int total = cnt * nc;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        int c = q / cnt, mvi = q - c * cnt;
+        sval[q] = A[(i64)(c0 + c) * lda + ml->mv[mvi].y];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        int c = q / cnt, mvi = q - c * cnt;
+        A[(i64)(c0 + c) * lda + ml->mv[mvi].x] = sval[q];
+    }
+}
+
 // max row touched must be known for variant B; the caller passes `rows_hint` (0 = unknown)
 static void laswp_impl(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx,
                        int rows_hint) {
     if (n <= 0 || incx == 0 || k2 < k1) return;
-    if (n <= 32 && rows_hint > 0 && (size_t)rows_hint * 8 <= 200 * 1024) {
+    (void)rows_hint;
+    const int np_all = k2 - k1 + 1;
+    if (np_all >= 4) {
+        // process in chunks of at most 2048 interchanges (shared-memory bound of the build kernel)
+        const int abs_inc = incx > 0 ? incx : -incx;
         static bool attr = false;
         if (!attr) {
-            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_colsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * LASWP_MAX_PIV * 4));
+            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               2 * LASWP_MAX_PIV * LASWP_CW * 8));
             attr = true;
         }
-        laswp_colsmem_kernel<<<n, 512, (size_t)rows_hint * 8, s>>>(rows_hint, A, lda, k1, k2, ipiv, incx);
-        count_launch();
+        for (int done = 0; done < np_all; done += LASWP_MAX_PIV) {
+            int cnt = min(LASWP_MAX_PIV, np_all - done);
+            int ck1, ck2;
+            const int* cpiv;
+            if (incx > 0) { ck1 = k1 + done; ck2 = ck1 + cnt - 1; cpiv = ipiv + (i64)(ck1 - k1) * (incx - 1); }
+            else { ck2 = k2 - done; ck1 = ck2 - cnt + 1; cpiv = ipiv + (i64)(k1 - ck1) + (i64)(k2 - ck2) * abs_inc; }
+            MoveList* ml = (MoveList*)ws_alloc(s, sizeof(MoveList) + sizeof(int2) * 2 * cnt);
+            laswp_build_kernel<<<1, 256, (size_t)6 * cnt * sizeof(int), s>>>(cnt, ck1, ck2, cpiv, incx, ml);
+            laswp_apply_kernel<<<ceil_div(n, LASWP_CW), 256, (size_t)2 * cnt * LASWP_CW * sizeof(double), s>>>(n, A, lda, ml);
+            count_launch(2);
+            ws_free(s, ml);
+        }
+        LB_CUDA_CHECK(cudaGetLastError());
         return;
     }
     // chunk the pivot list so that it fits in shared memory, preserving the application order
@@ -97,6 +187,29 @@ static void laswp_impl(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2
 void laswp(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx) {
     laswp_impl(s, n, A, lda, k1, k2, ipiv, incx, 0);
 }
+// Plan once, apply to several column ranges (the blocked LU driver applies one panel's interchanges to the
+// look-ahead slab, the rest of the trailing matrix and the columns on the left).  k2-k1+1 <= LASWP_MAX_PIV.
+void* laswp_plan(cudaStream_t s, int k1, int k2, const int* ipiv, int incx) {
+    const int cnt = k2 - k1 + 1;
+    if (cnt <= 0 || cnt > LASWP_MAX_PIV) return nullptr;
+    static bool attr = false;
+    if (!attr) {
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * LASWP_MAX_PIV * 4));
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           2 * LASWP_MAX_PIV * LASWP_CW * 8));
+        attr = true;
+    }
+    MoveList* ml = (MoveList*)ws_alloc(s, sizeof(MoveList) + sizeof(int2) * 2 * cnt);
+    laswp_build_kernel<<<1, 256, (size_t)6 * cnt * sizeof(int), s>>>(cnt, k1, k2, ipiv, incx, ml);
+    count_launch();
+    return ml;
+}
+void laswp_apply_plan(cudaStream_t s, int n, double* A, i64 lda, const void* plan, int npiv) {
+    if (n <= 0 || !plan) return;
+    laswp_apply_kernel<<<ceil_div(n, LASWP_CW), 256, (size_t)2 * npiv * LASWP_CW * sizeof(double), s>>>(n, A, lda, (const MoveList*)plan);
+    count_launch();
+}
+void laswp_plan_free(cudaStream_t s, void* plan) { ws_free(s, plan); }
 // variant with a known row extent (all pivots < rows): lets few-column calls use the staged kernel
 void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx) {
     laswp_impl(s, n, A, lda, k1, k2, ipiv, incx, rows);

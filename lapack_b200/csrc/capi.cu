@@ -9,6 +9,9 @@
 namespace lb {
 double fp64_peak(cudaStream_t s, int kind, int warps_per_cta, int ctas_per_sm, int iters);
 void gemm_set_config(int cfg);
+void gemm_set_tma(int on);
+void gemm_profile(int enable);
+void gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 void getrf_set_params(int nb, int leaf, int lookahead);
 void potrf_set_params(int nb, int lookahead);
 void geqrf_set_params(int nb, int lookahead);
@@ -32,6 +35,11 @@ double lb200_fp64_peak_tflops(void* stream, int kind, int warps_per_cta, int cta
     return lb::fp64_peak(S(stream), kind, warps_per_cta, ctas_per_sm, iters);
 }
 void lb200_set_gemm_config(int cfg) { lb::gemm_set_config(cfg); }
+void lb200_set_gemm_tma(int on) { lb::gemm_set_tma(on); }
+void lb200_profile_gemm(int enable) { lb::gemm_profile(enable); }
+void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* launches) {
+    lb::gemm_profile_read(total_ms, total_flops, launches);
+}
 #ifndef LB_MINIMAL
 void lb200_set_getrf_params(int nb, int leaf, int lookahead) { lb::getrf_set_params(nb, leaf, lookahead); }
 void lb200_set_potrf_params(int nb, int lookahead) { lb::potrf_set_params(nb, lookahead); }

@@ -15,6 +15,7 @@
 // Roofline: 2*M*N*K flops per launch against the FP64 DMMA peak; minimum HBM traffic
 // 8*(2*M*N + M*K + K*N) bytes.
 #include "lb_internal.h"
+#include <vector>
 
 namespace lb {
 
@@ -333,9 +334,54 @@ static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const Gemm
 }
 
 void gemm_set_config(int cfg) { g_gemm_cfg = cfg; }
+bool gemm_tma_try(cudaStream_t s, bool a_k, bool b_k, int m, int n, int k, double alpha, const double* A, i64 lda,
+                  const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri);
+
+// ---- optional per-launch timing of the large GEMMs (bench.py's roofline leg) ----------------------
+struct GemmProf {
+    bool on = false;
+    std::vector<cudaEvent_t> e0, e1;
+    std::vector<double> flops;
+    size_t used = 0;
+};
+static GemmProf g_prof;
+void gemm_profile(int enable) {
+    g_prof.on = enable != 0;
+    if (enable) g_prof.used = 0;
+}
+void gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+    double ms = 0.0, fl = 0.0;
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        float t = 0.f;
+        cudaEventSynchronize(g_prof.e1[i]);
+        if (cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]) == cudaSuccess) { ms += t; fl += g_prof.flops[i]; }
+    }
+    *total_ms = ms; *total_flops = fl; *launches = (long long)g_prof.used;
+}
+static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, int k, double alpha, const double* A, i64 lda,
+                      const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri);
 
 void gemm(cudaStream_t s, char transa, char transb, int m, int n, int k, double alpha, const double* A, i64 lda,
           const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri) {
+    double fl = 2.0 * m * n * (double)k * (tri ? 0.5 : 1.0);
+    bool prof = g_prof.on && fl >= 2e9 && g_prof.used < 16384;
+    size_t idx = 0;
+    if (prof) {
+        idx = g_prof.used++;
+        if (idx >= g_prof.e0.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            g_prof.e0.push_back(a); g_prof.e1.push_back(b); g_prof.flops.push_back(0.0);
+        }
+        g_prof.flops[idx] = fl;
+        cudaEventRecord(g_prof.e0[idx], s);
+    }
+    gemm_impl(s, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri);
+    if (prof) cudaEventRecord(g_prof.e1[idx], s);
+}
+
+static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, int k, double alpha, const double* A, i64 lda,
+                      const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri) {
     if (m <= 0 || n <= 0) return;
     if (alpha == 0.0 || k <= 0) {
         if (beta == 1.0) return;
@@ -378,6 +424,14 @@ void gemm(cudaStream_t s, char transa, char transb, int m, int n, int k, double 
                 return;
             }
         }
+    }
+    if (cfg < 0 || cfg == 3) {
+        // large, aligned problems: persistent TMA-fed kernel (gemm_tma.cu)
+        i64 t128 = (i64)ceil_div(m, 128) * ceil_div(n, 128);
+        if ((t128 >= num_sms() || cfg == 3) && k >= 32 &&
+            gemm_tma_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri))
+            return;
+        if (cfg == 3) cfg = -1;
     }
     if (cfg < 0) {
         // enough 128x128 tiles to fill the machine -> big tile; otherwise smaller tiles for parallelism

@@ -25,6 +25,9 @@
 namespace lb {
 
 void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx);
+void* laswp_plan(cudaStream_t s, int k1, int k2, const int* ipiv, int incx);
+void laswp_apply_plan(cudaStream_t s, int n, double* A, i64 lda, const void* plan, int npiv);
+void laswp_plan_free(cudaStream_t s, void* plan);
 
 static int g_nb = 512, g_lookahead = 1;
 void getrf_set_params(int nb, int leaf, int lookahead) {
@@ -34,12 +37,17 @@ void getrf_set_params(int nb, int leaf, int lookahead) {
 }
 
 // ------------------------------------------------------------------------------------------------
-struct Cand {
-    double key;   // |a| used for selection (NaN handling folded in)
-    int row;      // panel-relative row, 0-based
-    int pad;
+// Leaf kernel communication.  No central barrier counter: every CTA publishes, per column step, a tagged
+// packet {tag = epoch<<32 | row, key, the 16 row values}; the tag is stored last with st.release and every
+// CTA polls all G tags with ld.acquire, so "barrier" and "data exchange" cost one L2 round trip together.
+// Packets are double-buffered on the step parity; a CTA can only overwrite slot (c&1) at step c+2 after it
+// has seen every step-(c+1) packet, i.e. after every other CTA finished reading step c.
+struct LeafPacket {
+    unsigned long long tag;
+    double key;
+    double rowdata[16];
+    double pad[14];                  // 256-byte stride
 };
-
 struct LeafParams {
     int m, n;
     double* A;
@@ -48,32 +56,30 @@ struct LeafParams {
     int* info;        // device word: first zero pivot (absolute, 1-based) -- written only if still 0
     int info_off;     // absolute column offset of this leaf
     double sfmin;
-    unsigned* bar;
-    unsigned bar_base;
-    Cand* cand;       // [2][G]
-    double* candrow;  // [2][G][W]
-    double* toprow;   // [2][W]
-    int G;
+    unsigned epoch_base;
+    LeafPacket* cand;       // [2][G]
+    LeafPacket* top;        // [2]     current row c (published by its owner)
+    unsigned long long* hist;   // [W]  winner of every step, tagged, for the swap CTAs
+    int G;            // work CTAs; CTAs >= G apply the interchanges to the other panel columns
+    double* SW;       // element (leaf top row, panel column 0)
+    int sw_left, sw_right;   // panel columns left / right of the leaf
 };
 
 __device__ __forceinline__ bool cand_better(double k1, int r1, double k2, int r2) {
     return (k1 > k2) || (k1 == k2 && r1 < r2);
 }
-
-__device__ __forceinline__ void leaf_grid_barrier(unsigned* bar, unsigned target, int G) {
-    __syncthreads();
-    if (G > 1) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            atomicAdd(bar, 1u);
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(bar) : "memory");
-            } while ((int)(v - target) < 0);
-            __threadfence();
-        }
-        __syncthreads();
-    }
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long poll_tag(const unsigned long long* p, unsigned epoch) {
+    unsigned long long v;
+    do { v = ld_acquire_u64(p); } while ((unsigned)(v >> 32) != epoch);
+    return v;
 }
 
 template <int W, int THREADS>
@@ -84,13 +90,34 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
     __shared__ double s_prow[W], s_trow[W];
     __shared__ int s_win_row;
     __shared__ int s_loc_row;
+    __shared__ double s_loc_key;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x;
-    const int row = g * THREADS + tid;          // panel-relative row owned by this thread
-    const bool have = row < p.m;
     const int kmax = min(p.m, p.n);
 
+    if (g >= p.G) {
+        // ===== interchange CTAs: one panel column per thread, follow the winner history (dgetrf2.f:236,263) =====
+        const int t = (g - p.G) * THREADS + tid;
+        const bool valid = t < p.sw_left + p.sw_right;
+        const int col = (t < p.sw_left) ? t : t + p.n;        // skip the leaf's own columns
+        double* colp = p.SW + (i64)col * p.lda;
+        for (int c = 0; c < kmax; ++c) {
+            unsigned long long v = 0;
+            if (lane == 0) v = poll_tag(p.hist + c, p.epoch_base + c + 1);
+            v = __shfl_sync(0xffffffffu, v, 0);
+            const int prow = (int)(unsigned)(v & 0xffffffffu);
+            if (valid && prow != c) {
+                double x = colp[c], y = colp[prow];
+                colp[c] = y;
+                colp[prow] = x;
+            }
+        }
+        return;
+    }
+
+    const int row = g * THREADS + tid;          // panel-relative row owned by this thread
+    const bool have = row < p.m;
     double a[W];
 #pragma unroll
     for (int c = 0; c < W; ++c) a[c] = (have && c < p.n) ? p.A[row + (i64)c * p.lda] : 0.0;
@@ -99,6 +126,14 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
     for (int c = 0; c < W; ++c) {
         if (c < kmax) {
             const int slot = c & 1;
+            const unsigned epoch = p.epoch_base + c + 1;
+            // (0) the owner of row c publishes the current top row
+            if (have && row == c) {
+                LeafPacket* tp = p.top + slot;
+#pragma unroll
+                for (int q = 0; q < W; ++q) tp->rowdata[q] = a[q];
+                st_release_u64(&tp->tag, ((unsigned long long)epoch << 32));
+            }
             // (1) local arg-max over active rows (row >= c); IDAMAX semantics: first index of the max,
             //     NaN never wins unless it is the very first element (idamax.f:103 strict '>').
             double key = -1.0;
@@ -126,34 +161,26 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
                     int orow = __shfl_xor_sync(0xffffffffu, r2, off);
                     if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; }
                 }
-                if (lane == 0) {
-                    s_loc_row = r2;
-                    Cand cd; cd.key = k2; cd.row = r2; cd.pad = 0;
-                    p.cand[slot * p.G + g] = cd;
-                }
+                if (lane == 0) { s_loc_row = r2; s_loc_key = k2; }
             }
             __syncthreads();
-            // (2) publish the local winner's row and (owner of row c) the current top row
+            // (2) the thread owning the CTA's best row publishes it (data first, tag last with release)
             if (have && row == s_loc_row) {
-                double* dst = p.candrow + ((i64)slot * p.G + g) * W;
+                LeafPacket* cp = p.cand + slot * p.G + g;
+                cp->key = s_loc_key;
 #pragma unroll
-                for (int q = 0; q < W; ++q) dst[q] = a[q];
+                for (int q = 0; q < W; ++q) cp->rowdata[q] = a[q];
+                st_release_u64(&cp->tag, ((unsigned long long)epoch << 32) | (unsigned)row);
             }
-            if (have && row == c) {
-                double* dst = p.toprow + slot * W;
-#pragma unroll
-                for (int q = 0; q < W; ++q) dst[q] = a[q];
-            }
-            // (3) one grid-wide barrier per column
-            leaf_grid_barrier(p.bar, p.bar_base + (unsigned)(c + 1) * (unsigned)p.G, p.G);
-            // (4) every CTA picks the global winner and fetches the two rows
+            // (3)+(4) warp 0 waits for all G packets, picks the winner and fetches the two rows
             if (warp == 0) {
                 double k2 = -2.0;
                 int r2 = 0x7fffffff, g2 = 0;
                 for (int q = lane; q < p.G; q += 32) {
-                    const Cand* cp = p.cand + slot * p.G + q;
+                    const LeafPacket* cp = p.cand + slot * p.G + q;
+                    unsigned long long tag = poll_tag(&cp->tag, epoch);
                     double ck = __ldcg(&cp->key);
-                    int cr = __ldcg(&cp->row);
+                    int cr = (int)(unsigned)(tag & 0xffffffffu);
                     if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
                 }
 #pragma unroll
@@ -164,10 +191,15 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
                     if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
                 }
                 if (lane < W) {
-                    s_prow[lane] = __ldcg(p.candrow + ((i64)slot * p.G + g2) * W + lane);
-                    s_trow[lane] = __ldcg(p.toprow + slot * W + lane);
+                    (void)poll_tag(&p.cand[slot * p.G + g2].tag, epoch);        // own acquire for the data below
+                    (void)poll_tag(&p.top[slot].tag, epoch);
+                    s_prow[lane] = __ldcg(&p.cand[slot * p.G + g2].rowdata[lane]);
+                    s_trow[lane] = __ldcg(&p.top[slot].rowdata[lane]);
                 }
-                if (lane == 0) s_win_row = r2;
+                if (lane == 0) {
+                    s_win_row = r2;
+                    if (g == 0) st_release_u64(p.hist + c, ((unsigned long long)epoch << 32) | (unsigned)r2);
+                }
             }
             __syncthreads();
             const int prow = s_win_row;
@@ -210,29 +242,37 @@ constexpr int LEAF_W = 16;
 constexpr int LEAF_THREADS = 1024;
 
 struct LeafWs {
-    unsigned* bar = nullptr;
-    unsigned base = 0;
-    Cand* cand = nullptr;
-    double* candrow = nullptr;
-    double* toprow = nullptr;
+    unsigned epoch = 0;
+    LeafPacket* cand = nullptr;
+    LeafPacket* top = nullptr;
+    unsigned long long* hist = nullptr;
     int maxG = 0;
 };
 static LeafWs& leaf_ws() {
     static LeafWs w;
-    if (!w.bar) {
-        w.maxG = 1024;
-        LB_CUDA_CHECK(cudaMalloc(&w.bar, 256));
-        LB_CUDA_CHECK(cudaMemset(w.bar, 0, 256));
-        LB_CUDA_CHECK(cudaMalloc(&w.cand, sizeof(Cand) * 2 * w.maxG));
-        LB_CUDA_CHECK(cudaMalloc(&w.candrow, sizeof(double) * 2 * w.maxG * LEAF_W));
-        LB_CUDA_CHECK(cudaMalloc(&w.toprow, sizeof(double) * 2 * LEAF_W));
+    if (!w.cand) {
+        w.maxG = 256;
+        LB_CUDA_CHECK(cudaMalloc(&w.cand, sizeof(LeafPacket) * 2 * w.maxG));
+        LB_CUDA_CHECK(cudaMemset(w.cand, 0, sizeof(LeafPacket) * 2 * w.maxG));
+        LB_CUDA_CHECK(cudaMalloc(&w.top, sizeof(LeafPacket) * 2));
+        LB_CUDA_CHECK(cudaMemset(w.top, 0, sizeof(LeafPacket) * 2));
+        LB_CUDA_CHECK(cudaMalloc(&w.hist, sizeof(unsigned long long) * LEAF_W));
+        LB_CUDA_CHECK(cudaMemset(w.hist, 0, sizeof(unsigned long long) * LEAF_W));
     }
     return w;
 }
 
-// factor an m x n (n <= LEAF_W) panel; ipiv relative (1-based); *info set to info_off + col + 1 on the
-// first exact zero pivot (only if still zero)
-static void getrf_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
+// The panel the leaves belong to: P = element (0,0) of the panel, width columns; a leaf at column offset
+// `off` (== its row offset) interchanges rows in all the other panel columns as it goes.
+struct PanelCtx {
+    double* P;
+    int width;
+};
+
+// factor an m x n (n <= LEAF_W) leaf at panel offset `off`; ipiv relative (1-based); *info set to
+// info_off + col + 1 on the first exact zero pivot (only if still zero)
+static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n, double* A, i64 lda, int* ipiv, int* info,
+                       int info_off) {
     LeafWs& w = leaf_ws();
     LeafParams p;
     p.m = m; p.n = n; p.A = A; p.lda = lda; p.ipiv = ipiv; p.info = info; p.info_off = info_off;
@@ -243,38 +283,43 @@ static void getrf_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ip
         record_cuda_error(cudaErrorInvalidValue);
         return;
     }
-    p.bar = w.bar; p.bar_base = w.base; p.cand = w.cand; p.candrow = w.candrow; p.toprow = w.toprow;
-    getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G, LEAF_THREADS, 0, s>>>(p);
+    p.epoch_base = w.epoch; p.cand = w.cand; p.top = w.top; p.hist = w.hist;
+    p.SW = pc.P + off;
+    p.sw_left = off;
+    p.sw_right = pc.width - off - n;
+    const int S = ceil_div(p.sw_left + p.sw_right, LEAF_THREADS);
+    getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G + S, LEAF_THREADS, 0, s>>>(p);
     count_launch();
-    if (p.G > 1) w.base += (unsigned)min(m, n) * (unsigned)p.G;
+    w.epoch += (unsigned)min(m, n);
     LB_CUDA_CHECK(cudaGetLastError());
 }
 
-// recursive panel (the DGETRF2 recursion, dgetrf2.f:216-263) down to LEAF_W columns
-static void getrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
+// recursive panel (the DGETRF2 recursion, dgetrf2.f:216-263) down to LEAF_W columns.  The row interchanges
+// of dgetrf2.f:236 and :263 are applied by the leaves themselves to every other column of the panel.
+static void getrf_panel_rec(cudaStream_t s, const PanelCtx& pc, int off, int m, int n, double* A, i64 lda, int* ipiv,
+                            int* info, int info_off) {
     if (m <= 0 || n <= 0) return;
-    if (n <= LEAF_W) { getrf_leaf(s, m, n, A, lda, ipiv, info, info_off); return; }
+    if (n <= LEAF_W) { getrf_leaf(s, pc, off, m, n, A, lda, ipiv, info, info_off); return; }
     const int mn = min(m, n);
     int n1 = LEAF_W;
     while (n1 * 2 < mn) n1 *= 2;                 // power-of-two multiple of the leaf width, < mn
     if (n1 >= mn) n1 = max(1, mn / 2);
     if (n1 > mn) n1 = mn;
     const int n2 = n - n1;
-    //        [ A11 ]
-    // factor [ --- ]
-    //        [ A21 ]
-    getrf_panel(s, m, n1, A, lda, ipiv, info, info_off);
+    getrf_panel_rec(s, pc, off, m, n1, A, lda, ipiv, info, info_off);
     double* A12 = A + (i64)n1 * lda;
     double* A21 = A + n1;
     double* A22 = A + n1 + (i64)n1 * lda;
-    laswp(s, n2, A12, lda, 1, n1, ipiv, 1);                                    // dgetrf2.f:236
     trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, A, lda, A12, lda);               // dgetrf2.f:240
     if (m > n1) {
         gemm(s, 'N', 'N', m - n1, n2, n1, -1.0, A21, lda, A12, lda, 1.0, A22, lda);   // dgetrf2.f:245
-        getrf_panel(s, m - n1, n2, A22, lda, ipiv + n1, info, info_off + n1);          // dgetrf2.f:250
+        getrf_panel_rec(s, pc, off + n1, m - n1, n2, A22, lda, ipiv + n1, info, info_off + n1);   // dgetrf2.f:250
         iadd(s, min(m, n) - n1, ipiv + n1, n1);                                          // dgetrf2.f:257-259
-        laswp(s, n1, A, lda, n1 + 1, min(m, n), ipiv, 1);                               // dgetrf2.f:263
     }
+}
+static void getrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
+    PanelCtx pc{A, n};
+    getrf_panel_rec(s, pc, 0, m, n, A, lda, ipiv, info, info_off);
 }
 
 static std::mutex g_lib_mutex;
@@ -290,7 +335,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     if (m <= 0 || n <= 0) return;
     const int mn = min(m, n);
-    const int nb = g_nb;
+    const int nb = min(g_nb, 2048);
     if (nb >= mn) { getrf_panel(s, m, n, A, lda, ipiv, info, 0); return; }
 
     const bool la = g_lookahead != 0;
@@ -313,12 +358,14 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel, 0));
         double* Ajj = A + j + (i64)j * lda;
         const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
+        // one plan for this panel's interchanges (dgetrf.f:193,199), applied to three column ranges
+        void* plan = laswp_plan(su, j + 1, jn, piv, 1);
         // columns of the next panel first (look-ahead), then the rest
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
         if (jn < n) {
             const int w1 = (jb2 > 0) ? jb2 : (n - jn);       // width of the first slab
             double* A12 = A + j + (i64)jn * lda;
-            laswp(su, w1, A + (i64)jn * lda, lda, j + 1, jn, piv, 1);                        // dgetrf.f:199
+            laswp_apply_plan(su, w1, A + (i64)jn * lda, lda, plan, jb);                      // dgetrf.f:199
             trsm(su, 'L', 'L', 'N', 'U', jb, w1, 1.0, Ajj, lda, A12, lda);                   // dgetrf.f:204
             if (jn < m)
                 gemm(su, 'N', 'N', m - jn, w1, jb, -1.0, A + jn + (i64)j * lda, lda, A12, lda, 1.0,
@@ -335,7 +382,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 const int rest = n - jn - w1;
                 if (rest > 0) {
                     double* A13 = A + j + (i64)(jn + w1) * lda;
-                    laswp(su, rest, A + (i64)(jn + w1) * lda, lda, j + 1, jn, piv, 1);
+                    laswp_apply_plan(su, rest, A + (i64)(jn + w1) * lda, lda, plan, jb);
                     trsm(su, 'L', 'L', 'N', 'U', jb, rest, 1.0, Ajj, lda, A13, lda);
                     if (jn < m)
                         gemm(su, 'N', 'N', m - jn, rest, jb, -1.0, A + jn + (i64)j * lda, lda, A13, lda, 1.0,
@@ -344,7 +391,8 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
             }
         }
         // interchanges to the left of the panel (dgetrf.f:193)
-        if (j > 0) laswp(su, j, A, lda, j + 1, jn, piv, 1);
+        if (j > 0) laswp_apply_plan(su, j, A, lda, plan, jb);
+        laswp_plan_free(su, plan);
     }
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, su));

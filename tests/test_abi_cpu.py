@@ -1,0 +1,185 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads without a GPU, exports every symbol the
+headers declare, and reproduces the reference's argument checking / XERBLA positions (TESTING/LIN/derrge.f:133-184,
+derrpo.f:133-178, derrqr.f:118-130; BLAS/TESTING/dblat3.f DCHKE).  No compute call is made here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import lapack_b200
+    L = lapack_b200.lib()
+    L.lb200_set_xerbla_mode(2)
+    return lapack_b200
+
+
+def declared_symbols():
+    names = set()
+    for h in ("lapack_b200.h", "lapack_b200_f77.h", "lapack_b200_lapacke.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"\b(lb200_\w+|LAPACKE_\w+|[a-z0-9]+_)\s*\(", src):
+            n = m.group(1)
+            if n.startswith(("lb200_", "LAPACKE_")) or re.fullmatch(r"(d[a-z0-9]+|xerbla|lsame)_", n):
+                names.add(n)
+    return sorted(names)
+
+
+def test_library_exports_every_declared_symbol(lb):
+    L = lb.lib()
+    names = declared_symbols()
+    assert len(names) > 70
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_reference_lapacke_binds_to_our_symbols(lb):
+    """The reference's own LAPACKE C layer (compiled from /root/reference by oracle/Makefile) resolves its
+    Fortran symbols against liblapack_b200.so -- the link-time drop-in mechanism of SRC/VARIANTS/README:66-78."""
+    so = os.path.join(ROOT, "oracle", "_ref", "liblapacke_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    lb.lib()                                  # RTLD_GLOBAL: dgetrf_ ... become visible
+    R = C.CDLL(so, mode=C.RTLD_GLOBAL)
+    a = np.zeros((2, 2), order="F")
+    ipiv = np.zeros(2, dtype=np.int32)
+    # illegal lda -> dgetrf_ INFO=-4 -> LAPACKE shifts to -5 (lapacke_dgetrf_work.c:42-44); no GPU work happens
+    assert R.LAPACKE_dgetrf_work(102, 2, 2, a.ctypes.data_as(C.c_void_p), 1, ipiv.ctypes.data_as(C.c_void_p)) == -5
+    name = C.create_string_buffer(40)
+    info = C.c_int(0)
+    lb.lib().lb200_last_xerbla(name, C.byref(info))
+    assert name.value == b"DGETRF" and info.value == 4
+
+
+def _last(lb):
+    name = C.create_string_buffer(40)
+    info = C.c_int(0)
+    cnt = lb.lib().lb200_last_xerbla(name, C.byref(info))
+    return name.value.decode(), info.value, cnt
+
+
+def expect(lb, fn, routine, pos):
+    lb.lib().lb200_clear_xerbla()
+    ret = fn()
+    name, info, cnt = _last(lb)
+    assert cnt == 1 and name == routine and info == pos, (routine, pos, name, info, cnt)
+    return ret
+
+
+A = np.zeros((4, 4), order="F")
+B = np.zeros((4, 4), order="F")
+IP = np.zeros(4, dtype=np.int32)
+W = np.zeros(16)
+TAU = np.zeros(4)
+
+
+def test_lu_error_exits(lb):
+    f = lb.f77
+    assert expect(lb, lambda: f.dgetrf(-1, 0, A, 1, IP), "DGETRF", 1) == -1
+    assert expect(lb, lambda: f.dgetrf(0, -1, A, 1, IP), "DGETRF", 2) == -2
+    assert expect(lb, lambda: f.dgetrf(2, 1, A, 1, IP), "DGETRF", 4) == -4
+    assert expect(lb, lambda: f.dgetrf(-1, 0, A, 1, IP, True), "DGETRF2", 1) == -1
+    assert expect(lb, lambda: f.dgetrf(2, 1, A, 1, IP, True), "DGETRF2", 4) == -4
+    assert expect(lb, lambda: f.dgetrs("/", 0, 0, A, 1, IP, B, 1), "DGETRS", 1) == -1
+    assert expect(lb, lambda: f.dgetrs("N", -1, 0, A, 1, IP, B, 1), "DGETRS", 2) == -2
+    assert expect(lb, lambda: f.dgetrs("N", 0, -1, A, 1, IP, B, 1), "DGETRS", 3) == -3
+    assert expect(lb, lambda: f.dgetrs("N", 2, 1, A, 1, IP, B, 2), "DGETRS", 5) == -5
+    assert expect(lb, lambda: f.dgetrs("N", 2, 1, A, 2, IP, B, 1), "DGETRS", 8) == -8
+    assert expect(lb, lambda: f.dgesv(-1, 0, A, 1, IP, B, 1), "DGESV", 1) == -1
+    assert expect(lb, lambda: f.dgesv(0, -1, A, 1, IP, B, 1), "DGESV", 2) == -2
+    assert expect(lb, lambda: f.dgesv(2, 1, A, 1, IP, B, 2), "DGESV", 4) == -4
+    assert expect(lb, lambda: f.dgesv(2, 1, A, 2, IP, B, 1), "DGESV", 7) == -7
+
+
+def test_cholesky_error_exits(lb):
+    f = lb.f77
+    assert expect(lb, lambda: f.dpotrf("/", 0, A, 1), "DPOTRF", 1) == -1
+    assert expect(lb, lambda: f.dpotrf("U", -1, A, 1), "DPOTRF", 2) == -2
+    assert expect(lb, lambda: f.dpotrf("U", 2, A, 1), "DPOTRF", 4) == -4
+    assert expect(lb, lambda: f.dpotrf("U", 2, A, 1, True), "DPOTRF2", 4) == -4
+    assert expect(lb, lambda: f.dpotrs("/", 0, 0, A, 1, B, 1), "DPOTRS", 1) == -1
+    assert expect(lb, lambda: f.dpotrs("U", -1, 0, A, 1, B, 1), "DPOTRS", 2) == -2
+    assert expect(lb, lambda: f.dpotrs("U", 0, -1, A, 1, B, 1), "DPOTRS", 3) == -3
+    assert expect(lb, lambda: f.dpotrs("U", 2, 1, A, 1, B, 2), "DPOTRS", 5) == -5
+    assert expect(lb, lambda: f.dpotrs("U", 2, 1, A, 2, B, 1), "DPOTRS", 7) == -7
+    assert expect(lb, lambda: f.dposv("/", 0, 0, A, 1, B, 1), "DPOSV", 1) == -1
+    assert expect(lb, lambda: f.dposv("U", 2, 0, A, 1, B, 2), "DPOSV", 5) == -5
+    assert expect(lb, lambda: f.dposv("U", 2, 0, A, 2, B, 1), "DPOSV", 7) == -7
+
+
+def test_qr_error_exits_and_query(lb):
+    f = lb.f77
+    assert expect(lb, lambda: f.dgeqrf(-1, 0, A, 1, TAU, W, 1), "DGEQRF", 1) == -1
+    assert expect(lb, lambda: f.dgeqrf(0, -1, A, 1, TAU, W, 1), "DGEQRF", 2) == -2
+    assert expect(lb, lambda: f.dgeqrf(2, 1, A, 1, TAU, W, 1), "DGEQRF", 4) == -4
+    assert expect(lb, lambda: f.dgeqrf(1, 2, A, 1, TAU, W, 1), "DGEQRF", 7) == -7
+    assert expect(lb, lambda: f.dgeqr2(-1, 0, A, 1, TAU, W), "DGEQR2", 1) == -1
+    assert expect(lb, lambda: f.dgeqr2(2, 1, A, 1, TAU, W), "DGEQR2", 4) == -4
+    wq = np.zeros(1)
+    assert f.dgeqrf(300, 200, A, 300, TAU, wq, -1) == 0 and wq[0] == 200 * 32    # dgeqrf.f:197-204
+    assert f.dgeqrf(0, 5, A, 1, TAU, wq, -1) == 0 and wq[0] == 1
+
+
+def test_quick_returns_need_no_gpu(lb):
+    """M==0 or N==0 return before any device work (dgetrf.f:159, dpotrf.f:161, dgeqrf.f:209-212)."""
+    f = lb.f77
+    lb.lib().lb200_clear_xerbla()
+    assert f.dgetrf(0, 4, A, 1, IP) == 0 and f.dgetrf(4, 0, A, 4, IP) == 0
+    assert f.dpotrf("L", 0, A, 1) == 0
+    assert f.dgetrs("N", 0, 1, A, 1, IP, B, 1) == 0 and f.dgetrs("N", 4, 0, A, 4, IP, B, 4) == 0
+    w = np.zeros(1)
+    assert f.dgeqrf(0, 3, A, 1, TAU, w, 3) == 0 and w[0] == 1
+    assert _last(lb)[2] == 0
+
+
+def test_blas3_error_exits(lb):
+    f = lb.f77
+    expect(lb, lambda: f.dgemm("/", "N", 0, 0, 0, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 1)
+    expect(lb, lambda: f.dgemm("N", "/", 0, 0, 0, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 2)
+    expect(lb, lambda: f.dgemm("N", "N", -1, 0, 0, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 3)
+    expect(lb, lambda: f.dgemm("N", "N", 0, -1, 0, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 4)
+    expect(lb, lambda: f.dgemm("N", "N", 0, 0, -1, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 5)
+    expect(lb, lambda: f.dgemm("N", "N", 2, 0, 0, 1.0, A, 1, B, 1, 0.0, W, 2), "DGEMM", 8)
+    expect(lb, lambda: f.dgemm("N", "N", 0, 0, 2, 1.0, A, 1, B, 1, 0.0, W, 1), "DGEMM", 10)
+    expect(lb, lambda: f.dgemm("N", "N", 2, 0, 0, 1.0, A, 2, B, 1, 0.0, W, 1), "DGEMM", 13)
+    expect(lb, lambda: f.dtrsm("/", "U", "N", "N", 0, 0, 1.0, A, 1, B, 1), "DTRSM", 1)
+    expect(lb, lambda: f.dtrsm("L", "/", "N", "N", 0, 0, 1.0, A, 1, B, 1), "DTRSM", 2)
+    expect(lb, lambda: f.dtrsm("L", "U", "/", "N", 0, 0, 1.0, A, 1, B, 1), "DTRSM", 3)
+    expect(lb, lambda: f.dtrsm("L", "U", "N", "/", 0, 0, 1.0, A, 1, B, 1), "DTRSM", 4)
+    expect(lb, lambda: f.dtrsm("L", "U", "N", "N", -1, 0, 1.0, A, 1, B, 1), "DTRSM", 5)
+    expect(lb, lambda: f.dtrsm("L", "U", "N", "N", 0, -1, 1.0, A, 1, B, 1), "DTRSM", 6)
+    expect(lb, lambda: f.dtrsm("L", "U", "N", "N", 2, 0, 1.0, A, 1, B, 2), "DTRSM", 9)
+    expect(lb, lambda: f.dtrsm("L", "U", "N", "N", 2, 0, 1.0, A, 2, B, 1), "DTRSM", 11)
+    expect(lb, lambda: f.dtrmm("R", "U", "N", "N", 0, 2, 1.0, A, 1, B, 1), "DTRMM", 9)
+    expect(lb, lambda: f.dsyrk("/", "N", 0, 0, 1.0, A, 1, 0.0, W, 1), "DSYRK", 1)
+    expect(lb, lambda: f.dsyrk("U", "/", 0, 0, 1.0, A, 1, 0.0, W, 1), "DSYRK", 2)
+    expect(lb, lambda: f.dsyrk("U", "N", -1, 0, 1.0, A, 1, 0.0, W, 1), "DSYRK", 3)
+    expect(lb, lambda: f.dsyrk("U", "N", 0, -1, 1.0, A, 1, 0.0, W, 1), "DSYRK", 4)
+    expect(lb, lambda: f.dsyrk("U", "N", 2, 0, 1.0, A, 1, 0.0, W, 2), "DSYRK", 7)
+    expect(lb, lambda: f.dsyrk("U", "N", 2, 0, 1.0, A, 2, 0.0, W, 1), "DSYRK", 10)
+
+
+def test_lapacke_layer_errors(lb):
+    L = lb.lib()
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    assert L.LAPACKE_dgetrf(100, 2, 2, vp(A), 2, vp(IP)) == -1                      # bad layout
+    assert L.LAPACKE_dgetrf_work(101, 2, 3, vp(A), 2, vp(IP)) == -5                 # row-major lda < n
+    assert L.LAPACKE_dgetrf_work(102, 2, 2, vp(A), 1, vp(IP)) == -5                 # Fortran -4 shifted by one
+    assert L.LAPACKE_dpotrf_work(101, C.c_char(b"L"), 3, vp(A), 2) == -5
+    assert L.LAPACKE_dgetrs_work(101, C.c_char(b"N"), 2, 3, vp(A), 2, vp(IP), vp(B), 2) == -9
+    assert L.LAPACKE_dgesv_work(101, 2, 3, vp(A), 1, vp(IP), vp(B), 3) == -5
+    assert L.LAPACKE_dgeqrf_work(101, 2, 3, vp(A), 2, vp(TAU), vp(W), 16) == -5
+    assert L.LAPACKE_dlaswp_work(101, 3, vp(A), 2, 1, 1, vp(np.ones(1, dtype=np.int32)), 1) == -4
+    wq = np.zeros(1)
+    assert L.LAPACKE_dgeqrf_work(102, 300, 200, vp(A), 300, vp(TAU), vp(wq), -1) == 0 and wq[0] == 6400
+    nan = np.full((2, 2), np.nan, order="F")
+    L.LAPACKE_set_nancheck(1)
+    assert L.LAPACKE_dgetrf(102, 2, 2, vp(nan), 2, vp(IP)) == -4                    # NaN pre-check (lapacke_dgetrf.c:42-49)
+    assert L.LAPACKE_dpotrf(102, C.c_char(b"L"), 2, vp(nan), 2) == -4
+    assert L.LAPACKE_dgesv(102, 2, 1, vp(A), 2, vp(IP), vp(nan), 2) == -7
