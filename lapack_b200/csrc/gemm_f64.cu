@@ -52,13 +52,13 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double x, double
                  : "d"(x), "d"(y));
 }
 
-constexpr int BK = 16;
+constexpr int BK = 16;      // default k-tile
 constexpr int PAD = 4;
 
 // Shared-memory tile of one operand: EXT = extent along m (or n), BK along k.
 //   K-major  (KMAJ=true):  element (e,k) at e*(BK+PAD) + k      (k contiguous in global memory)
 //   MN-major (KMAJ=false): element (e,k) at k*(EXT+PAD) + e      (e contiguous in global memory)
-template <int EXT, bool KMAJ>
+template <int EXT, bool KMAJ, int BK = 16>
 struct TileLayout {
     static constexpr int ELEMS = KMAJ ? EXT * (BK + PAD) : BK * (EXT + PAD);
     __device__ static __forceinline__ int off(int e, int k) { return KMAJ ? e * (BK + PAD) + k : k * (EXT + PAD) + e; }
@@ -68,7 +68,7 @@ struct TileLayout {
 // depend on the k-tile index is done once in init(); issue() only adds the k offset and clamps at the K
 // edge (zero fill), so the steady-state loop spends its issue slots on LDS/DMMA.
 //   g points at element (e=0,k=0) of the whole operand; e0 = tile origin, elim/klim = operand extents.
-template <int EXT, bool KMAJ, bool AL16, int NTHREADS>
+template <int EXT, bool KMAJ, bool AL16, int NTHREADS, int BK = 16>
 struct TileLoader {
     static constexpr int N = AL16 ? (EXT * BK / 2) / NTHREADS : (EXT * BK) / NTHREADS;
     static_assert((AL16 ? (EXT * BK / 2) : (EXT * BK)) % NTHREADS == 0, "tile/thread mismatch");
@@ -121,14 +121,16 @@ struct TileLoader {
     }
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, bool AL16, int STAGES>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, (WARPS_M * WARPS_N <= 4) ? 2 : 1)
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, bool AL16, int STAGES, int BK = 16>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
+                                  ((BM / WARPS_M) * (BN / WARPS_N) <= 1024) ? (512 / (WARPS_M * WARPS_N * 32) > 0 ? 512 / (WARPS_M * WARPS_N * 32) : 1)
+                                                                            : ((WARPS_M * WARPS_N <= 4) ? 2 : 1))
     gemm_f64_dmma_kernel(GemmParams p) {
     constexpr int NTHREADS = WARPS_M * WARPS_N * 32;
     constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
     constexpr int MT = WM / 8, NT = WN / 8;
-    using LA = TileLayout<BM, A_KMAJ>;
-    using LB = TileLayout<BN, B_KMAJ>;
+    using LA = TileLayout<BM, A_KMAJ, BK>;
+    using LB = TileLayout<BN, B_KMAJ, BK>;
     constexpr int STAGE_ELEMS = LA::ELEMS + LB::ELEMS;
 
     extern __shared__ __align__(16) double smem[];
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, (WARPS_M * WARPS_N <= 4
         for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     const int KT = (p.K + BK - 1) / BK;
-    TileLoader<BM, A_KMAJ, AL16, NTHREADS> ldA;
-    TileLoader<BN, B_KMAJ, AL16, NTHREADS> ldB;
+    TileLoader<BM, A_KMAJ, AL16, NTHREADS, BK> ldA;
+    TileLoader<BN, B_KMAJ, AL16, NTHREADS, BK> ldB;
     ldA.init(p.A, p.lda, m0, p.M, tid);
     ldB.init(p.B, p.ldb, n0, p.N, tid);
 
@@ -302,7 +304,7 @@ __global__ void splitk_reduce_kernel(int m, int n, int nz, double alpha, double 
 
 static int g_gemm_cfg = -1;   // -1 auto, 0 = 128x128x8w, 1 = 128x64x4w, 2 = 64x64 (2 warps)
 
-template <int BM, int BN, int WMW, int WNW, int STAGES>
+template <int BM, int BN, int WMW, int WNW, int STAGES, int BKT = 16>
 static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const GemmParams& p0) {
     GemmParams p = p0;
     p.tiles_m = ceil_div(p.M, BM);
@@ -312,8 +314,8 @@ static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const Gemm
     dim3 grid((unsigned)((i64)p.tiles_m * p.tiles_n), (unsigned)ceil_div(p.K, p.kchunk));
 #define LB_LAUNCH(AK, BKM, AL)                                                                                  \
     {                                                                                                           \
-        auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES>;                                  \
-        smem = sizeof(double) * STAGES * (TileLayout<BM, AK>::ELEMS + TileLayout<BN, BKM>::ELEMS);               \
+        auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES, BKT>;                             \
+        smem = sizeof(double) * STAGES * (TileLayout<BM, AK, BKT>::ELEMS + TileLayout<BN, BKM, BKT>::ELEMS);     \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
             LB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
@@ -336,6 +338,8 @@ static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const Gemm
 void gemm_set_config(int cfg) { g_gemm_cfg = cfg; }
 bool gemm_tma_try(cudaStream_t s, bool a_k, bool b_k, int m, int n, int k, double alpha, const double* A, i64 lda,
                   const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri);
+bool gemm_tma64_try(cudaStream_t s, bool a_k, bool b_k, int m, int n, int k, double alpha, const double* A, i64 lda,
+                    const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri);
 
 // ---- optional per-launch timing of the large GEMMs (bench.py's roofline leg) ----------------------
 struct GemmProf {
@@ -425,23 +429,28 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
             }
         }
     }
-    if (cfg < 0 || cfg == 3) {
-        // large, aligned problems: persistent TMA-fed kernel (gemm_tma.cu)
-        i64 t128 = (i64)ceil_div(m, 128) * ceil_div(n, 128);
-        if ((t128 >= num_sms() || cfg == 3) && k >= 32 &&
-            gemm_tma_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri))
-            return;
-        if (cfg == 3) cfg = -1;
+    if (cfg == 3) {
+        // persistent warp-specialised TMA kernel (gemm_tma.cu): one CTA per SM for the whole GEMM, so it must not
+        // be used while a look-ahead panel needs SMs; measured 31.3 TFLOP/s at K=512 vs 33.6 for the default below.
+        if (k >= 32 && gemm_tma_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri)) return;
+        cfg = -1;
     }
-    if (cfg < 0) {
-        // enough 128x128 tiles to fill the machine -> big tile; otherwise smaller tiles for parallelism
-        i64 t128 = (i64)ceil_div(m, 128) * ceil_div(n, 128);
-        i64 t12864 = (i64)ceil_div(m, 128) * ceil_div(n, 64);
-        if (t128 >= 2 * num_sms()) cfg = 0;
-        else if (t12864 >= num_sms()) cfg = 1;
-        else cfg = 2;
+    // default: 64x64 tiles, 4 warps of 32x32, 2-stage cp.async ring, 4 CTAs per SM (measured best on B200:
+    // 33.6 TFLOP/s = 90% of the DMMA peak at K=512; profiles/r01_gemm_config_sweep.txt)
+    if (cfg == 12) {   // 64x64 TMA-fed kernel (same tile shape as cfg 8, operands moved by cp.async.bulk.tensor)
+        if (k >= 16 && gemm_tma64_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri)) return;
+        cfg = -1;
     }
-    if (cfg == 0) launch_cfg<128, 128, 2, 4, 4>(s, a_k, b_k, al16, p);
+    if (cfg < 0) cfg = 8;
+    if (cfg == 4) launch_cfg<128, 64, 4, 2, 3>(s, a_k, b_k, al16, p);          // 8 warps of 32x32, 2 CTAs/SM
+    else if (cfg == 5) launch_cfg<128, 128, 4, 4, 4>(s, a_k, b_k, al16, p);     // 16 warps of 32x32, 1 CTA/SM
+    else if (cfg == 6) launch_cfg<64, 64, 2, 2, 4>(s, a_k, b_k, al16, p);       // 4 warps of 32x32, 2 CTAs/SM (smem)
+    else if (cfg == 7) launch_cfg<64, 64, 2, 2, 3>(s, a_k, b_k, al16, p);       // 3 CTAs/SM
+    else if (cfg == 8) launch_cfg<64, 64, 2, 2, 2>(s, a_k, b_k, al16, p);       // 4 CTAs/SM
+    else if (cfg == 9) launch_cfg<64, 64, 2, 2, 3, 32>(s, a_k, b_k, al16, p);   // BK=32
+    else if (cfg == 10) launch_cfg<64, 128, 2, 2, 3>(s, a_k, b_k, al16, p);     // 4 warps of 32x64
+    else if (cfg == 11) launch_cfg<128, 64, 2, 2, 3, 32>(s, a_k, b_k, al16, p); // cfg1 with BK=32
+    else if (cfg == 0) launch_cfg<128, 128, 2, 4, 4>(s, a_k, b_k, al16, p);
     else if (cfg == 1) launch_cfg<128, 64, 2, 2, 3>(s, a_k, b_k, al16, p);
     else launch_cfg<64, 64, 1, 2, 4>(s, a_k, b_k, al16, p);
 }

@@ -257,6 +257,161 @@ __global__ void __launch_bounds__(NTHREADS, 1)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Small-tile TMA kernel: 64 x 64 tile, 4 warps of 32 x 32, 3-stage ring, 4 CTAs per SM, NOT persistent.
+// This is the shape that measured best on B200 for the trailing updates (many small CTAs keep the DMMA pipe
+// busy across each other's barriers and epilogues, and retire continuously so that a high-priority look-ahead
+// panel can get SMs).  Thread 0 issues the TMA loads for the stage that has just been consumed; everybody
+// waits on the stage's mbarrier.  No per-thread address arithmetic, no cp.async bookkeeping.
+namespace t64 {
+constexpr int TM = 64, TN = 64, TSTAGES = 3, TTHREADS = 128;
+constexpr int TA_BYTES = TM * BK * 8, TB_BYTES = TN * BK * 8, TSTAGE_BYTES = TA_BYTES + TB_BYTES;
+constexpr int TSMEM_BYTES = TSTAGES * TSTAGE_BYTES + 1024 + 64;
+}  // namespace t64
+
+template <bool A_KMAJ, bool B_KMAJ>
+__global__ void __launch_bounds__(t64::TTHREADS, 4)
+    gemm_f64_tma64_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p) {
+    using namespace t64;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned long long* bars = (unsigned long long*)(smem + TSTAGES * TSTAGE_BYTES);
+    const unsigned full0 = smem_u32(bars);
+    const unsigned sbase = smem_u32(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    constexpr int GROUP = 16;
+    const int t = blockIdx.x;
+    const int width = GROUP * p.tiles_n;
+    const int group_id = t / width;
+    const int first_m = group_id * GROUP;
+    const int gsz = min(p.tiles_m - first_m, GROUP);
+    const int m0 = (first_m + (t % width) % gsz) * TM;
+    const int n0 = ((t % width) / gsz) * TN;
+    if ((p.tri == 1 && m0 + TM - 1 < n0) || (p.tri == 2 && n0 + TN - 1 < m0)) return;
+
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) mbar_init(full0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const int KT = (p.K + BK - 1) / BK;
+    auto issue = [&](int kt) {
+        const int s = kt % TSTAGES;
+        const unsigned bar = full0 + 8 * s;
+        mbar_expect_tx(bar, TSTAGE_BYTES);
+        const unsigned sa = sbase + s * TSTAGE_BYTES, sb = sa + TA_BYTES;
+        const int k0 = kt * BK;
+        if (A_KMAJ) tma_load_2d(sa, &mapA, k0, m0, bar);
+        else {
+#pragma unroll
+            for (int b = 0; b < TM / 16; ++b) tma_load_2d(sa + b * (BK * 128), &mapA, m0 + 16 * b, k0, bar);
+        }
+        if (B_KMAJ) tma_load_2d(sb, &mapB, k0, n0, bar);
+        else {
+#pragma unroll
+            for (int b = 0; b < TN / 16; ++b) tma_load_2d(sb + b * (BK * 128), &mapB, n0 + 16 * b, k0, bar);
+        }
+    };
+    if (tid == 0) {
+        for (int kt = 0; kt < TSTAGES && kt < KT; ++kt) issue(kt);
+    }
+    if (p.beta != 0.0) {   // pull the C tile towards L2 for the read-modify-write epilogue
+        for (int l = tid; l < TN * (TM / 16); l += TTHREADS) {
+            int n = n0 + l / (TM / 16), m = m0 + (l % (TM / 16)) * 16;
+            if (n < p.N && m < p.M) {
+                const double* ptr = p.C + (i64)n * p.ldc + m;
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+            }
+        }
+    }
+
+    const int warp_m = warp & 1, warp_n = warp >> 1;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    constexpr int MT = 4, NT = 4;
+    int aoff[MT], boff[NT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a) aoff[a] = A_KMAJ ? k_frag_off(warp_m * 4 + a, g4, t4) : mn_frag_off(warp_m * 4 + a, g4, t4);
+#pragma unroll
+    for (int b = 0; b < NT; ++b) boff[b] = TA_BYTES + (B_KMAJ ? k_frag_off(warp_n * 4 + b, g4, t4) : mn_frag_off(warp_n * 4 + b, g4, t4));
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % TSTAGES;
+        mbar_wait(full0 + 8 * s, (kt / TSTAGES) & 1);
+        const unsigned char* st = smem + s * TSTAGE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int a = 0; a < MT; ++a) {
+                int off = A_KMAJ ? (aoff[a] ^ (kk * 8)) : ((aoff[a] + kk * 128) ^ ((kk & 4) << 4));
+                af[a] = *reinterpret_cast<const double*>(st + off);
+            }
+#pragma unroll
+            for (int b = 0; b < NT; ++b) {
+                int off = B_KMAJ ? (boff[b] ^ (kk * 8)) : ((boff[b] + kk * 128) ^ ((kk & 4) << 4));
+                bf[b] = *reinterpret_cast<const double*>(st + off);
+            }
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) dmma(acc[a][b][0], acc[a][b][1], bf[b], af[a]);
+        }
+        __syncthreads();                                   // the stage has been read by all four warps
+        if (tid == 0 && kt + TSTAGES < KT) issue(kt + TSTAGES);
+    }
+
+    const bool vec_ok = !A_KMAJ && ((p.ldc & 1) == 0) && ((((uintptr_t)p.C) & 15) == 0);
+    const double alpha = p.alpha, beta = p.beta;
+#pragma unroll
+    for (int b = 0; b < NT; ++b) {
+        const int n = n0 + (B_KMAJ ? k_frag_row(warp_n * 4 + b, g4) : mn_frag_row(warp_n * 4 + b, g4));
+        if (n >= p.N) continue;
+        double* ccol = p.C + (i64)n * p.ldc;
+        double c0[MT], c1[MT];
+        int r0[MT], r1[MT];
+        bool ok0[MT], ok1[MT];
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+            r0[a] = m0 + (A_KMAJ ? k_frag_row(warp_m * 4 + a, 2 * t4) : mn_frag_row(warp_m * 4 + a, 2 * t4));
+            r1[a] = m0 + (A_KMAJ ? k_frag_row(warp_m * 4 + a, 2 * t4 + 1) : mn_frag_row(warp_m * 4 + a, 2 * t4 + 1));
+            ok0[a] = r0[a] < p.M;
+            ok1[a] = r1[a] < p.M;
+            if (p.tri == 1) { ok0[a] = ok0[a] && (r0[a] >= n); ok1[a] = ok1[a] && (r1[a] >= n); }
+            if (p.tri == 2) { ok0[a] = ok0[a] && (r0[a] <= n); ok1[a] = ok1[a] && (r1[a] <= n); }
+            c0[a] = c1[a] = 0.0;
+            if (beta != 0.0) {
+                if (vec_ok && ok0[a] && ok1[a]) {
+                    double2 c = *reinterpret_cast<const double2*>(ccol + r0[a]);
+                    c0[a] = c.x; c1[a] = c.y;
+                } else {
+                    if (ok0[a]) c0[a] = ccol[r0[a]];
+                    if (ok1[a]) c1[a] = ccol[r1[a]];
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < MT; ++a) {
+            double v0 = alpha * acc[a][b][0], v1 = alpha * acc[a][b][1];
+            if (beta != 0.0) { v0 += beta * c0[a]; v1 += beta * c1[a]; }
+            if (vec_ok && ok0[a] && ok1[a]) {
+                *reinterpret_cast<double2*>(ccol + r0[a]) = make_double2(v0, v1);
+            } else {
+                if (ok0[a]) ccol[r0[a]] = v0;
+                if (ok1[a]) ccol[r1[a]] = v1;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -291,6 +446,38 @@ static bool make_map(CUtensorMap* map, const double* base, bool kmaj, int ext, i
 }
 
 }  // namespace tma
+
+// 64x64 non-persistent TMA kernel (default for aligned operands)
+bool gemm_tma64_try(cudaStream_t s, bool a_k, bool b_k, int m, int n, int k, double alpha, const double* A, i64 lda,
+                    const double* B, i64 ldb, double beta, double* C, i64 ldc, int tri) {
+    using namespace tma;
+    using namespace tma::t64;
+    if ((((uintptr_t)A) & 15) || (((uintptr_t)B) & 15) || (lda & 1) || (ldb & 1)) return false;
+    if (lda * 8 >= (1LL << 40) || ldb * 8 >= (1LL << 40)) return false;
+    CUtensorMap mapA, mapB;
+    if (!make_map(&mapA, A, a_k, m, k, lda, TM)) return false;
+    if (!make_map(&mapB, B, b_k, n, k, ldb, TN)) return false;
+    Params p;
+    p.M = m; p.N = n; p.K = k; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.tri = tri;
+    p.tiles_m = ceil_div(m, TM); p.tiles_n = ceil_div(n, TN);
+    const i64 grid = (i64)p.tiles_m * p.tiles_n;
+#define LB_TMA64_LAUNCH(AK, BKM)                                                                                     \
+    {                                                                                                                \
+        auto kern = gemm_f64_tma64_kernel<AK, BKM>;                                                                  \
+        static bool attr_set = false;                                                                                \
+        if (!attr_set) {                                                                                             \
+            LB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TSMEM_BYTES));     \
+            attr_set = true;                                                                                         \
+        }                                                                                                            \
+        kern<<<(unsigned)grid, TTHREADS, TSMEM_BYTES, s>>>(mapA, mapB, p);                                           \
+    }
+    if (a_k) { if (b_k) LB_TMA64_LAUNCH(true, true) else LB_TMA64_LAUNCH(true, false) }
+    else     { if (b_k) LB_TMA64_LAUNCH(false, true) else LB_TMA64_LAUNCH(false, false) }
+#undef LB_TMA64_LAUNCH
+    count_launch();
+    LB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
 
 static int g_tma_enabled = 1;
 void gemm_set_tma(int on) { g_tma_enabled = on; }

@@ -340,19 +340,35 @@ __global__ void scale_by_dev_kernel(int m, int n, double* __restrict__ A, i64 ld
 
 static std::mutex g_qr_mutex;
 
-static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, int nb) {
+// C := (I - V T^T V^T) C for the m x nc block C, V/T given as clean copies  (dlarfb.f:248-304 as three GEMMs)
+static void apply_block_reflector(cudaStream_t s, int m, int nc, int k, const double* Vc, i64 ldvc, const double* T, i64 ldt,
+                                  double* C, i64 ldc, double* W1, double* W2, i64 ldw) {
+    if (nc <= 0) return;
+    gemm(s, 'T', 'N', k, nc, m, 1.0, Vc, ldvc, C, ldc, 0.0, W1, ldw);       // W1 = V^T C
+    gemm(s, 'T', 'N', k, nc, k, 1.0, T, ldt, W1, ldw, 0.0, W2, ldw);        // W2 = T^T W1
+    gemm(s, 'N', 'N', m, nc, k, -1.0, Vc, ldvc, W2, ldw, 1.0, C, ldc);      // C -= V W2
+}
+
+static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, int nb, bool lookahead) {
     if (m <= 0 || n <= 0) return;
     const int k = min(m, n);
     nb = min(nb, k);
     if (nb < QW) nb = min(QW, k);
-    // scratch
+    const bool la = lookahead && k > nb;
+    // scratch: two (Vc, T) sets so that panel j+1 can be built while update j still reads set j
     const i64 ldvc = (m + 1) & ~1;
     const i64 ldt = (nb + 1) & ~1;
     const i64 ldw = (nb + 1) & ~1;
-    double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * nb);
-    double* T = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
-    double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
-    double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
+    double* Vc[2];
+    double* T[2];
+    Vc[0] = (double*)ws_alloc(s, sizeof(double) * ldvc * nb);
+    T[0] = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    Vc[1] = la ? (double*)ws_alloc(s, sizeof(double) * ldvc * nb) : Vc[0];
+    T[1] = la ? (double*)ws_alloc(s, sizeof(double) * ldt * nb) : T[0];
+    double* W1p = (double*)ws_alloc(s, sizeof(double) * ldw * nb);            // in-panel scratch (panel stream)
+    double* W2p = (double*)ws_alloc(s, sizeof(double) * ldw * nb);
+    double* W1u = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));    // trailing-update scratch
+    double* W2u = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
     unsigned long long* amax_bits = (unsigned long long*)ws_alloc(s, 64);
     double* scale = (double*)(amax_bits + 2);
 
@@ -364,34 +380,66 @@ static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double*
     scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 0, 0);
     count_launch(3);
 
-    for (int j = 0; j < k; j += nb) {
+    Aux& ax = aux();
+    cudaStream_t sp = la ? ax.panel_stream : s;
+    cudaStream_t su = la ? ax.update_stream : s;
+    cudaEvent_t ev_panel = ax.ev[6], ev_next = ax.ev[7], ev_join = ax.ev[2];
+    if (la) {
+        LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_join, 0));
+    }
+    auto panel = [&](int j, int jb, int set) {
+        LB_CUDA_CHECK(cudaMemsetAsync(T[set], 0, sizeof(double) * ldt * nb, sp));
+        geqrf_panel(sp, m - j, jb, A + j + (i64)j * lda, lda, tau + j, Vc[set], ldvc, T[set], ldt, W1p, W2p);
+    };
+    panel(0, min(nb, k), 0);
+    if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
+    int set = 0;
+    for (int j = 0; j < k; j += nb, set ^= (la ? 1 : 0)) {
         const int jb = min(nb, k - j);
+        const int jn = j + jb;
         const int mj = m - j;
-        double* Ajj = A + j + (i64)j * lda;
-        LB_CUDA_CHECK(cudaMemsetAsync(T, 0, sizeof(double) * ldt * nb, s));
-        geqrf_panel(s, mj, jb, Ajj, lda, tau + j, Vc, ldvc, T, ldt, W1, W2);
-        const int nt = n - j - jb;
-        if (nt > 0) {
-            double* C = A + j + (i64)(j + jb) * lda;
-            gemm(s, 'T', 'N', jb, nt, mj, 1.0, Vc, ldvc, C, lda, 0.0, W1, ldw);       // W1 = V^T C
-            gemm(s, 'T', 'N', jb, nt, jb, 1.0, T, ldt, W1, ldw, 0.0, W2, ldw);        // W2 = T^T W1
-            gemm(s, 'N', 'N', mj, nt, jb, -1.0, Vc, ldvc, W2, ldw, 1.0, C, lda);      // C -= V W2
+        if (jn >= n) break;
+        if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel, 0));
+        const int jb2 = (jn < k) ? min(nb, k - jn) : 0;
+        if (jb2 > 0) {
+            // look-ahead: next panel's columns first, then factor it while the rest is updated
+            apply_block_reflector(su, mj, jb2, jb, Vc[set], ldvc, T[set], ldt, A + j + (i64)jn * lda, lda, W1u, W2u, ldw);
+            if (la) { LB_CUDA_CHECK(cudaEventRecord(ev_next, su)); LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_next, 0)); }
+            if (la) {
+                panel(jn, jb2, set ^ 1);
+                LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
+            }
+            apply_block_reflector(su, mj, n - jn - jb2, jb, Vc[set], ldvc, T[set], ldt, A + j + (i64)(jn + jb2) * lda, lda, W1u,
+                                  W2u, ldw);
+            if (!la) panel(jn, jb2, set);     // sequential mode: same scratch set, after the whole update
+        } else {
+            apply_block_reflector(su, mj, n - jn, jb, Vc[set], ldvc, T[set], ldt, A + j + (i64)jn * lda, lda, W1u, W2u, ldw);
         }
+    }
+    if (la) {
+        LB_CUDA_CHECK(cudaEventRecord(ev_join, su));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
+        LB_CUDA_CHECK(cudaEventRecord(ev_next, sp));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_next, 0));
     }
     scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 1, 1);   // un-scale R only
     count_launch();
-    ws_free(s, Vc); ws_free(s, T); ws_free(s, W1); ws_free(s, W2); ws_free(s, amax_bits);
+    ws_free(s, Vc[0]); ws_free(s, T[0]);
+    if (la) { ws_free(s, Vc[1]); ws_free(s, T[1]); }
+    ws_free(s, W1p); ws_free(s, W2p); ws_free(s, W1u); ws_free(s, W2u); ws_free(s, amax_bits);
     LB_CUDA_CHECK(cudaGetLastError());
 }
 
 void geqrf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
     std::lock_guard<std::mutex> lock(g_qr_mutex);
-    geqrf_impl(s, m, n, A, lda, tau, g_qr_nb);
+    geqrf_impl(s, m, n, A, lda, tau, g_qr_nb, g_qr_lookahead != 0);
 }
 // DGEQR2: same factorization, panel-only code path (one recursive panel per 64 columns)
 void geqr2(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
     std::lock_guard<std::mutex> lock(g_qr_mutex);
-    geqrf_impl(s, m, n, A, lda, tau, 64);
+    geqrf_impl(s, m, n, A, lda, tau, 64, false);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -121,6 +121,70 @@ static void scale_full(cudaStream_t s, int m, int n, double alpha, double* B, i6
     count_launch();
 }
 
+// ----------------------------------------------------------------------------------------------
+// Fused small left-lower solve (no transpose): T*X = B with T (m x m, m <= 256) lower triangular, B m x n.
+// Used inside the LU panel recursion (dgetrf2.f:240) where the recursive version would cost ~2 launches per
+// 32 rows on the critical path.  One CTA owns TS_COLS columns of B (kept in shared memory); per 32-row
+// block: (1) warp-per-column forward substitution with shuffles, (2) all threads update the rows below,
+// streaming the 32-column strip of T from L2.
+constexpr int TS_COLS = 8;
+constexpr int TS_MAXM = 256;
+__global__ void __launch_bounds__(256) trsm_left_lower_small_kernel(int m, int n, const double* __restrict__ A, i64 lda,
+                                                                    bool unit, double* __restrict__ B, i64 ldb) {
+    __shared__ double sB[TS_COLS][TS_MAXM + 2];
+    __shared__ double sT[32][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * TS_COLS;
+    const int nc = min(TS_COLS, n - c0);
+    for (int q = tid; q < nc * m; q += 256) {
+        int c = q / m, r = q - c * m;
+        sB[c][r] = B[r + (i64)(c0 + c) * ldb];
+    }
+    __syncthreads();
+    for (int kb = 0; kb < m; kb += 32) {
+        const int bs = min(32, m - kb);
+        // diagonal block -> shared (only the lower triangle is read)
+        for (int q = tid; q < 32 * 32; q += 256) {
+            int i = q & 31, k = q >> 5;
+            sT[i][k] = (i < bs && k < bs && i >= k) ? A[(kb + i) + (i64)(kb + k) * lda] : 0.0;
+        }
+        __syncthreads();
+        // (1) forward substitution: warp w solves column w of the slab, lane = row inside the block
+        if (warp < nc) {
+            double x = (lane < bs) ? sB[warp][kb + lane] : 0.0;
+            for (int k = 0; k < bs; ++k) {
+                if (!unit && lane == k) x = x / sT[k][k];
+                double xk = __shfl_sync(0xffffffffu, x, k);
+                if (lane > k) x = x - xk * sT[lane][k];
+            }
+            if (lane < bs) sB[warp][kb + lane] = x;
+        }
+        __syncthreads();
+        // (2) rows below the block: B(r,:) -= T(r, kb:kb+bs) * X(kb:kb+bs, :)
+        for (int r = kb + 32 + tid; r < m; r += 256) {
+            double acc[TS_COLS];
+#pragma unroll
+            for (int c = 0; c < TS_COLS; ++c) acc[c] = 0.0;
+            const double* trow = A + r + (i64)kb * lda;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                if (k < bs) {
+                    double t = trow[(i64)k * lda];
+#pragma unroll
+                    for (int c = 0; c < TS_COLS; ++c) acc[c] = fma(t, sB[c][kb + k], acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < TS_COLS; ++c) sB[c][r] -= acc[c];
+        }
+        __syncthreads();
+    }
+    for (int q = tid; q < nc * m; q += 256) {
+        int c = q / m, r = q - c * m;
+        B[r + (i64)(c0 + c) * ldb] = sB[c][r];
+    }
+}
+
 static inline bool is(char c, char u) { return c == u || c == (char)(u + 32); }
 
 // split point: largest multiple of TB (power-of-two times TB preferred) not exceeding half, at least TB
@@ -198,7 +262,11 @@ void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, in
         if (alpha == 0.0) return;
     }
     const bool left = is(side, 'L'), upper = is(uplo, 'U'), tr = !is(trans, 'N'), unit = is(diag, 'U');
-    if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
+    if (left && !upper && !tr && m <= TS_MAXM && m > TB && n <= 4096) {
+        // latency-critical in-panel solve: one fused kernel instead of the recursion
+        trsm_left_lower_small_kernel<<<ceil_div(n, TS_COLS), 256, 0, s>>>(m, n, A, lda, unit, B, ldb);
+        count_launch();
+    } else if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     else trsm_right_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     LB_CUDA_CHECK(cudaGetLastError());
 }
