@@ -150,6 +150,75 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------- GPU leg
+def run_dist(args, rank, world, local_rank):
+    """N > 1: ONE DGETRF of order n_dist block-column-cyclic over the N GPUs (BASELINE configs[4]); NCCL panel broadcast."""
+    import torch
+    import torch.distributed as dist
+    import lapack_b200 as lb
+    from lapack_b200.dist import BlockCyclic1D, GpuOps, fill_local_random, pgetrf
+    from lapack_b200.dist_check import randomized_residual
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    L = lb.lib()
+    n, nb = args.n_dist, args.nb_dist
+    desc = BlockCyclic1D(n, nb, world, rank)
+    ops = GpuOps(dev)
+    a0 = fill_local_random(ops, desc, device=dev)
+    a = lb.dev.colmajor(n, desc.local_cols(), device=dev)
+    fl = flops_getrf(n)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    ipiv = info = None
+    for _ in range(max(args.warmup, 1)):
+        a.copy_(a0)
+        ipiv, info = pgetrf(ops, dist, desc, a)
+    barrier()
+    resid = None if args.no_check else randomized_residual(torch, dist, desc, a0, a, ipiv)
+    sampler = ClockSampler(local_rank)
+    launches0 = L.lb200_launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        a.copy_(a0)
+        pgetrf(ops, dist, desc, a)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    lt = torch.tensor([float(L.lb200_launch_count() - launches0)], device=dev, dtype=torch.float64)
+    dist.all_reduce(lt)
+    ms = t.item()
+    value = fl * args.steps / (ms * 1e-3) * 1e-12
+    peak = max(L.lb200_fp64_peak_tflops(None, 0, 8, 2, 20000) for _ in range(2))
+    if rank == 0:
+        line = {
+            "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"one DGETRF n={n} (BASELINE configs[4]) distributed block-column-cyclic (2D block-cyclic, 1 x {world} grid, NB={nb}) "
+                                   "over the GPUs; panel + pivots broadcast with NCCL, look-ahead; DLARNV(2) seed 1988-1991",
+                       "n": n, "parallelism": f"block-cyclic 1x{world}", "l2": "local matrix far larger than L2; restored from an HBM copy every step"},
+            "pct_of_fp64_peak": value / (world * peak), "roofline": {"bound": "tensor", "achieved": value / world, "peak": peak, "unit": "TFLOP/s",
+                                                                       "frac": value / (world * peak), "traffic": None,
+                                                                       "note": "whole-factorization rate per GPU vs the in-run DMMA peak"},
+            "cpu_baseline": None,
+            "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 4,
+                    "note": "the distributed matrix is generated on the devices (128 GiB does not pass through one host buffer); only IPIV/INFO return to the host"},
+            "gpu_launches": int(lt.item()), "clocks": clocks,
+            "checks": {"randomized_residual_ratio": resid, "info": int(info)},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import lapack_b200 as lb
@@ -334,6 +403,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--n", type=int, default=32768)
+    ap.add_argument("--n-dist", type=int, default=131072, help="order of the single distributed DGETRF when --gpus > 1")
+    ap.add_argument("--nb-dist", type=int, default=512)
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent n=32768 replicas instead of one distributed matrix")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -344,6 +416,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if world > 1 and not args.replicas:
+        run_dist(args, rank, world, local_rank)
         return
     run_ours(args, rank, world, local_rank)
 

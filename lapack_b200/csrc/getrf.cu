@@ -342,12 +342,15 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     Aux& ax = aux();
     cudaStream_t sp = la ? ax.panel_stream : s;    // panel stream
     cudaStream_t su = la ? ax.update_stream : s;   // trailing-update stream
-    cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2];
+    cudaStream_t sl = la ? ax.side_stream : s;     // interchanges left of the panel: off the critical path
+    cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2], ev_plan = ax.ev[8], ev_left = ax.ev[9];
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
         LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_join, 0));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_join, 0));
     }
+    bool left_pending = false;
     // first panel
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
@@ -390,10 +393,23 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 }
             }
         }
-        // interchanges to the left of the panel (dgetrf.f:193)
-        if (j > 0) laswp_apply_plan(su, j, A, lda, plan, jb);
-        laswp_plan_free(su, plan);
+        // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns: the only
+        // remaining reader is the trailing GEMM of the PREVIOUS step (its L21 operand), which precedes this point
+        // on `su`.  So the left interchanges wait for `su` to get here and then run on a low-priority side
+        // stream, concurrently with this step's trailing update instead of in front of the next one.
+        if (la) {
+            LB_CUDA_CHECK(cudaEventRecord(ev_plan, su));
+            LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
+        }
+        if (j > 0) laswp_apply_plan(sl, j, A, lda, plan, jb);
+        laswp_plan_free(sl, plan);
+        left_pending = true;
     }
+    if (la && left_pending) {
+        LB_CUDA_CHECK(cudaEventRecord(ev_left, sl));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_left, 0));
+    }
+    (void)left_pending;
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, su));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));

@@ -85,7 +85,8 @@ inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 struct Aux {
     cudaStream_t panel_stream = nullptr;   // high priority
     cudaStream_t update_stream = nullptr;
-    cudaEvent_t ev[8];
+    cudaStream_t side_stream = nullptr;    // low priority: work that is off the critical path (left-of-panel interchanges)
+    cudaEvent_t ev[16];
     bool ready = false;
 };
 Aux& aux();

@@ -59,7 +59,8 @@ Aux& aux() {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
         LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.panel_stream, cudaStreamNonBlocking, hi));
         LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.update_stream, cudaStreamNonBlocking, lo));
-        for (int i = 0; i < 8; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
+        LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.side_stream, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 16; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
         a.ready = true;
     }
     return a;

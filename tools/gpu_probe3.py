@@ -20,7 +20,7 @@ def cm(rows, cols, ld=None):
     return buf, torch.as_strided(buf, (rows, cols), (1, ld), 0)
 
 fails = 0
-L.lb200_set_gemm_config(3)
+L.lb200_set_gemm_config(12)
 for ta in "NT":
     for tb in "NT":
         for (m, n, k) in ((128, 128, 64), (256, 384, 128), (129, 131, 33), (1000, 777, 515), (4096, 300, 48), (5, 300, 35), (2048, 2048, 1000)):
@@ -56,7 +56,7 @@ for uplo in "LU":
 print("TMA gemm failures:", fails)
 
 for (m, n, k) in ((8192, 8192, 8192), (16384, 16384, 512), (16384, 16384, 256), (16384, 16384, 128), (32768, 32768, 512), (8192, 8192, 512), (4096, 4096, 512)):
-    for cfg in (3, 1):
+    for cfg in (12, 8):
         L.lb200_set_gemm_config(cfg)
         for (ta, tb) in (("N", "N"), ("N", "T"), ("T", "N")):
             if (ta, tb) != ("N", "N") and (m, n, k) != (16384, 16384, 512): continue
