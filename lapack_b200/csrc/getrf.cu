@@ -82,6 +82,9 @@ __device__ __forceinline__ unsigned long long poll_tag(const unsigned long long*
     return v;
 }
 
+// The column loop is NOT unrolled: after step c every thread stores its column-c value (final L or U entry)
+// and rotates its register window one column to the left, so that the active column is always a[0].  The loop
+// body therefore exists once in the instruction stream.
 template <int W, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
     constexpr int NWARP = THREADS / 32;
@@ -97,17 +100,22 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
     const int kmax = min(p.m, p.n);
 
     if (g >= p.G) {
-        // ===== interchange CTAs: one panel column per thread, follow the winner history (dgetrf2.f:236,263) =====
+        // ===== interchange CTAs: one panel column per thread, follow the winner history (dgetrf2.f:236,263).
+        // Columns of the leaf itself are included once they are final (column q < c has been stored by the work
+        // CTAs before their step-c packets, which CTA 0 acquired before releasing hist[c]).
         const int t = (g - p.G) * THREADS + tid;
-        const bool valid = t < p.sw_left + p.sw_right;
-        const int col = (t < p.sw_left) ? t : t + p.n;        // skip the leaf's own columns
-        double* colp = p.SW + (i64)col * p.lda;
+        const int width = p.sw_left + p.n + p.sw_right;
+        const bool valid = t < width;
+        const int own = t - p.sw_left;                        // index inside the leaf, if 0 <= own < n
+        double* colp = p.SW + (i64)t * p.lda;
+#pragma unroll 1
         for (int c = 0; c < kmax; ++c) {
             unsigned long long v = 0;
             if (lane == 0) v = poll_tag(p.hist + c, p.epoch_base + c + 1);
             v = __shfl_sync(0xffffffffu, v, 0);
             const int prow = (int)(unsigned)(v & 0xffffffffu);
-            if (valid && prow != c) {
+            const bool mine = valid && (own < 0 || own >= p.n || own < c);
+            if (mine && prow != c) {
                 double x = colp[c], y = colp[prow];
                 colp[c] = y;
                 colp[prow] = x;
@@ -118,122 +126,127 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
 
     const int row = g * THREADS + tid;          // panel-relative row owned by this thread
     const bool have = row < p.m;
-    double a[W];
+    double a[W];                                 // a[q] = A(row, c + q): window starting at the active column c
 #pragma unroll
-    for (int c = 0; c < W; ++c) a[c] = (have && c < p.n) ? p.A[row + (i64)c * p.lda] : 0.0;
+    for (int q = 0; q < W; ++q) a[q] = (have && q < p.n) ? p.A[row + (i64)q * p.lda] : 0.0;
 
+#pragma unroll 1
+    for (int c = 0; c < kmax; ++c) {
+        const int slot = c & 1;
+        const unsigned epoch = p.epoch_base + c + 1;
+        // (0) the owner of row c publishes the current top row
+        if (have && row == c) {
+            LeafPacket* tp = p.top + slot;
 #pragma unroll
-    for (int c = 0; c < W; ++c) {
-        if (c < kmax) {
-            const int slot = c & 1;
-            const unsigned epoch = p.epoch_base + c + 1;
-            // (0) the owner of row c publishes the current top row
-            if (have && row == c) {
-                LeafPacket* tp = p.top + slot;
+            for (int q = 0; q < W; ++q) tp->rowdata[q] = a[q];
+            st_release_u64(&tp->tag, ((unsigned long long)epoch << 32));
+        }
+        // (1) local arg-max over active rows (row >= c); IDAMAX semantics: first index of the max,
+        //     NaN never wins unless it is the very first element (idamax.f:103 strict '>').
+        double key = -1.0;
+        int krow = 0x7fffffff;
+        if (have && row >= c) {
+            double v = fabs(a[0]);
+            if (v != v) v = (row == c) ? CUDART_INF : -1.0;
+            key = v;
+            krow = row;
+        }
 #pragma unroll
-                for (int q = 0; q < W; ++q) tp->rowdata[q] = a[q];
-                st_release_u64(&tp->tag, ((unsigned long long)epoch << 32));
+        for (int off = 16; off > 0; off >>= 1) {
+            double ok = __shfl_xor_sync(0xffffffffu, key, off);
+            int orow = __shfl_xor_sync(0xffffffffu, krow, off);
+            if (cand_better(ok, orow, key, krow)) { key = ok; krow = orow; }
+        }
+        if (lane == 0) { s_key[warp] = key; s_row[warp] = krow; }
+        __syncthreads();
+        if (warp == 0) {
+            double k2 = (lane < NWARP) ? s_key[lane] : -1.0;
+            int r2 = (lane < NWARP) ? s_row[lane] : 0x7fffffff;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; }
             }
-            // (1) local arg-max over active rows (row >= c); IDAMAX semantics: first index of the max,
-            //     NaN never wins unless it is the very first element (idamax.f:103 strict '>').
-            double key = -1.0;
-            int krow = 0x7fffffff;
-            if (have && row >= c) {
-                double v = fabs(a[c]);
-                if (v != v) v = (row == c) ? CUDART_INF : -1.0;
-                key = v;
-                krow = row;
+            if (lane == 0) { s_loc_row = r2; s_loc_key = k2; }
+        }
+        __syncthreads();
+        // (2) the thread owning the CTA's best row publishes it (data first, tag last with release)
+        if (have && row == s_loc_row) {
+            LeafPacket* cp = p.cand + slot * p.G + g;
+            cp->key = s_loc_key;
+#pragma unroll
+            for (int q = 0; q < W; ++q) cp->rowdata[q] = a[q];
+            st_release_u64(&cp->tag, ((unsigned long long)epoch << 32) | (unsigned)row);
+        }
+        // (3)+(4) warp 0 waits for all G packets, picks the winner and fetches the two rows
+        if (warp == 0) {
+            double k2 = -2.0;
+            int r2 = 0x7fffffff, g2 = 0;
+            for (int q = lane; q < p.G; q += 32) {
+                const LeafPacket* cp = p.cand + slot * p.G + q;
+                unsigned long long tag = poll_tag(&cp->tag, epoch);
+                double ck = __ldcg(&cp->key);
+                int cr = (int)(unsigned)(tag & 0xffffffffu);
+                if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                double ok = __shfl_xor_sync(0xffffffffu, key, off);
-                int orow = __shfl_xor_sync(0xffffffffu, krow, off);
-                if (cand_better(ok, orow, key, krow)) { key = ok; krow = orow; }
+                double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                int og = __shfl_xor_sync(0xffffffffu, g2, off);
+                if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
             }
-            if (lane == 0) { s_key[warp] = key; s_row[warp] = krow; }
-            __syncthreads();
-            if (warp == 0) {
-                double k2 = (lane < NWARP) ? s_key[lane] : -1.0;
-                int r2 = (lane < NWARP) ? s_row[lane] : 0x7fffffff;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    double ok = __shfl_xor_sync(0xffffffffu, k2, off);
-                    int orow = __shfl_xor_sync(0xffffffffu, r2, off);
-                    if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; }
-                }
-                if (lane == 0) { s_loc_row = r2; s_loc_key = k2; }
+            if (lane < W) {
+                (void)poll_tag(&p.cand[slot * p.G + g2].tag, epoch);        // own acquire for the data below
+                (void)poll_tag(&p.top[slot].tag, epoch);
+                s_prow[lane] = __ldcg(&p.cand[slot * p.G + g2].rowdata[lane]);
+                s_trow[lane] = __ldcg(&p.top[slot].rowdata[lane]);
             }
-            __syncthreads();
-            // (2) the thread owning the CTA's best row publishes it (data first, tag last with release)
-            if (have && row == s_loc_row) {
-                LeafPacket* cp = p.cand + slot * p.G + g;
-                cp->key = s_loc_key;
-#pragma unroll
-                for (int q = 0; q < W; ++q) cp->rowdata[q] = a[q];
-                st_release_u64(&cp->tag, ((unsigned long long)epoch << 32) | (unsigned)row);
-            }
-            // (3)+(4) warp 0 waits for all G packets, picks the winner and fetches the two rows
-            if (warp == 0) {
-                double k2 = -2.0;
-                int r2 = 0x7fffffff, g2 = 0;
-                for (int q = lane; q < p.G; q += 32) {
-                    const LeafPacket* cp = p.cand + slot * p.G + q;
-                    unsigned long long tag = poll_tag(&cp->tag, epoch);
-                    double ck = __ldcg(&cp->key);
-                    int cr = (int)(unsigned)(tag & 0xffffffffu);
-                    if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    double ok = __shfl_xor_sync(0xffffffffu, k2, off);
-                    int orow = __shfl_xor_sync(0xffffffffu, r2, off);
-                    int og = __shfl_xor_sync(0xffffffffu, g2, off);
-                    if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
-                }
-                if (lane < W) {
-                    (void)poll_tag(&p.cand[slot * p.G + g2].tag, epoch);        // own acquire for the data below
-                    (void)poll_tag(&p.top[slot].tag, epoch);
-                    s_prow[lane] = __ldcg(&p.cand[slot * p.G + g2].rowdata[lane]);
-                    s_trow[lane] = __ldcg(&p.top[slot].rowdata[lane]);
-                }
-                if (lane == 0) {
-                    s_win_row = r2;
-                    if (g == 0) st_release_u64(p.hist + c, ((unsigned long long)epoch << 32) | (unsigned)r2);
-                }
-            }
-            __syncthreads();
-            const int prow = s_win_row;
-            const double pivot = s_prow[c];
-            // (5) interchange through the published copies (dgetrf2.f:196-200; whole rows of the leaf)
-            if (prow != c) {
-                if (have && row == prow) {
-#pragma unroll
-                    for (int q = 0; q < W; ++q) a[q] = s_trow[q];
-                } else if (have && row == c) {
-#pragma unroll
-                    for (int q = 0; q < W; ++q) a[q] = s_prow[q];
-                }
-            }
-            // (6) pivot index / singularity flag (dgetrf2.f:191-192,212-214)
-            if (g == 0 && tid == 0) {
-                p.ipiv[c] = prow + 1;
-                if (pivot == 0.0 && *p.info == 0) *p.info = p.info_off + c + 1;
-            }
-            // (7) scale (reciprocal unless |pivot| < SFMIN, dgetrf2.f:204-210) and rank-1 update
-            if (pivot != 0.0 && have && row > c) {
-                double l;
-                if (fabs(pivot) >= p.sfmin) l = a[c] * (1.0 / pivot);
-                else l = a[c] / pivot;
-                a[c] = l;
-#pragma unroll
-                for (int q = c + 1; q < W; ++q) a[q] = fma(-l, s_prow[q], a[q]);
+            if (lane == 0) {
+                s_win_row = r2;
+                if (g == 0) st_release_u64(p.hist + c, ((unsigned long long)epoch << 32) | (unsigned)r2);
             }
         }
+        __syncthreads();
+        const int prow = s_win_row;
+        const double pivot = s_prow[0];
+        // (5) interchange through the published copies (dgetrf2.f:196-200); columns left of c were already
+        //     stored and are exchanged in global memory by the interchange CTAs
+        if (prow != c) {
+            if (have && row == prow) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) a[q] = s_trow[q];
+            } else if (have && row == c) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) a[q] = s_prow[q];
+            }
+        }
+        // (6) pivot index / singularity flag (dgetrf2.f:191-192,212-214)
+        if (g == 0 && tid == 0) {
+            p.ipiv[c] = prow + 1;
+            if (pivot == 0.0 && *p.info == 0) *p.info = p.info_off + c + 1;
+        }
+        // (7) scale (reciprocal unless |pivot| < SFMIN, dgetrf2.f:204-210) and rank-1 update
+        if (pivot != 0.0 && have && row > c) {
+            double l;
+            if (fabs(pivot) >= p.sfmin) l = a[0] * (1.0 / pivot);
+            else l = a[0] / pivot;
+            a[0] = l;
+#pragma unroll
+            for (int q = 1; q < W; ++q) a[q] = fma(-l, s_prow[q], a[q]);
+        }
+        // (8) column c is final for every row: store it and slide the window
+        if (have) p.A[row + (i64)c * p.lda] = a[0];
+#pragma unroll
+        for (int q = 0; q + 1 < W; ++q) a[q] = a[q + 1];
+        a[W - 1] = 0.0;
     }
+    // wide leaf (m < n): the columns right of the last pivot are still in the window
     if (have) {
 #pragma unroll
-        for (int c = 0; c < W; ++c)
-            if (c < p.n) p.A[row + (i64)c * p.lda] = a[c];
+        for (int q = 0; q < W; ++q)
+            if (kmax + q < p.n) p.A[row + (i64)(kmax + q) * p.lda] = a[q];
     }
 }
 
@@ -258,6 +271,7 @@ static LeafWs& leaf_ws() {
         LB_CUDA_CHECK(cudaMemset(w.top, 0, sizeof(LeafPacket) * 2));
         LB_CUDA_CHECK(cudaMalloc(&w.hist, sizeof(unsigned long long) * LEAF_W));
         LB_CUDA_CHECK(cudaMemset(w.hist, 0, sizeof(unsigned long long) * LEAF_W));
+
     }
     return w;
 }
@@ -287,7 +301,7 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     p.SW = pc.P + off;
     p.sw_left = off;
     p.sw_right = pc.width - off - n;
-    const int S = ceil_div(p.sw_left + p.sw_right, LEAF_THREADS);
+    const int S = ceil_div(pc.width, LEAF_THREADS);
     getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G + S, LEAF_THREADS, 0, s>>>(p);
     count_launch();
     w.epoch += (unsigned)min(m, n);
@@ -340,40 +354,72 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
 
     const bool la = g_lookahead != 0;
     Aux& ax = aux();
-    cudaStream_t sp = la ? ax.panel_stream : s;    // panel stream
-    cudaStream_t su = la ? ax.update_stream : s;   // trailing-update stream
-    cudaStream_t sl = la ? ax.side_stream : s;     // interchanges left of the panel: off the critical path
+    // Streams (look-ahead on): sp = panel (highest priority), sq = memory-bound preparation of the trailing
+    // columns (interchanges + U12 solve, medium priority), su = trailing GEMMs (low priority), sl = interchanges
+    // left of the panel (low priority, off the critical path).  The trailing columns are processed in three
+    // chunks -- next panel's columns, a quarter of the rest, the remainder -- so that the preparation of chunk
+    // c+1 overlaps with the GEMM of chunk c.
+    cudaStream_t sp = la ? ax.panel_stream : s;
+    cudaStream_t sq = la ? ax.prep_stream : s;
+    cudaStream_t su = la ? ax.update_stream : s;
+    cudaStream_t sl = la ? ax.side_stream : s;
     cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2], ev_plan = ax.ev[8], ev_left = ax.ev[9];
+    cudaEvent_t ev_gemm = ax.ev[10];
+    cudaEvent_t ev_prep[3] = {ax.ev[11], ax.ev[12], ax.ev[13]};
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_join, 0));
         LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_join, 0));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_join, 0));
     }
-    bool left_pending = false;
     // first panel
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
+    bool gemm_recorded = false;
 
     for (int j = 0; j < mn; j += nb) {
         const int jb = min(nb, mn - j);
         const int jn = j + jb;                       // first column after this panel
-        if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_panel, 0));
         double* Ajj = A + j + (i64)j * lda;
         const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
-        // one plan for this panel's interchanges (dgetrf.f:193,199), applied to three column ranges
-        void* plan = laswp_plan(su, j + 1, jn, piv, 1);
-        // columns of the next panel first (look-ahead), then the rest
+        if (la) {
+            LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
+            if (gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));   // update j-1 is complete
+        }
+        // one plan for this panel's interchanges (dgetrf.f:193,199), applied to all column ranges
+        void* plan = laswp_plan(sq, j + 1, jn, piv, 1);
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
+        // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel)
+        int c[4];
+        int nchunk = 0;
+        c[0] = jn;
         if (jn < n) {
-            const int w1 = (jb2 > 0) ? jb2 : (n - jn);       // width of the first slab
-            double* A12 = A + j + (i64)jn * lda;
-            laswp_apply_plan(su, w1, A + (i64)jn * lda, lda, plan, jb);                      // dgetrf.f:199
-            trsm(su, 'L', 'L', 'N', 'U', jb, w1, 1.0, Ajj, lda, A12, lda);                   // dgetrf.f:204
+            const int w1 = (jb2 > 0) ? jb2 : (n - jn);
+            c[++nchunk] = jn + w1;
+            const int rest = n - jn - w1;
+            if (rest > 0) {
+                int h1 = (rest >= 4096) ? ((rest / 4 + 63) / 64) * 64 : rest;
+                c[++nchunk] = jn + w1 + h1;
+                if (h1 < rest) c[++nchunk] = n;
+            }
+        }
+        // preparation on sq: interchanges + block row of U for every chunk, in order
+        for (int q = 0; q < nchunk; ++q) {
+            const int w = c[q + 1] - c[q];
+            laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);                              // dgetrf.f:199
+            trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);         // dgetrf.f:204
+            if (la) LB_CUDA_CHECK(cudaEventRecord(ev_prep[q], sq));
+        }
+        if (la) LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
+        // GEMMs on su; the next panel is factored right after the first chunk
+        for (int q = 0; q < nchunk; ++q) {
+            const int w = c[q + 1] - c[q];
+            if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_prep[q], 0));
             if (jn < m)
-                gemm(su, 'N', 'N', m - jn, w1, jb, -1.0, A + jn + (i64)j * lda, lda, A12, lda, 1.0,
-                     A + jn + (i64)jn * lda, lda);                                          // dgetrf.f:212
-            if (jb2 > 0) {
+                gemm(su, 'N', 'N', m - jn, w, jb, -1.0, A + jn + (i64)j * lda, lda, A + j + (i64)c[q] * lda, lda, 1.0,
+                     A + jn + (i64)c[q] * lda, lda);                                                   // dgetrf.f:212
+            if (q == 0 && jb2 > 0) {
                 if (la) {
                     LB_CUDA_CHECK(cudaEventRecord(ev_next, su));
                     LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_next, 0));
@@ -382,39 +428,25 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
                 iadd(sp, min(m - jn, jb2), ipiv + jn, jn);                                   // dgetrf.f:187-189
                 if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
-                const int rest = n - jn - w1;
-                if (rest > 0) {
-                    double* A13 = A + j + (i64)(jn + w1) * lda;
-                    laswp_apply_plan(su, rest, A + (i64)(jn + w1) * lda, lda, plan, jb);
-                    trsm(su, 'L', 'L', 'N', 'U', jb, rest, 1.0, Ajj, lda, A13, lda);
-                    if (jn < m)
-                        gemm(su, 'N', 'N', m - jn, rest, jb, -1.0, A + jn + (i64)j * lda, lda, A13, lda, 1.0,
-                             A + jn + (i64)(jn + w1) * lda, lda);
-                }
             }
         }
-        // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns: the only
-        // remaining reader is the trailing GEMM of the PREVIOUS step (its L21 operand), which precedes this point
-        // on `su`.  So the left interchanges wait for `su` to get here and then run on a low-priority side
-        // stream, concurrently with this step's trailing update instead of in front of the next one.
-        if (la) {
-            LB_CUDA_CHECK(cudaEventRecord(ev_plan, su));
-            LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
-        }
+        if (la) { LB_CUDA_CHECK(cudaEventRecord(ev_gemm, su)); gemm_recorded = true; }
+        // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns whose only
+        // remaining reader was the trailing GEMM of the previous step (sq waited for it above), so they run on
+        // a low-priority side stream concurrently with this step's trailing update.
+        if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
         if (j > 0) laswp_apply_plan(sl, j, A, lda, plan, jb);
         laswp_plan_free(sl, plan);
-        left_pending = true;
     }
-    if (la && left_pending) {
+    if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_left, sl));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_left, 0));
-    }
-    (void)left_pending;
-    if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, su));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_join, 0));
         LB_CUDA_CHECK(cudaEventRecord(ev_next, sp));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_next, 0));
+        LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_plan, 0));
     }
 }
 

@@ -1,0 +1,107 @@
+"""LAPACKE layer on the GPU: our LAPACKE_* entry points and the REFERENCE's own LAPACKE C layer (compiled in place
+from /root/reference into oracle/_ref/liblapacke_ref.so, bound to our Fortran symbols) must agree with the oracle for
+both matrix layouts (LAPACKE/src/lapacke_dgetrf_work.c:45-70 row-major semantics)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = (1988, 1989, 1990, 1991)
+ROW, COL = 101, 102
+
+
+def vp(x):
+    return x.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def libs():
+    import lapack_b200
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ours = lapack_b200.lib()
+    ours.lb200_set_xerbla_mode(2)
+    out = [("ours", ours)]
+    so = os.path.join(ROOT, "oracle", "_ref", "liblapacke_ref.so")
+    if os.path.exists(so):
+        out.append(("reference-lapacke", C.CDLL(so, mode=C.RTLD_GLOBAL)))
+    return out
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dgetrf_dgetrs_dgesv(libs, layout):
+    for name, L in libs:
+        for (m, n) in ((40, 40), (300, 200), (200, 300)):
+            a, seed = O.random_matrix(m, n, SEED)
+            ref = a.copy(order="F")
+            ipiv_ref, _ = O.dgetrf(ref)
+            buf = np.array(a, order="C" if layout == ROW else "F", copy=True)
+            lda = n if layout == ROW else m
+            ipiv = np.zeros(min(m, n), dtype=np.int32)
+            assert L.LAPACKE_dgetrf(layout, m, n, vp(buf), lda, vp(ipiv)) == 0, name
+            assert np.array_equal(ipiv, ipiv_ref), name
+            assert np.max(np.abs(buf - ref)) < 1e-11, name
+        n, nrhs = 250, 3
+        a, seed = O.random_matrix(n, n, SEED)
+        x, _ = O.random_matrix(n, nrhs, seed)
+        b = a @ x
+        abuf = np.array(a, order="C" if layout == ROW else "F", copy=True)
+        bbuf = np.array(b, order="C" if layout == ROW else "F", copy=True)
+        ipiv = np.zeros(n, dtype=np.int32)
+        assert L.LAPACKE_dgesv(layout, n, nrhs, vp(abuf), n, vp(ipiv), vp(bbuf), nrhs if layout == ROW else n) == 0
+        assert np.max(np.abs(bbuf - x)) < 1e-10, name
+        b2 = np.array(b, order="C" if layout == ROW else "F", copy=True)
+        assert L.LAPACKE_dgetrs(layout, C.c_char(b"N"), n, nrhs, vp(abuf), n, vp(ipiv), vp(b2), nrhs if layout == ROW else n) == 0
+        assert np.max(np.abs(b2 - x)) < 1e-10, name
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+@pytest.mark.parametrize("uplo", ["L", "U"])
+def test_lapacke_dpotrf_dposv(libs, layout, uplo):
+    for name, L in libs:
+        n, nrhs = 220, 2
+        s, seed = O.spd_matrix(n, SEED)
+        ref = s.copy(order="F")
+        assert O.dpotrf(uplo, ref) == 0
+        buf = np.array(s, order="C" if layout == ROW else "F", copy=True)
+        assert L.LAPACKE_dpotrf(layout, C.c_char(uplo.encode()), n, vp(buf), n) == 0, name
+        tri = np.tril if uplo == "L" else np.triu
+        assert np.max(np.abs(tri(buf) - tri(ref))) < 1e-12, name
+        x, _ = O.random_matrix(n, nrhs, seed)
+        b = s @ x
+        abuf = np.array(s, order="C" if layout == ROW else "F", copy=True)
+        bbuf = np.array(b, order="C" if layout == ROW else "F", copy=True)
+        assert L.LAPACKE_dposv(layout, C.c_char(uplo.encode()), n, nrhs, vp(abuf), n, vp(bbuf), nrhs if layout == ROW else n) == 0
+        assert np.max(np.abs(bbuf - x)) < 1e-10, name
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dgeqrf(libs, layout):
+    for name, L in libs:
+        m, n = 260, 180
+        a, _ = O.random_matrix(m, n, SEED)
+        ref = a.copy(order="F")
+        tau_ref, _, _ = O.dgeqrf(ref)
+        buf = np.array(a, order="C" if layout == ROW else "F", copy=True)
+        tau = np.zeros(n)
+        assert L.LAPACKE_dgeqrf(layout, m, n, vp(buf), n if layout == ROW else m, vp(tau)) == 0, name
+        assert np.max(np.abs(buf - ref)) < 1e-10 and np.max(np.abs(tau - tau_ref)) < 1e-11, name
+
+
+def test_lapacke_nancheck_and_singular(libs):
+    for name, L in libs:
+        a, _ = O.random_matrix(50, 50, SEED)
+        a[:, 9] = 0.0
+        ipiv = np.zeros(50, dtype=np.int32)
+        buf = a.copy(order="F")
+        assert L.LAPACKE_dgetrf(COL, 50, 50, vp(buf), 50, vp(ipiv)) == 10, name        # INFO = zero-pivot column
+        buf = a.copy(order="F")
+        buf[3, 4] = np.nan
+        assert L.LAPACKE_dgetrf(COL, 50, 50, vp(buf), 50, vp(ipiv)) == -4, name        # NaN pre-check
