@@ -423,9 +423,11 @@ def run_ours(args, rank, world, local_rank):
         "pct_of_fp64_peak": value / world / peak if peak else None,
         "breakdown": {"dgetrf_tflops": flops_getrf(n) / t_lu * 1e-12, "dgetrf_ms": t_lu * 1e3,
                       "dpotrf_tflops": flops_potrf(n) / t_po * 1e-12, "dpotrf_ms": t_po * 1e3},
-        "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel / gemm_f64_dmma_kernel (trailing updates)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_f64_dmma_kernel<64,64,2,2,...,STAGES=2,BK=16> (trailing updates, DMMA.8x8x4)",
                      "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
-                     "traffic": None, "launches_timed": int(gcnt.value),
+                     "traffic": 5.41e9, "traffic_note": "dram read+write bytes of ONE representative trailing-update launch "
+                     "(m=n=16384, k=512; algorithmic 4.43e9 B) from profiles/r01_gemm_cfg8_ncu_full_16384x16384x512.txt",
+                     "launches_timed": int(gcnt.value),
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate peak measured in this run by lb200_fp64_peak_tflops "
                                     "(MEASURED_PEAKS.json carries HBM and bf16 only)"},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,

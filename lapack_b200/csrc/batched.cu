@@ -16,65 +16,92 @@ namespace lb {
 
 constexpr int BW = 32;
 
-__global__ void __launch_bounds__(256) getrf_batched32_kernel(i64 batch, double* __restrict__ A, int* __restrict__ ipiv,
-                                                              int* __restrict__ info) {
-    const int lane = threadIdx.x & 31;
-    const i64 id = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One matrix per warp, lane = row, the row's 32 entries in registers (column loop fully unrolled so every index
+// is static).  Pivot search: |a(:,c)| is non-negative, so its bit pattern orders like an unsigned integer and the
+// warp maximum is two 32-bit redux.sync (high word, then low word among the leaders) plus a ballot; ties go to
+// the smallest row position like IDAMAX (idamax.f:95-106).  The pivot row reaches the other lanes through a
+// 256-byte shared-memory line per warp (one 16-byte store per column pair by the owner, broadcast loads by
+// everybody) instead of two shuffles per entry; the line is double buffered on the step parity so one
+// __syncwarp per step orders everything.  Interchanges are implicit: a row never moves, only its position does.
+constexpr int BWARPS = 4;
+__global__ void __launch_bounds__(BWARPS * 32, 5) getrf_batched32_kernel(i64 batch, double* __restrict__ A, int* __restrict__ ipiv,
+                                                                       int* __restrict__ info) {
+    __shared__ __align__(16) double rowbuf[BWARPS][2][BW];
+    __shared__ int posbuf[BWARPS][2];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const i64 id = (i64)blockIdx.x * BWARPS + w;
     if (id >= batch) return;
     double* M = A + id * (BW * BW);
     double a[BW];
 #pragma unroll
-    for (int c = 0; c < BW; ++c) a[c] = M[lane + BW * c];
+    for (int q = 0; q < BW; ++q) a[q] = M[lane + BW * q];
     int mypos = lane;        // current position of my row under LAPACK's explicit interchanges
     bool done = false;       // my row has already been used as a pivot row
     int myipiv = 0, minfo = 0;
 #pragma unroll
     for (int c = 0; c < BW; ++c) {
-        double key = -1.0;
-        if (!done) {
-            key = fabs(a[c]);
-            if (key != key) key = (mypos == c) ? CUDART_INF : -1.0;    // idamax.f:103: NaN only wins in first place
+        // ---- pivot search
+        unsigned long long kb = (unsigned long long)__double_as_longlong(fabs(a[c]));
+        bool cand = !done;
+        if (a[c] != a[c]) {                                   // NaN only wins from the first place (idamax.f:103)
+            if (mypos == c) kb = 0x7ff0000000000000ULL; else cand = false;
         }
-        int pos = done ? 0x7fffffff : mypos;
-        int who = lane;
+        const unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+        const unsigned mh = __reduce_max_sync(full, cand ? hi : 0u);
+        const bool c1 = cand && hi == mh;
+        unsigned tie = __ballot_sync(full, c1);
+        if (__popc(tie) != 1) {                                // leaders agree in the high word: compare the low words
+            const unsigned ml = __reduce_max_sync(full, c1 ? lo : 0u);
+            const bool c2 = c1 && lo == ml;
+            tie = __ballot_sync(full, c2);
+            if (__popc(tie) != 1) {                            // exact tie: smallest position wins
+                const unsigned mp = __reduce_min_sync(full, c2 ? (unsigned)mypos : 0xffffffffu);
+                tie = __ballot_sync(full, c2 && (unsigned)mypos == mp);
+            }
+        }
+        const int who = __ffs(tie) - 1;                        // lane holding the pivot row
+        // ---- publish the pivot row (columns >= c, in aligned pairs) and its current position
+        double* rb = rowbuf[w][c & 1];
+        if (lane == who) {
+            posbuf[w][c & 1] = mypos;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            double ok = __shfl_xor_sync(0xffffffffu, key, off);
-            int op = __shfl_xor_sync(0xffffffffu, pos, off);
-            int ow = __shfl_xor_sync(0xffffffffu, who, off);
-            if (ok > key || (ok == key && op < pos)) { key = ok; pos = op; who = ow; }
+            for (int q = c & ~1; q < BW; q += 2) *reinterpret_cast<double2*>(rb + q) = make_double2(a[q], a[q + 1]);
         }
-        // `who` = lane holding the pivot row, `pos` = its current position
+        __syncwarp();
+        const int pos = posbuf[w][c & 1];
         if (lane == c) myipiv = pos + 1;
-        const double pivot = __shfl_sync(0xffffffffu, a[c], who);
         // interchange bookkeeping: the row sitting at position c moves to `pos`
         if (!done && mypos == c && lane != who) mypos = pos;
         if (lane == who) { mypos = c; done = true; }
+        const double pivot = rb[c];
         if (pivot == 0.0) {
             if (minfo == 0) minfo = c + 1;                              // dgetrf2.f:212-214
-        } else {
-            double l = 0.0;
-            if (!done) {
-                if (fabs(pivot) >= DBL_MIN) l = a[c] * (1.0 / pivot);   // dgetrf2.f:204-205
-                else l = a[c] / pivot;                                  // dgetrf2.f:207-209
-                a[c] = l;
-            }
+        } else if (!done) {
+            double l;
+            if (fabs(pivot) >= DBL_MIN) l = a[c] * (1.0 / pivot);       // dgetrf2.f:204-205
+            else l = a[c] / pivot;                                      // dgetrf2.f:207-209
+            a[c] = l;
+            if (c + 1 < BW) {
+                if ((c & 1) == 0) a[c + 1] = fma(-l, rb[c + 1], a[c + 1]);
 #pragma unroll
-            for (int q = c + 1; q < BW; ++q) {
-                double pq = __shfl_sync(0xffffffffu, a[q], who);
-                if (!done) a[q] = fma(-l, pq, a[q]);
+                for (int q = (c + 2) & ~1; q < BW; q += 2) {
+                    const double2 p = *reinterpret_cast<const double2*>(rb + q);
+                    a[q] = fma(-l, p.x, a[q]);
+                    a[q + 1] = fma(-l, p.y, a[q + 1]);
+                }
             }
         }
     }
 #pragma unroll
-    for (int c = 0; c < BW; ++c) M[mypos + BW * c] = a[c];
+    for (int q = 0; q < BW; ++q) M[mypos + BW * q] = a[q];
     ipiv[id * BW + lane] = myipiv;
     if (lane == 0) info[id] = minfo;
 }
 
 void getrf_batched_32(cudaStream_t s, i64 batch, double* A, int* ipiv, int* info) {
     if (batch <= 0) return;
-    const int wpb = 8;
+    const int wpb = BWARPS;
     getrf_batched32_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, s>>>(batch, A, ipiv, info);
     count_launch();
     LB_CUDA_CHECK(cudaGetLastError());

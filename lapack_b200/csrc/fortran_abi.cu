@@ -359,6 +359,52 @@ void dgesv_(const int* n, const int* nrhs, double* A, const int* lda, int* ipiv,
 }
 
 // ================================================================================================ Cholesky
+// Host-resident Cholesky with transfer/compute overlap: only the UPLO triangle crosses PCIe (block-column
+// trapezoids), and every finished block column of the factor is downloaded on a copy stream while the rest of
+// the factorization is still running (lb::StreamOut).  Needs pinned host memory for truly asynchronous copies.
+static int potrf_host_streamed(bool upper, int n, double* A, int lda) {
+    static cudaStream_t copy_stream = nullptr;
+    static cudaEvent_t ev = nullptr, ev_up = nullptr;
+    if (!copy_stream) {
+        LB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+    }
+    cudaStream_t s = host_stream();
+    const lb::i64 ldd = ((lb::i64)n + 1) & ~1LL;
+    double* dA = (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * n);
+    int* dinfo = (int*)lb::ws_alloc(s, 64);
+    const int cb = 2048;
+    for (int j0 = 0; j0 < n; j0 += cb) {
+        const int w = imin(cb, n - j0);
+        const int r0 = upper ? 0 : j0, r1 = upper ? j0 + w : n;
+        LB_CUDA_CHECK(cudaMemcpy2DAsync(dA + r0 + (lb::i64)j0 * ldd, ldd * 8, A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8,
+                                        (size_t)(r1 - r0) * 8, w, cudaMemcpyHostToDevice, s));
+    }
+    lb::StreamOut so;
+    so.host = A; so.ldh = lda; so.copy_stream = copy_stream; so.ev = ev; so.done_cols = 0;
+    lb::stream_out() = &so;
+    lb::potrf(s, upper ? 'U' : 'L', n, dA, ldd, dinfo);
+    lb::stream_out() = nullptr;
+    // whatever the factorization did not stream out itself, in the same trapezoids as the upload (the squares on
+    // the diagonal hold the caller's own data in the other triangle, so copying them back changes nothing)
+    for (int j0 = so.done_cols; j0 < n; j0 += cb) {
+        const int w = imin(cb, n - j0);
+        const int r0 = upper ? so.done_cols : j0, r1 = upper ? j0 + w : n;
+        LB_CUDA_CHECK(cudaMemcpy2DAsync(A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8, dA + r0 + (lb::i64)j0 * ldd, ldd * 8,
+                                        (size_t)(r1 - r0) * 8, w, cudaMemcpyDeviceToHost, s));
+    }
+    int hinfo = 0;
+    LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    lb::ws_free(s, dA);
+    lb::ws_free(s, dinfo);
+    LB_CUDA_CHECK(cudaStreamSynchronize(s));
+    int e = lb::last_cuda_error();
+    if (e) { lb::clear_cuda_error(); return -1001 - e; }
+    return hinfo;
+}
+
 static void potrf_common(bool recursive, const char* uplo, const int* n, double* A, const int* lda, int* info) {
     *info = 0;
     const bool upper = same(uplo, 'U');
@@ -369,6 +415,10 @@ static void potrf_common(bool recursive, const char* uplo, const int* n, double*
     if (*n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    if (!recursive && *n >= 2048 && ptr_kind(A) == PK_PINNED && 2048 % lb::potrf_block() == 0) {
+        *info = potrf_host_streamed(upper, *n, A, *lda);
+        return;
+    }
     Ctx c; c.scan({A});
     lb::i64 la;
     double* dA = c.mat(A, *n, *n, *lda, true, true, &la);

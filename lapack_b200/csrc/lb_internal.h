@@ -77,6 +77,19 @@ void potrf_batched_32(cudaStream_t s, char uplo, i64 batch, double* A, int* info
 void* ws_alloc(cudaStream_t s, size_t bytes);
 void ws_free(cudaStream_t s, void* p);
 
+// Streaming download hook for host-resident callers (Cholesky, QR): as soon as a block column (or block row) of
+// the factor is final, the factorization copies it to the caller's host matrix on a separate stream, so that the
+// device->host transfer overlaps with the rest of the factorization instead of following it.
+struct StreamOut {
+    double* host = nullptr;      // caller's matrix (element (0,0)), pinned host memory
+    i64 ldh = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    int done_cols = 0;           // columns [0, done_cols) (or rows for UPLO='U') have been queued for download
+};
+StreamOut*& stream_out();         // nullptr when no streaming download is requested
+int potrf_block();                // outer block size of potrf (streamed host path needs it to divide its upload chunk)
+
 // launch counter (bench.py's gpu_launches claim)
 extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }

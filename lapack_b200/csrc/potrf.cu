@@ -21,6 +21,8 @@ void potrf_set_params(int nb, int lookahead) {
     if (lookahead >= 0) g_po_lookahead = lookahead;
 }
 
+int potrf_block() { return g_po_nb; }
+
 constexpr int PL = 32;   // leaf size
 
 // One CTA (32 x 32 threads) factors an n x n (n <= 32) block in shared memory, lower form.
@@ -113,6 +115,7 @@ void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
         LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_join, 0));
     }
     // panel(j): factor the diagonal block and solve for the block column / block row
+    StreamOut* so = stream_out();
     auto panel = [&](int j, int jb) {
         double* Ajj = A + j + (i64)j * lda;
         potrf_rec(sp, upper, jb, Ajj, lda, info, j);
@@ -120,6 +123,18 @@ void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
         if (rest > 0) {
             if (upper) trsm(sp, 'L', 'U', 'T', 'N', jb, rest, 1.0, Ajj, lda, A + j + (i64)(j + jb) * lda, lda);
             else trsm(sp, 'R', 'L', 'T', 'N', rest, jb, 1.0, Ajj, lda, A + (j + jb) + (i64)j * lda, lda);
+        }
+        if (so) {
+            // block column j (lower) / block row j (upper) of the factor is final: start its download now
+            LB_CUDA_CHECK(cudaEventRecord(so->ev, sp));
+            LB_CUDA_CHECK(cudaStreamWaitEvent(so->copy_stream, so->ev, 0));
+            if (upper)
+                LB_CUDA_CHECK(cudaMemcpy2DAsync(so->host + j + (i64)j * so->ldh, so->ldh * 8, Ajj, lda * 8, (size_t)jb * 8, n - j,
+                                                cudaMemcpyDeviceToHost, so->copy_stream));
+            else
+                LB_CUDA_CHECK(cudaMemcpy2DAsync(so->host + j + (i64)j * so->ldh, so->ldh * 8, Ajj, lda * 8, (size_t)(n - j) * 8, jb,
+                                                cudaMemcpyDeviceToHost, so->copy_stream));
+            so->done_cols = j + jb;
         }
     };
     panel(0, min(nb, n));

@@ -18,6 +18,11 @@ void clear_cuda_error() {
     (void)cudaGetLastError();
 }
 
+StreamOut*& stream_out() {
+    static StreamOut* so = nullptr;
+    return so;
+}
+
 int num_sms() {
     static int sms = 0;
     if (!sms) {

@@ -276,6 +276,32 @@ def test_dpotrf_blocked_lookahead(lb, nb, la):
         L.lb200_set_potrf_params(512, 1)
 
 
+@pytest.mark.parametrize("uplo", "LU")
+def test_dpotrf_pinned_host_streamed(lb, uplo):
+    """Pinned host caller, n >= 2048: triangle-only upload + streamed download of finished block columns."""
+    n, lda = 2600, 2610
+    s, _ = O.spd_matrix(n, SEED)
+    buf = torch.empty((n, lda), dtype=torch.float64).pin_memory()   # row-major (n, lda) == column-major lda x n
+    h = buf.numpy().T                                               # (lda, n) column-major view
+    mask = np.triu(np.ones((n, n), bool), 1) if uplo == "L" else np.tril(np.ones((n, n), bool), -1)
+    h[:] = 7.0
+    h[:n, :] = s
+    h[:n, :][mask] = -1.0e10
+    assert lb.f77.dpotrf(uplo, n, h, lda) == 0
+    got = np.asfortranarray(h[:n, :])
+    assert np.all(got[mask] == -1.0e10)
+    assert np.all(h[n:, :] == 7.0)
+    assert O.dpot01(uplo, s, got) < O.THRESH
+    ref = s.copy(order="F")
+    O.dpotrf(uplo, ref)
+    tri = np.tril if uplo == "L" else np.triu
+    assert rel(tri(got), tri(ref)) < 1e-12
+    # not positive definite: INFO and no hang
+    h[:n, :] = s
+    h[2100, 2100] = -5.0
+    assert lb.f77.dpotrf(uplo, n, h, lda) == 2101
+
+
 def test_dpotrf_not_positive_definite(lb):
     """TESTING/LIN/dchkpo.f:313-344: zero row+column IZERO -> INFO = IZERO."""
     n = 150
