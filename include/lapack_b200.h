@@ -34,6 +34,9 @@ void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* l
 void lb200_set_gemm_config(int cfg);   /* -1 auto, 0/1/2 force a cp.async tile shape, 3 force the TMA kernel */
 void lb200_set_gemm_tma(int on);       /* 0 disables the TMA fast path (falls back to cp.async) */
 void lb200_set_getrf_params(int nb, int leaf, int lookahead);
+/* panels of at most ctas*1024 rows are factored by the thread-block-cluster leaf kernel (default 8, 0 = never, max 16) */
+void lb200_set_getrf_cluster_max(int ctas);
+void lb200_set_geqrf_cluster_max(int ctas);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);
 

@@ -48,6 +48,8 @@ def _declare(L):
     L.lb200_fp64_peak_tflops.argtypes = [VP, i, i, i, i]
     L.lb200_set_gemm_config.argtypes = [i]
     L.lb200_set_getrf_params.argtypes = [i, i, i]
+    L.lb200_set_getrf_cluster_max.argtypes = [i]
+    L.lb200_set_geqrf_cluster_max.argtypes = [i]
     L.lb200_set_potrf_params.argtypes = [i, i]
     L.lb200_set_geqrf_params.argtypes = [i, i]
     L.lb200_dgemm.argtypes = [VP, ch, ch, i, i, i, d, VP, LL, VP, LL, d, VP, LL]

@@ -411,8 +411,9 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
     // the slices go to scratch and are summed in a fixed order (deterministic).
     {
         i64 t64 = (i64)ceil_div(m, 64) * ceil_div(n, 64);
-        if (t64 * 4 <= num_sms() && k >= 4096) {
-            int nz = (int)min((i64)(k / 1024), (i64)(2 * num_sms()) / t64);
+        if (t64 * 4 <= num_sms() && k >= 1024) {
+            // slices of at least 256 in K, about two CTAs per SM in total
+            int nz = (int)min((i64)(k / 256), (i64)(2 * num_sms()) / t64);
             if (nz >= 2) {
                 int kchunk = ceil_div(ceil_div(k, nz), BK) * BK;
                 nz = ceil_div(k, kchunk);

@@ -226,6 +226,229 @@ __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_kernel(QrLeafParams p) 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cluster leaf (panels of at most 16 x 1024 rows): the CTAs form one thread-block cluster and the per-column
+// reduction travels through distributed shared memory + the hardware cluster barrier.  R rows per thread
+// (row = g*R*THREADS + r*THREADS + tid); the W-column window rotates so that the active column is a[.][0] and the
+// column loop exists once in the instruction stream.  At step c the window holds, at positions
+//   0          : column c (the vector being reduced),
+//   1..live-1  : columns c+1..W-1 (to be updated),            live = W - c
+//   live..W-1  : the finished reflectors v_0..v_{c-1} (position W-1 = v_{c-1}).
+// One fused reduction per column gives  sum x^2,  x^T C(:,q)  and the dots  v_i^T v_{c-1}  that DLARFT needs.
+__device__ __forceinline__ void qcl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void qcl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned qcl_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double qcl_ld(unsigned addr, unsigned rank) {
+    unsigned ra;
+    double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles instead of 80: every round each lane gives
+// away half of its values.  On return v[0] in lane l is the warp total of value index l >> 1.
+__device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane) {
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const bool hi = lane & 16;
+        const double send = hi ? v[j] : v[j + 8], keep = hi ? v[j + 8] : v[j];
+        v[j] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const bool hi = lane & 8;
+        const double send = hi ? v[j] : v[j + 4], keep = hi ? v[j + 4] : v[j];
+        v[j] = keep + __shfl_xor_sync(full, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const bool hi = lane & 4;
+        const double send = hi ? v[j] : v[j + 2], keep = hi ? v[j + 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(full, send, 4);
+    }
+    {
+        const bool hi = lane & 2;
+        const double send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(full, send, 2);
+    }
+    v[0] += __shfl_xor_sync(full, v[0], 1);
+}
+
+template <int W, int THREADS, int R>
+__global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafParams p) {
+    static_assert(W == 16, "warp_reduce16 handles 16 values");
+    constexpr int NWARP = THREADS / 32;
+    constexpr int ROWS = THREADS * R;
+    __shared__ double s_red[NWARP][W];
+    __shared__ __align__(16) double s_part[2][W];
+    __shared__ __align__(16) double s_top[2][W];
+    __shared__ double s_tot[W];
+    __shared__ double s_trow[W];
+    __shared__ double s_hh[4];        // tau, beta, scale of the current reflector
+    __shared__ double s_G[W][W];      // s_G[i][c] = V(:,i)^T v_c, i < c
+    __shared__ double s_tau[W];
+    __shared__ double s_T[W][W];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x;
+    const int C = p.G;
+    const int row0 = g * ROWS + tid;
+    const int kmax = min(p.m, p.n);
+    const unsigned part_base = qcl_smem(&s_part[0][0]);
+    const unsigned top_base = qcl_smem(&s_top[0][0]);
+
+    double a[R][W];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * THREADS;
+#pragma unroll
+        for (int q = 0; q < W; ++q) a[r][q] = (row < p.m && q < p.n) ? p.A[row + (i64)q * p.lda] : 0.0;
+    }
+
+    // step c = 0..kmax-1: reflector c; step c = kmax: only the v_i^T v_{kmax-1} dots
+#pragma unroll 1
+    for (int c = 0; c <= kmax; ++c) {
+        const int slot = c & 1;
+        const int live = W - c;
+        const int pc = c - 1;
+        const bool main_step = c < kmax;
+        double red[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) red[q] = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r * THREADS;
+            if (row < p.m) {
+                const double x = (main_step && row > c) ? a[r][0] : 0.0;
+                // finished reflector v_pc sits at position W-1 (unit diagonal at row pc, zero above)
+                const double vp = (c >= 1 && row >= pc) ? ((row == pc) ? 1.0 : a[r][W - 1]) : 0.0;
+                red[0] = fma(main_step ? x : vp, a[r][0], red[0]);   // x^2, or v_0^T v_pc at the extra step of a full leaf
+#pragma unroll
+                for (int q = 1; q < W; ++q) red[q] = fma((q < live) ? x : vp, a[r][q], red[q]);   // q = W-1 is live only at c = 0
+            }
+        }
+        warp_reduce16(red, lane);
+        if ((lane & 1) == 0) s_red[warp][lane >> 1] = red[0];
+        __syncthreads();
+        if (tid < W) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) v += s_red[w][tid];
+            s_part[slot][tid] = v;
+        }
+        if (main_step && row0 == c) {                          // row c always lives in CTA 0, r = 0
+#pragma unroll
+            for (int q = 0; q < W; ++q) s_top[slot][q] = a[0][q];
+        }
+        qcl_arrive();
+        qcl_wait();
+        if (warp == 0) {
+            if (lane < W) {
+                double v = 0.0;
+                for (int q = 0; q < C; ++q) v += qcl_ld(part_base + (slot * W + lane) * 8, (unsigned)q);
+                s_tot[lane] = v;
+                // DLARFG (dlarfg.f:140-186) with xnorm^2 = total[0]; every lane of the half-warp gets total[0]
+                const double t0 = __shfl_sync(0x0000ffffu, v, 0);
+                const double alpha = main_step ? qcl_ld(top_base + (slot * W + 0) * 8, 0u) : 0.0;
+                if (lane == 0 && main_step) {
+                    const double xnorm = sqrt(t0);
+                    double tau = 0.0, beta = alpha, scale = 0.0;
+                    if (xnorm != 0.0) {
+                        beta = -copysign(dev_dlapy2(alpha, xnorm), alpha);
+                        tau = (beta - alpha) / beta;
+                        scale = 1.0 / (alpha - beta);
+                    }
+                    s_hh[0] = tau; s_hh[1] = beta; s_hh[2] = scale;
+                    s_tau[c] = tau;
+                    if (g == 0) p.tau[c] = tau;
+                }
+            } else if (main_step) {
+                s_trow[lane - W] = qcl_ld(top_base + (slot * W + (lane - W)) * 8, 0u);
+            }
+        }
+        __syncthreads();
+        if (c >= 1 && tid < pc) s_G[tid][pc] = s_tot[live + tid];      // position live+i holds v_i
+        if (main_step) {
+            const double tau = s_hh[0], beta = s_hh[1], scale = s_hh[2];
+            if (tau != 0.0) {
+                // w(q) = C(1,q) + v2^T C2(:,q)  (dlarf1f.f:247-250);  C -= tau*v*w^T (dlarf1f.f:256-258)
+                double tw[W];
+#pragma unroll
+                for (int q = 1; q < W; ++q) tw[q] = -tau * (s_trow[q] + scale * s_tot[q]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int row = row0 + r * THREADS;
+                    if (row < p.m && row > c) {
+                        const double v = a[r][0] * scale;            // DSCAL by 1/(alpha-beta), dlarfg.f:178
+                        a[r][0] = v;
+#pragma unroll
+                        for (int q = 1; q < W; ++q)
+                            if (q < live) a[r][q] = fma(tw[q], v, a[r][q]);
+                    } else if (row == c) {
+                        a[r][0] = beta;
+#pragma unroll
+                        for (int q = 1; q < W; ++q)
+                            if (q < live) a[r][q] = a[r][q] + tw[q];
+                    }
+                }
+            }
+            // rotate the window: column c goes to the back
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const double t0 = a[r][0];
+#pragma unroll
+                for (int q = 0; q + 1 < W; ++q) a[r][q] = a[r][q + 1];
+                a[r][W - 1] = t0;
+            }
+        }
+    }
+    __syncthreads();
+
+    // T for the leaf (dlarft_lvl2.f:199-258): T(0:c,c) = T(0:c,0:c) * (-tau_c * G(0:c,c)), T(c,c) = tau_c
+    if (g == 0 && warp == 0) {
+        for (int c = 0; c < kmax; ++c) {
+            const double tc = s_tau[c];
+            double tmp = (lane < c) ? -tc * s_G[lane][c] : 0.0;
+            double out = 0.0;
+            for (int j = 0; j < c; ++j) {
+                double tj = __shfl_sync(0xffffffffu, tmp, j);
+                if (lane <= j && lane < c) out += s_T[lane][j] * tj;
+            }
+            if (lane < c) s_T[lane][c] = (tc == 0.0) ? 0.0 : out;
+            if (lane == c) s_T[c][c] = tc;
+            __syncwarp();
+        }
+        for (int idx = lane; idx < kmax * kmax; idx += 32) {
+            int i = idx % kmax, j = idx / kmax;
+            if (i <= j) p.T[i + (i64)j * p.ldt] = s_T[i][j];
+        }
+    }
+    // window position q now holds column (q + kmax) mod W
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * THREADS;
+        if (row < p.m) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int col = (q + kmax) % W;
+                if (col < p.n) {
+                    p.A[row + (i64)col * p.lda] = a[r][q];
+                    if (p.Vc) {
+                        double v = a[r][q];
+                        if (col >= kmax || row < col) v = 0.0;
+                        else if (row == col) v = 1.0;
+                        p.Vc[row + (i64)col * p.ldvc] = v;
+                    }
+                }
+            }
+        }
+    }
+    qcl_arrive();
+    qcl_wait();
+}
+
 struct QrWs {
     unsigned* bar = nullptr;
     unsigned base = 0;
@@ -245,6 +468,30 @@ static QrWs& qr_ws() {
     return w;
 }
 
+constexpr int QCL_THREADS = 256, QCL_R = 4;       // cluster leaf: 256 threads x 4 rows = 1024 rows per CTA
+static_assert(QCL_THREADS * QCL_R == QTHREADS, "both leaf kernels cover 1024 rows per CTA");
+static int g_qr_cluster_max = 16;
+void geqrf_set_cluster_max(int c) { g_qr_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
+static int qr_cluster_hw_max() {
+    static int hw_max = 0;
+    if (!hw_max) {
+        auto kern = geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R>;
+        hw_max = 8;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(16); q.blockDim = dim3(QCL_THREADS);
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int nact = 0;
+            if (cudaOccupancyMaxActiveClusters(&nact, kern, &q) == cudaSuccess && nact > 0) hw_max = 16;
+        }
+        (void)cudaGetLastError();
+    }
+    return hw_max;
+}
+
 // leaf: m x n (n <= QW); writes A (R and v), tau, Vc (clean, may be null) and the n x n T block
 static void geqr2_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, double* Vc, i64 ldvc, double* T,
                        i64 ldt) {
@@ -258,6 +505,19 @@ static void geqr2_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, double*
         return;
     }
     p.bar = w.bar; p.bar_base = w.base; p.part = w.part; p.toprow = w.toprow;
+    if (p.G <= g_qr_cluster_max && p.G <= qr_cluster_hw_max()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p.G);
+        cfg.blockDim = dim3(QCL_THREADS);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)p.G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R>, p));
+        count_launch();
+        return;
+    }
     geqr2_leaf_kernel<QW, QTHREADS><<<p.G, QTHREADS, 0, s>>>(p);
     count_launch();
     if (p.G > 1) w.base += (unsigned)(min(m, n) + 1) * (unsigned)p.G;

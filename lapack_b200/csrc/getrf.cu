@@ -30,6 +30,8 @@ void laswp_apply_plan(cudaStream_t s, int n, double* A, i64 lda, const void* pla
 void laswp_plan_free(cudaStream_t s, void* plan);
 
 static int g_nb = 512, g_lookahead = 1;
+static int g_cluster_max = 16;      // panels of up to this many 1024-row CTAs use the cluster leaf (0 = never)
+void getrf_set_cluster_max(int c) { g_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
 void getrf_set_params(int nb, int leaf, int lookahead) {
     (void)leaf;
     if (nb > 0) g_nb = nb;
@@ -55,6 +57,7 @@ struct LeafParams {
     int* ipiv;        // panel-relative, 1-based on output
     int* info;        // device word: first zero pivot (absolute, 1-based) -- written only if still 0
     int info_off;     // absolute column offset of this leaf
+    int piv_base;     // added to every pivot index written (row offset of the leaf inside the caller's matrix)
     double sfmin;
     unsigned epoch_base;
     LeafPacket* cand;       // [2][G]
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
         }
         // (6) pivot index / singularity flag (dgetrf2.f:191-192,212-214)
         if (g == 0 && tid == 0) {
-            p.ipiv[c] = prow + 1;
+            p.ipiv[c] = prow + 1 + p.piv_base;
             if (pivot == 0.0 && *p.info == 0) *p.info = p.info_off + c + 1;
         }
         // (7) scale (reciprocal unless |pivot| < SFMIN, dgetrf2.f:204-210) and rank-1 update
@@ -251,8 +254,280 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_kernel(LeafParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Cluster leaf (panels of at most CL_MAX_CTAS*1024 rows): the work CTAs form ONE thread-block cluster, so the
+// per-column exchange goes through distributed shared memory and the hardware cluster barrier instead of L2
+// round trips.  Per column: CTA-local arg-max, the best row and (in CTA 0) the current top row are written
+// to the CTA's own shared memory, barrier.cluster, warp 0 of every CTA reads the C candidate heads remotely,
+// picks the winner and pulls the two rows; one __syncthreads later every thread swaps/scales/updates.
+// All W columns stay in registers until the end (the window rotates cyclically), so an interchange moves whole
+// leaf rows and only the panel columns OUTSIDE the leaf are left to the interchange CTAs (second cluster).
+struct ClusterCand {
+    double key;
+    int row;
+    int pad;
+    double rowdata[16];
+};
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ double ld_dsmem_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_dsmem_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Warp arg-max of (key, row) with IDAMAX tie-breaking.  key >= 0 for candidates (its high word then orders like
+// an unsigned integer), key < 0 = no candidate.  Fast path: one redux.sync on the high words and a ballot; only
+// when several lanes agree in the high word does the full butterfly run.
+__device__ __forceinline__ void warp_argmax(double& key, int& krow) {
+    const unsigned full = 0xffffffffu;
+    const bool cand = key >= 0.0;
+    const unsigned hi = cand ? (unsigned)__double2hiint(key) + 1u : 0u;      // +1: a candidate 0.0 still beats "none"
+    const unsigned mh = __reduce_max_sync(full, hi);
+    const unsigned tie = __ballot_sync(full, hi == mh);
+    if (__popc(tie) == 1) {
+        const int src = __ffs(tie) - 1;
+        key = __shfl_sync(full, key, src);
+        krow = __shfl_sync(full, krow, src);
+        return;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ok = __shfl_xor_sync(full, key, off);
+        int orow = __shfl_xor_sync(full, krow, off);
+        if (cand_better(ok, orow, key, krow)) { key = ok; krow = orow; }
+    }
+}
+
+// R rows per thread (row = g*R*THREADS + r*THREADS + tid): the per-step bookkeeping (reductions, barriers, the
+// pull of the pivot row) is paid once per thread, so few fat threads beat many thin ones -- the kernel is bound
+// by instruction issue, not by latency.
+template <int W, int THREADS, int R>
+__global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafParams p) {
+    constexpr int NWARP = THREADS / 32;
+    constexpr int ROWS = THREADS * R;
+    __shared__ double s_key[NWARP];
+    __shared__ int s_row[NWARP];
+    __shared__ __align__(16) ClusterCand s_cand[2];
+    __shared__ __align__(16) double s_top[2][W];
+    __shared__ __align__(16) double s_prow[W];
+    __shared__ __align__(16) double s_trow[W];
+    __shared__ int s_win_row;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x;
+    const int C = p.G;                                        // cluster size == number of work CTAs
+    const int kmax = min(p.m, p.n);
+
+    if (g >= C) {
+        // ===== interchange CTAs (second cluster): the panel columns outside the leaf (dgetrf2.f:236,263)
+        const int width = p.sw_left + p.n + p.sw_right;
+        if ((g - C) * THREADS >= width) return;
+        const int t = (g - C) * THREADS + tid;
+        const int own = t - p.sw_left;
+        const bool mine = t < width && (own < 0 || own >= p.n);
+        double* colp = p.SW + (i64)t * p.lda;
+#pragma unroll 1
+        for (int c = 0; c < kmax; ++c) {
+            unsigned long long v = 0;
+            if (lane == 0) {
+                const unsigned epoch = p.epoch_base + c + 1;
+                do { v = ld_relaxed_u64(p.hist + c); } while ((unsigned)(v >> 32) != epoch);
+            }
+            v = __shfl_sync(0xffffffffu, v, 0);
+            const int prow = (int)(unsigned)(v & 0xffffffffu);
+            if (mine && prow != c) {
+                double x = colp[c], y = colp[prow];
+                colp[c] = y;
+                colp[prow] = x;
+            }
+        }
+        return;
+    }
+
+    const int row0 = g * ROWS + tid;             // rows row0 + r*THREADS
+    double a[R][W];                              // a[r][q] = A(row_r, (c + q) mod W) at step c
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * THREADS;
+#pragma unroll
+        for (int q = 0; q < W; ++q) a[r][q] = (row < p.m && q < p.n) ? p.A[row + (i64)q * p.lda] : 0.0;
+    }
+    const unsigned cand_base = smem_u32(&s_cand[0]);
+    const unsigned top_base = smem_u32(&s_top[0][0]);
+
+#pragma unroll 1
+    for (int c = 0; c < kmax; ++c) {
+        const int slot = c & 1;
+        // (1) CTA-local arg-max over the active rows, IDAMAX semantics (idamax.f:95-106)
+        double key = -1.0;
+        int krow = 0x7fffffff;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int row = row0 + r * THREADS;
+            if (row < p.m && row >= c) {
+                double v = fabs(a[r][0]);
+                if (v != v) v = (row == c) ? CUDART_INF : -1.0;
+                if (v > key) { key = v; krow = row; }          // rows ascend with r: strict '>' keeps the first
+            }
+        }
+        if (key < 0.0) krow = 0x7fffffff;
+        warp_argmax(key, krow);
+        if (lane == 0) { s_key[warp] = key; s_row[warp] = krow; }
+        __syncthreads();
+        {   // every warp reduces the NWARP partial results itself (no second CTA barrier)
+            double k2 = (lane < NWARP) ? s_key[lane] : -1.0;
+            int r2 = (lane < NWARP) ? s_row[lane] : 0x7fffffff;
+#pragma unroll
+            for (int off = NWARP / 2; off > 0; off >>= 1) {
+                double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; }
+            }
+            key = __shfl_sync(0xffffffffu, k2, 0);
+            krow = __shfl_sync(0xffffffffu, r2, 0);
+        }
+        // (2) publish the CTA's best row (and the top row) in this CTA's shared memory
+        if (krow == 0x7fffffff) {
+            if (tid == 0) { s_cand[slot].key = -2.0; s_cand[slot].row = 0x7fffffff; }     // no active row here
+        } else if (((krow - row0) % THREADS) == 0 && krow >= row0 && krow < row0 + R * THREADS) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (krow == row0 + r * THREADS) {
+                    s_cand[slot].key = key;
+                    s_cand[slot].row = krow;
+#pragma unroll
+                    for (int q = 0; q < W; ++q) s_cand[slot].rowdata[q] = a[r][q];
+                }
+        }
+        if (row0 == c) {                                       // row c always lives in CTA 0, r = 0
+#pragma unroll
+            for (int q = 0; q < W; ++q) s_top[slot][q] = a[0][q];
+        }
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        // (3) warp 0: winner over the C candidates, then pull the winner's row and the top row
+        if (warp == 0) {
+            double k2 = -3.0;
+            int r2 = 0x7fffffff, g2 = 0;
+            if (lane < C) {
+                const unsigned ra = mapa_u32(cand_base + slot * (unsigned)sizeof(ClusterCand), (unsigned)lane);
+                k2 = ld_dsmem_f64(ra);
+                r2 = ld_dsmem_s32(ra + 8);
+                g2 = lane;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                int og = __shfl_xor_sync(0xffffffffu, g2, off);
+                if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
+            }
+            if (lane < W) {
+                const unsigned ra = mapa_u32(cand_base + slot * (unsigned)sizeof(ClusterCand) + 16 + lane * 8, (unsigned)g2);
+                s_prow[lane] = ld_dsmem_f64(ra);
+            } else if (lane < 2 * W) {
+                const unsigned ta = mapa_u32(top_base + (slot * W + (lane - W)) * 8, 0u);
+                s_trow[lane - W] = ld_dsmem_f64(ta);
+            }
+            if (lane == 0) s_win_row = r2;
+        }
+        __syncthreads();
+        const int prow = s_win_row;
+        double pr[W];
+#pragma unroll
+        for (int q = 0; q < W; q += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(&s_prow[q]);
+            pr[q] = v.x; pr[q + 1] = v.y;
+        }
+        const double pivot = pr[0];
+        // (4) interchange whole leaf rows through the published copies (dgetrf2.f:196-200)
+        if (prow != c) {
+            if (((prow - row0) % THREADS) == 0 && prow >= row0 && prow < row0 + R * THREADS) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (prow == row0 + r * THREADS) {
+#pragma unroll
+                        for (int q = 0; q < W; ++q) a[r][q] = s_trow[q];
+                    }
+            }
+            if (row0 == c) {
+#pragma unroll
+                for (int q = 0; q < W; ++q) a[0][q] = pr[q];
+            }
+        }
+        // (5) pivot index / singularity flag (dgetrf2.f:191-192,212-214); winner history for the interchange CTAs
+        if (g == 0 && tid == 32) {
+            p.ipiv[c] = prow + 1 + p.piv_base;
+            if (pivot == 0.0 && *p.info == 0) *p.info = p.info_off + c + 1;
+            st_relaxed_u64(p.hist + c, ((unsigned long long)(p.epoch_base + c + 1) << 32) | (unsigned)prow);
+        }
+        // (6) scale (reciprocal unless |pivot| < SFMIN, dgetrf2.f:204-210) and rank-1 update of the live columns
+        if (pivot != 0.0) {
+            const bool use_rcp = fabs(pivot) >= p.sfmin;
+            const double rcp = 1.0 / pivot;
+            const int live = W - c;                           // window positions 1..live-1 hold columns > c
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int row = row0 + r * THREADS;
+                if (row < p.m && row > c) {
+                    const double l = use_rcp ? a[r][0] * rcp : a[r][0] / pivot;
+                    a[r][0] = l;
+#pragma unroll
+                    for (int q = 1; q < W; ++q)
+                        if (q < live) a[r][q] = fma(-l, pr[q], a[r][q]);
+                }
+            }
+        }
+        // (7) rotate the window: column c goes to the back
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double t0 = a[r][0];
+#pragma unroll
+            for (int q = 0; q + 1 < W; ++q) a[r][q] = a[r][q + 1];
+            a[r][W - 1] = t0;
+        }
+    }
+    // window position q now holds column (q + kmax) mod W
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * THREADS;
+        if (row < p.m) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int col = (q + kmax) % W;
+                if (col < p.n) p.A[row + (i64)col * p.lda] = a[r][q];
+            }
+        }
+    }
+    // nobody may exit while its shared memory can still be read by a peer
+    cluster_arrive_release();
+    cluster_wait_acquire();
+}
+
+// ------------------------------------------------------------------------------------------------
 constexpr int LEAF_W = 16;
 constexpr int LEAF_THREADS = 1024;
+constexpr int CL_THREADS = 256, CL_R = 4;     // cluster leaf: 256 threads x 4 rows = 1024 rows per CTA
+static_assert(CL_THREADS * CL_R == LEAF_THREADS, "both leaf kernels cover 1024 rows per CTA");
 
 struct LeafWs {
     unsigned epoch = 0;
@@ -281,15 +556,39 @@ static LeafWs& leaf_ws() {
 struct PanelCtx {
     double* P;
     int width;
+    int piv_base;     // row offset of the panel inside the caller's matrix (dgetrf.f:183-186 shift, done at the source)
 };
 
 // factor an m x n (n <= LEAF_W) leaf at panel offset `off`; ipiv relative (1-based); *info set to
 // info_off + col + 1 on the first exact zero pivot (only if still zero)
+// largest cluster this device/driver schedules for the cluster leaf (16 is a non-portable size)
+static int cluster_hw_max() {
+    static int hw_max = 0;
+    if (!hw_max) {
+        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R>;
+        hw_max = 8;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(16); q.blockDim = dim3(CL_THREADS);
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            int nact = 0;
+            if (cudaOccupancyMaxActiveClusters(&nact, kern, &q) == cudaSuccess && nact > 0) hw_max = 16;
+        }
+        (void)cudaGetLastError();
+    }
+    return hw_max;
+}
+
 static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n, double* A, i64 lda, int* ipiv, int* info,
                        int info_off) {
+    // pivots are written relative to the top of the matrix the panel belongs to: pc.piv_base + row offset of the leaf
     LeafWs& w = leaf_ws();
     LeafParams p;
     p.m = m; p.n = n; p.A = A; p.lda = lda; p.ipiv = ipiv; p.info = info; p.info_off = info_off;
+    p.piv_base = pc.piv_base + off;
     p.sfmin = DBL_MIN;   // DLAMCH('S') (INSTALL/dlamch.f:111-122)
     p.G = ceil_div(m, LEAF_THREADS);
     if (p.G > w.maxG || p.G > num_sms()) {
@@ -302,6 +601,26 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     p.sw_left = off;
     p.sw_right = pc.width - off - n;
     const int S = ceil_div(pc.width, LEAF_THREADS);
+    if (p.G <= g_cluster_max && p.G <= cluster_hw_max()) {
+        // one cluster of G work CTAs (+ clusters of interchange CTAs when the panel is wider than the leaf)
+        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R>;
+        const bool outside = pc.width > n;
+        int nclusters = 1;
+        if (outside) nclusters += ceil_div(ceil_div(pc.width, CL_THREADS), p.G);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.G * nclusters));
+        cfg.blockDim = dim3(CL_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)p.G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+        count_launch();
+        w.epoch += (unsigned)min(m, n);
+        return;
+    }
     getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G + S, LEAF_THREADS, 0, s>>>(p);
     count_launch();
     w.epoch += (unsigned)min(m, n);
@@ -327,12 +646,13 @@ static void getrf_panel_rec(cudaStream_t s, const PanelCtx& pc, int off, int m, 
     trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, A, lda, A12, lda);               // dgetrf2.f:240
     if (m > n1) {
         gemm(s, 'N', 'N', m - n1, n2, n1, -1.0, A21, lda, A12, lda, 1.0, A22, lda);   // dgetrf2.f:245
-        getrf_panel_rec(s, pc, off + n1, m - n1, n2, A22, lda, ipiv + n1, info, info_off + n1);   // dgetrf2.f:250
-        iadd(s, min(m, n) - n1, ipiv + n1, n1);                                          // dgetrf2.f:257-259
+        // dgetrf2.f:250; the index shift of dgetrf2.f:257-259 is applied by the leaves themselves (piv_base)
+        getrf_panel_rec(s, pc, off + n1, m - n1, n2, A22, lda, ipiv + n1, info, info_off + n1);
     }
 }
+// piv_base = info_off = row/column offset of the panel inside the caller's matrix
 static void getrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info, int info_off) {
-    PanelCtx pc{A, n};
+    PanelCtx pc{A, n, info_off};
     getrf_panel_rec(s, pc, 0, m, n, A, lda, ipiv, info, info_off);
 }
 
@@ -425,8 +745,8 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                     LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_next, 0));
                 }
                 // factor the next panel (overlaps with the rest of this update when look-ahead is on)
+                // the leaves write absolute pivot rows (dgetrf.f:187-189 shift applied at the source)
                 getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
-                iadd(sp, min(m - jn, jb2), ipiv + jn, jn);                                   // dgetrf.f:187-189
                 if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
             }
         }

@@ -177,6 +177,40 @@ def test_dgetrf_blocked_lookahead(lb, nb, la):
         L.lb200_set_getrf_params(512, 0, 1)
 
 
+@pytest.mark.parametrize("cluster_max", [0, 2, 8, 16])
+def test_dgetrf_leaf_kernels_agree(lb, cluster_max):
+    """The global-exchange leaf (cluster_max=0) and the thread-block-cluster leaf give the same pivots and factors
+    as the reference, including panels that span several CTAs, ties, zero columns and NaN entries."""
+    L = lb.lib()
+    L.lb200_set_getrf_cluster_max(cluster_max)
+    try:
+        for (m, n) in ((3000, 40), (2500, 300), (1025, 1025), (5000, 17)):
+            a, _ = O.random_matrix(m, n, SEED)
+            a[:, 3] = np.round(a[:, 3] * 4.0) / 4.0                # many exact ties in one column
+            a[m // 2:, 5] = a[m // 2, 5]                           # a long run of equal entries
+            a[:, 7] = 0.0                                          # exactly singular column -> INFO = 8 (if reached)
+            ref = a.copy(order="F")
+            ipiv_ref, info_ref = O.dgetrf2(ref)
+            got = a.copy(order="F")
+            ipiv, info = lb.f77.getrf(got, True)
+            assert info == info_ref, (m, n)
+            assert np.array_equal(ipiv, ipiv_ref), (m, n)
+            assert rel(got, ref) < 1e-10
+        # NaN handling of IDAMAX (idamax.f:103): a NaN is never selected unless it sits in the first place
+        a, _ = O.random_matrix(2100, 20, SEED)
+        a[1500, 2] = np.nan
+        a[4, 4] = np.nan
+        ref = a.copy(order="F")
+        ipiv_ref, info_ref = O.dgetrf2(ref)
+        got = a.copy(order="F")
+        ipiv, info = lb.f77.getrf(got, True)
+        assert info == info_ref
+        assert np.array_equal(ipiv, ipiv_ref)
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+    finally:
+        L.lb200_set_getrf_cluster_max(16)
+
+
 def test_dgetrf_singular_info(lb):
     """TESTING/LIN/dchkge.f:328-347: zero a column -> INFO = that column, factorization completes."""
     n = 120
