@@ -257,6 +257,65 @@ void dtrmm_(const char* side, const char* uplo, const char* transa, const char* 
 }
 
 // ================================================================================================ LU
+// Host-resident square DGETRF with transfer/compute overlap: one level of the DGETRF2 recursion (dgetrf2.f:216-263)
+// at the top.  The left n1 columns are uploaded first and factored (blocked DGETRF) while the right n - n1 columns
+// are still crossing PCIe; then A12/A22 get the accumulated interchanges, the triangular solve and ONE large-K GEMM,
+// A22 is factored, and its interchanges go back to the left columns.  U12 is downloaded while A22 is factored.
+static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
+    static cudaStream_t copy_stream = nullptr;
+    static cudaEvent_t ev_up = nullptr, ev_u12 = nullptr;
+    if (!copy_stream) {
+        LB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+        LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_u12, cudaEventDisableTiming));
+    }
+    cudaStream_t s = host_stream();
+    const lb::i64 ldd = ((lb::i64)n + 1) & ~1LL;
+    double* dA = (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * n);
+    int* dp = (int*)lb::ws_alloc(s, sizeof(int) * (size_t)n);
+    int* dinfo = (int*)lb::ws_alloc(s, 64);          // dinfo[0] = left part / result, dinfo[8] = A22
+    const int n1 = imin(n - 512, ((n / 4 + 511) / 512) * 512), n2 = n - n1;
+    double* dA12 = dA + (lb::i64)n1 * ldd;
+    double* dA22 = dA12 + n1;
+    // make sure the scratch exists before the copy stream touches it
+    LB_CUDA_CHECK(cudaEventRecord(ev_up, s));
+    LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_up, 0));
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(dA, ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, n1, cudaMemcpyHostToDevice, s));
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(dA12, ldd * 8, A + (lb::i64)n1 * lda, (size_t)lda * 8, (size_t)n * 8, n2,
+                                    cudaMemcpyHostToDevice, copy_stream));
+    LB_CUDA_CHECK(cudaEventRecord(ev_up, copy_stream));
+    lb::getrf(s, n, n1, dA, ldd, dp, dinfo);                                            // dgetrf2.f:231
+    LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
+    lb::laswp(s, n2, dA12, ldd, 1, n1, dp, 1);                                          // dgetrf2.f:236
+    lb::trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, dA, ldd, dA12, ldd);                   // dgetrf2.f:240
+    LB_CUDA_CHECK(cudaEventRecord(ev_u12, s));
+    LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(A + (lb::i64)n1 * lda, (size_t)lda * 8, dA12, ldd * 8, (size_t)n1 * 8, n2,
+                                    cudaMemcpyDeviceToHost, copy_stream));              // U12 is final
+    lb::gemm(s, 'N', 'N', n2, n2, n1, -1.0, dA + n1, ldd, dA12, ldd, 1.0, dA22, ldd);   // dgetrf2.f:245
+    lb::getrf(s, n2, n2, dA22, ldd, dp + n1, dinfo + 8);                                // dgetrf2.f:250
+    LB_CUDA_CHECK(cudaEventRecord(ev_u12, s));                                          // A22 is final
+    LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
+    lb::info_max_offset(s, dinfo, dinfo + 8, n1);                                       // dgetrf2.f:251-252
+    lb::iadd(s, n2, dp + n1, n1);                                                       // dgetrf2.f:257-259
+    lb::laswp(s, n1, dA, ldd, n1 + 1, n, dp, 1);                                        // dgetrf2.f:263
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(A + n1 + (lb::i64)n1 * lda, (size_t)lda * 8, dA22, ldd * 8, (size_t)n2 * 8, n2,
+                                    cudaMemcpyDeviceToHost, copy_stream));
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, ldd * 8, (size_t)n * 8, n1, cudaMemcpyDeviceToHost, s));
+    LB_CUDA_CHECK(cudaMemcpyAsync(ipiv, dp, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    int hinfo = 0;
+    LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    lb::ws_free(s, dA);
+    lb::ws_free(s, dp);
+    lb::ws_free(s, dinfo);
+    LB_CUDA_CHECK(cudaStreamSynchronize(s));
+    int e = lb::last_cuda_error();
+    if (e) { lb::clear_cuda_error(); return -1001 - e; }
+    return hinfo;
+}
+
 static void getrf_common(bool recursive, const int* m, const int* n, double* A, const int* lda, int* ipiv, int* info) {
     *info = 0;
     if (*m < 0) *info = -1;
@@ -266,6 +325,10 @@ static void getrf_common(bool recursive, const int* m, const int* n, double* A, 
     if (*m == 0 || *n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    if (!recursive && *m == *n && *n >= 8192 && ptr_kind(A) == PK_PINNED && ptr_kind(ipiv) != PK_DEVICE) {
+        *info = getrf_host_streamed(*n, A, *lda, ipiv);
+        return;
+    }
     Ctx c; c.scan({A, ipiv});
     lb::i64 la;
     double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
@@ -362,7 +425,18 @@ void dgesv_(const int* n, const int* nrhs, double* A, const int* lda, int* ipiv,
 // Host-resident Cholesky with transfer/compute overlap: only the UPLO triangle crosses PCIe (block-column
 // trapezoids), and every finished block column of the factor is downloaded on a copy stream while the rest of
 // the factorization is still running (lb::StreamOut).  Needs pinned host memory for truly asynchronous copies.
-static int potrf_host_streamed(bool upper, int n, double* A, int lda) {
+// upload only the UPLO triangle of a host matrix, as block-column trapezoids
+static void upload_triangle(cudaStream_t s, bool upper, int n, const double* A, int lda, double* dA, lb::i64 ldd, int cb) {
+    for (int j0 = 0; j0 < n; j0 += cb) {
+        const int w = imin(cb, n - j0);
+        const int r0 = upper ? 0 : j0, r1 = upper ? j0 + w : n;
+        LB_CUDA_CHECK(cudaMemcpy2DAsync(dA + r0 + (lb::i64)j0 * ldd, ldd * 8, A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8,
+                                        (size_t)(r1 - r0) * 8, w, cudaMemcpyHostToDevice, s));
+    }
+}
+
+// DPOTRF, or DPOSV when nrhs > 0 (factor, then solve only if INFO = 0, dposv.f:176-183)
+static int potrf_host_streamed(bool upper, int n, double* A, int lda, int nrhs = 0, double* B = nullptr, int ldb = 0) {
     static cudaStream_t copy_stream = nullptr;
     static cudaEvent_t ev = nullptr, ev_up = nullptr;
     if (!copy_stream) {
@@ -373,14 +447,12 @@ static int potrf_host_streamed(bool upper, int n, double* A, int lda) {
     cudaStream_t s = host_stream();
     const lb::i64 ldd = ((lb::i64)n + 1) & ~1LL;
     double* dA = (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * n);
+    double* dB = nrhs > 0 ? (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * nrhs) : nullptr;
     int* dinfo = (int*)lb::ws_alloc(s, 64);
     const int cb = 2048;
-    for (int j0 = 0; j0 < n; j0 += cb) {
-        const int w = imin(cb, n - j0);
-        const int r0 = upper ? 0 : j0, r1 = upper ? j0 + w : n;
-        LB_CUDA_CHECK(cudaMemcpy2DAsync(dA + r0 + (lb::i64)j0 * ldd, ldd * 8, A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8,
-                                        (size_t)(r1 - r0) * 8, w, cudaMemcpyHostToDevice, s));
-    }
+    upload_triangle(s, upper, n, A, lda, dA, ldd, cb);
+    if (nrhs > 0)
+        LB_CUDA_CHECK(cudaMemcpy2DAsync(dB, ldd * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, s));
     lb::StreamOut so;
     so.host = A; so.ldh = lda; so.copy_stream = copy_stream; so.ev = ev; so.done_cols = 0;
     lb::stream_out() = &so;
@@ -396,8 +468,16 @@ static int potrf_host_streamed(bool upper, int n, double* A, int lda) {
     }
     int hinfo = 0;
     LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (nrhs > 0) {
+        LB_CUDA_CHECK(cudaStreamSynchronize(s));               // INFO decides whether the solve happens
+        if (hinfo == 0 && lb::last_cuda_error() == 0) {
+            lb::potrs(s, upper ? 'U' : 'L', n, nrhs, dA, ldd, dB, ldd);
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(B, (size_t)ldb * 8, dB, ldd * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, s));
+        }
+    }
     LB_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
     lb::ws_free(s, dA);
+    if (dB) lb::ws_free(s, dB);
     lb::ws_free(s, dinfo);
     LB_CUDA_CHECK(cudaStreamSynchronize(s));
     int e = lb::last_cuda_error();
@@ -465,6 +545,11 @@ void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const in
     if (*n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    if (*n >= 2048 && ptr_kind(A) == PK_PINNED && (*nrhs == 0 || ptr_kind(B) == PK_PINNED || ptr_kind(B) == PK_HOST) &&
+        2048 % lb::potrf_block() == 0) {
+        *info = potrf_host_streamed(upper, *n, A, *lda, *nrhs, B, *ldb);
+        return;
+    }
     Ctx c; c.scan({A, B});
     lb::i64 la, lbb;
     double* dA = c.mat(A, *n, *n, *lda, true, true, &la);

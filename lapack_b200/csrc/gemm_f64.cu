@@ -296,7 +296,16 @@ __global__ void splitk_reduce_kernel(int m, int n, int nz, double alpha, double 
         if (tri == 2 && i > j) continue;
         double acc = 0.0;
         const double* q = P + i + (i64)j * m;
-        for (int z = 0; z < nz; ++z) acc += q[(i64)z * m * n];
+        const i64 zs = (i64)m * n;
+        int z = 0;
+        for (; z + 8 <= nz; z += 8) {          // eight loads in flight, added in slice order
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(q + (i64)(z + u) * zs);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += v[u];
+        }
+        for (; z < nz; ++z) acc += __ldcs(q + (i64)z * zs);
         double* c = C + i + (i64)j * ldc;
         *c = (beta == 0.0) ? alpha * acc : alpha * acc + beta * (*c);
     }

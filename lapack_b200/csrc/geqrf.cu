@@ -346,8 +346,13 @@ __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafPa
         qcl_wait();
         if (warp == 0) {
             if (lane < W) {
+                // all C remote loads are issued before the first add (fixed summation order, same in every CTA)
+                double pv[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pv[q] = (q < C) ? qcl_ld(part_base + (slot * W + lane) * 8, (unsigned)q) : 0.0;
                 double v = 0.0;
-                for (int q = 0; q < C; ++q) v += qcl_ld(part_base + (slot * W + lane) * 8, (unsigned)q);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) v += pv[q];
                 s_tot[lane] = v;
                 // DLARFG (dlarfg.f:140-186) with xnorm^2 = total[0]; every lane of the half-warp gets total[0]
                 const double t0 = __shfl_sync(0x0000ffffu, v, 0);

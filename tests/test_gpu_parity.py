@@ -211,6 +211,39 @@ def test_dgetrf_leaf_kernels_agree(lb, cluster_max):
         L.lb200_set_getrf_cluster_max(16)
 
 
+def test_dgetrf_pinned_host_streamed(lb):
+    """Pinned host caller, square n >= 8192: split upload / top-level recursion (fortran_abi.cu getrf_host_streamed)."""
+    n, lda = 8200, 8208
+    a, _ = O.random_matrix(n, n, SEED)
+    buf = torch.empty((n, lda), dtype=torch.float64).pin_memory()
+    h = buf.numpy().T                                               # (lda, n) column-major view
+    h[:] = 7.0
+    h[:n, :] = a
+    ipiv = np.zeros(n, dtype=np.int32)
+    assert lb.f77.dgetrf(n, n, h, lda, ipiv) == 0
+    got = np.asfortranarray(h[:n, :])
+    assert np.all(h[n:, :] == 7.0)
+    # same pivots and factors as the device-resident blocked driver
+    ad = np_to_dev(lb, a)
+    piv_d, info_d = lb.dev.getrf(ad)
+    assert np.array_equal(ipiv, piv_d.cpu().numpy())
+    assert rel(got, dev_to_np(ad)) < 1e-10
+    # residual by a GPU product (the oracle's O(n^3) checker is too slow at this size)
+    L = torch.tril(ad, -1) + torch.eye(n, dtype=torch.float64, device=ad.device)
+    U = torch.triu(ad)
+    pa = torch.from_numpy(a).to(ad.device)
+    for i in range(n):                                              # apply the interchanges to A
+        p = int(ipiv[i]) - 1
+        if p != i:
+            tmp = pa[i].clone(); pa[i] = pa[p]; pa[p] = tmp
+    resid = float((L @ U - pa).abs().sum(dim=0).max()) / (n * float(pa.abs().sum(dim=0).max()) * EPS)
+    assert resid < O.THRESH
+    # exactly singular column in the right part -> INFO from the second half, shifted (dgetrf2.f:251-252)
+    h[:n, :] = a
+    h[:n, 5000] = 0.0
+    assert lb.f77.dgetrf(n, n, h, lda, ipiv) == 5001
+
+
 def test_dgetrf_singular_info(lb):
     """TESTING/LIN/dchkge.f:328-347: zero a column -> INFO = that column, factorization completes."""
     n = 120
@@ -334,6 +367,22 @@ def test_dpotrf_pinned_host_streamed(lb, uplo):
     h[:n, :] = s
     h[2100, 2100] = -5.0
     assert lb.f77.dpotrf(uplo, n, h, lda) == 2101
+    # DPOSV through the same streamed path (pinned A, pageable B): solution vs the reference, B untouched on failure
+    h[:n, :] = s
+    h[:n, :][mask] = -1.0e10
+    x_true, _ = O.random_matrix(n, 2, (7, 8, 9, 11))
+    b = np.asfortranarray(s @ x_true)
+    b_ref = b.copy(order="F")
+    a_ref = s.copy(order="F")
+    assert O.dposv(uplo, a_ref, b_ref) == 0
+    assert lb.f77.dposv(uplo, n, 2, h, lda, b, n) == 0
+    assert rel(b, b_ref) < 1e-10
+    assert np.all(h[:n, :][mask] == -1.0e10)
+    h[:n, :] = s
+    h[5, 5] = 0.0
+    b2 = b_ref.copy(order="F")
+    assert lb.f77.dposv(uplo, n, 2, h, lda, b2, n) == 6
+    assert np.array_equal(b2, b_ref)
 
 
 def test_dpotrf_not_positive_definite(lb):
