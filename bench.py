@@ -186,6 +186,8 @@ def run_dist(args, rank, world, local_rank):
     from lapack_b200.dist_check import randomized_residual
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: ONE JSON line only
     dist.init_process_group("nccl", device_id=dev)
     L = lb.lib()
     n, nb = args.n_dist, args.nb_dist
@@ -268,6 +270,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
