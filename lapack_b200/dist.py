@@ -112,6 +112,37 @@ class GpuOps:
     def to_float64(self, x):
         return x.to(self.torch.float64)
 
+    # ---- Cholesky (lower)
+    def potrf_panel(self, panel):
+        """panel = A(j:n, j:j+jb): Cholesky of the jb x jb diagonal block, then L21 = A21 L11^-T; returns device INFO"""
+        jb = panel.shape[1]
+        info = self.dev.potrf("L", panel[:jb, :])
+        if panel.shape[0] > jb:
+            self.dev.trsm("R", "L", "T", "N", 1.0, panel[:jb, :], panel[jb:, :])
+        return info
+
+    def syrk_update(self, l, c):
+        """c (w x w, lower triangle) -= l l^T"""
+        self.dev.syrk("L", "N", -1.0, l, 1.0, c)
+
+    def gemm_nt_update(self, a, b, c):
+        """c -= a b^T"""
+        if c.shape[0] > 0 and c.shape[1] > 0:
+            self.dev.gemm("N", "T", -1.0, a, b, 1.0, c)
+
+    # ---- QR
+    def qr_panel(self, panel):
+        """in-place DGEQRF of a tall panel; returns (tau, T) with T the jb x jb triangular factor of the block reflector"""
+        tau = self.dev.geqrf(panel)
+        k = tau.shape[0]
+        t = self.dev.larft(panel[:, :k], tau)
+        return tau, t
+
+    def larfb_lt(self, v, t, c):
+        """c := H^T c with H = I - V T V^T (V unit lower trapezoidal, stored below the diagonal of v)"""
+        if c.shape[1] > 0:
+            self.dev.larfb("L", "T", v, t, c)
+
 
 def pgetrf(ops, dist, desc: BlockCyclic1D, aloc, lookahead: bool = True):
     """Distributed LU with partial pivoting of the block-column-cyclic matrix `aloc` (n x local_cols, in place).
@@ -160,7 +191,7 @@ def pgetrf(ops, dist, desc: BlockCyclic1D, aloc, lookahead: bool = True):
             work.wait()
         tail = cur[n * nb: n * nb + nb + 8]
         piv = ops.to_int32(tail[:jb])                      # relative to row j, 1-based
-        ipiv_all.append((j, piv, tail[nb: nb + 1]))
+        ipiv_all.append((j, piv, tail[nb: nb + 1] * 1.0))       # a copy: the buffer is reused two steps later
         pv = panel_view(cur, n - j, jb)                    # rows j..n-1 of panel k
         l11, l21 = pv[:jb, :], pv[jb:, :]
 
@@ -214,6 +245,169 @@ def pgetrf(ops, dist, desc: BlockCyclic1D, aloc, lookahead: bool = True):
         if info == 0 and v > 0:
             info = v + j
     return ipiv, info
+
+
+def ppotrf(ops, dist, desc: BlockCyclic1D, aloc, lookahead: bool = True):
+    """Distributed Cholesky A = L L^T (UPLO = 'L') of the block-column-cyclic matrix `aloc` (n x local_cols, in place;
+    only the lower triangle is referenced, like SRC/dpotrf.f:65-71).  Right-looking (SRC/VARIANTS/cholesky/RL/dpotrf.f:
+    205-229): per step the owner's factored block column L(j:n, j:j+jb) is broadcast and every rank updates its local
+    trailing block columns c:  A(c:n, c) -= L(c:n, k) L(c:c+w, k)^T  (DSYRK on the diagonal block, DGEMM below).
+    Returns INFO (0, or the order of the first leading minor that is not positive)."""
+    n, nb, me = desc.n, desc.nb, desc.rank
+    nblk = desc.nblocks
+    bufs = [ops.empty_vec(n * nb + 8) for _ in range(2)]
+    infos = []
+
+    def panel_view(buf, rows, jb):
+        return buf[: n * nb].view(nb, n).t()[:rows, :jb]
+
+    def factor_and_pack(k, buf):
+        j, jb = k * nb, desc.width(k)
+        lo = desc.local_offset(k)
+        panel = aloc[j:, lo:lo + jb]
+        inf = ops.potrf_panel(panel)
+        ops.copy(panel_view(buf, n - j, jb), panel)
+        tail = buf[n * nb: n * nb + 8]
+        tail.zero_()
+        ops.copy(tail[:1], ops.to_float64(inf))
+
+    def start_bcast(k, buf):
+        if dist is None or desc.world == 1:
+            return None
+        return dist.broadcast(buf, src=desc.owner(k), async_op=True)
+
+    def update_block(c, pv, j):
+        """apply panel (rows j.., in pv) to local block column c (global index)"""
+        gc, w = c * nb, desc.width(c)
+        lo = desc.local_offset(c)
+        lc = pv[gc - j: gc - j + w, :]                     # L(gc:gc+w, k)
+        ops.syrk_update(lc, aloc[gc:gc + w, lo:lo + w])
+        if gc + w < n:
+            ops.gemm_nt_update(pv[gc - j + w:, :], lc, aloc[gc + w:, lo:lo + w])
+
+    if desc.owner(0) == me:
+        factor_and_pack(0, bufs[0])
+    work = start_bcast(0, bufs[0])
+    for k in range(nblk):
+        cur, nxt = bufs[k % 2], bufs[(k + 1) % 2]
+        j, jb = k * nb, desc.width(k)
+        if work is not None:
+            work.wait()
+        infos.append((j, cur[n * nb: n * nb + 1] * 1.0))        # a copy: the buffer is reused two steps later
+        pv = panel_view(cur, n - j, jb)
+        mine = [c for c in desc.local_blocks() if c > k]
+        work = None
+        nk = k + 1
+        if nk < nblk:
+            if desc.owner(nk) == me:
+                if lookahead:
+                    update_block(nk, pv, j)
+                    factor_and_pack(nk, nxt)
+                    work = start_bcast(nk, nxt)
+                    for c in mine:
+                        if c != nk:
+                            update_block(c, pv, j)
+                else:
+                    for c in mine:
+                        update_block(c, pv, j)
+                    factor_and_pack(nk, nxt)
+                    work = start_bcast(nk, nxt)
+            else:
+                if lookahead:
+                    work = start_bcast(nk, nxt)
+                for c in mine:
+                    update_block(c, pv, j)
+                if not lookahead:
+                    work = start_bcast(nk, nxt)
+    info = 0
+    for (j, inf) in infos:
+        v = int(round(float(inf.cpu().numpy()[0])))
+        if info == 0 and v > 0:
+            info = v + j
+    return info
+
+
+def pgeqrf(ops, dist, desc: BlockCyclic1D, aloc, lookahead: bool = True):
+    """Distributed Householder QR (SRC/dgeqrf.f:244-267) of the block-column-cyclic matrix `aloc` (n x local_cols, in
+    place: R on/above the diagonal, the reflectors V below).  Per step the owner factors its block column (DGEQRF
+    panel + DLARFT), broadcasts V, T and tau in one message, and every rank applies H^T = I - V T^T V^T to its local
+    trailing columns (DLARFB 'L','T','F','C', dgeqrf.f:262).  Returns tau (length n, replicated)."""
+    n, nb, me = desc.n, desc.nb, desc.rank
+    nblk = desc.nblocks
+    bufs = [ops.empty_vec(n * nb + nb * nb + nb) for _ in range(2)]
+    taus = []
+
+    def panel_view(buf, rows, jb):
+        return buf[: n * nb].view(nb, n).t()[:rows, :jb]
+
+    def t_view(buf, jb):
+        return buf[n * nb: n * nb + nb * nb].view(nb, nb).t()[:jb, :jb]
+
+    def factor_and_pack(k, buf):
+        j, jb = k * nb, desc.width(k)
+        lo = desc.local_offset(k)
+        panel = aloc[j:, lo:lo + jb]
+        tau, t = ops.qr_panel(panel)
+        ops.copy(panel_view(buf, n - j, jb), panel)
+        kk = tau.shape[0]
+        tv = t_view(buf, jb)
+        tv.zero_()
+        ops.copy(tv[:kk, :kk], t)
+        tt = buf[n * nb + nb * nb: n * nb + nb * nb + nb]
+        tt.zero_()
+        ops.copy(tt[:kk], tau)
+
+    def start_bcast(k, buf):
+        if dist is None or desc.world == 1:
+            return None
+        return dist.broadcast(buf, src=desc.owner(k), async_op=True)
+
+    if desc.owner(0) == me:
+        factor_and_pack(0, bufs[0])
+    work = start_bcast(0, bufs[0])
+    for k in range(nblk):
+        cur, nxt = bufs[k % 2], bufs[(k + 1) % 2]
+        j, jb = k * nb, desc.width(k)
+        kk = min(jb, n - j)
+        if work is not None:
+            work.wait()
+        taus.append((j, kk, cur[n * nb + nb * nb: n * nb + nb * nb + nb] * 1.0))   # a copy (buffer reuse)
+        v = panel_view(cur, n - j, jb)[:, :kk]
+        t = t_view(cur, jb)[:kk, :kk]
+        c_after = desc.first_local_col_after(k)
+        nloc = aloc.shape[1]
+        work = None
+        nk = k + 1
+
+        def apply(c0, c1):
+            if c1 > c0:
+                ops.larfb_lt(v, t, aloc[j:, c0:c1])
+
+        if nk < nblk:
+            if desc.owner(nk) == me:
+                w = desc.width(nk)
+                if lookahead:
+                    apply(c_after, c_after + w)
+                    factor_and_pack(nk, nxt)
+                    work = start_bcast(nk, nxt)
+                    apply(c_after + w, nloc)
+                else:
+                    apply(c_after, nloc)
+                    factor_and_pack(nk, nxt)
+                    work = start_bcast(nk, nxt)
+            else:
+                if lookahead:
+                    work = start_bcast(nk, nxt)
+                apply(c_after, nloc)
+                if not lookahead:
+                    work = start_bcast(nk, nxt)
+        else:
+            apply(c_after, nloc)
+    import numpy as np
+    tau = np.zeros(n)
+    for (j, kk, tt) in taus:
+        tau[j:j + kk] = tt.cpu().numpy()[:kk]
+    return tau
 
 
 def fill_local_random(ops_dev, desc: BlockCyclic1D, iseed=(1988, 1989, 1990, 1991), device="cuda"):

@@ -65,3 +65,74 @@ def test_pgetrf_gloo_matches_oracle(world, n, nb, lookahead):
             assert int(d["info"]) == info_ref == 0
         assert np.max(np.abs(lu - ref)) < 1e-11
         assert O.dget01(a, lu, ipiv_ref) < O.THRESH
+
+
+def _spawn(world, n, nb, lookahead, which, extra=()):
+    """returns the list of per-rank npz dicts"""
+    port = _free_port()
+    tmp = tempfile.mkdtemp()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py"), str(n), str(nb), str(lookahead), tmp, which]
+        procs.append(subprocess.Popen(cmd + [str(x) for x in extra], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out.decode()[-2000:]
+    return [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,n,nb,lookahead", [(2, 96, 16, 1), (3, 100, 16, 0), (2, 130, 32, 1)])
+def test_ppotrf_gloo_matches_oracle(world, n, nb, lookahead):
+    res = _spawn(world, n, nb, lookahead, "potrf")
+    s, _ = O.spd_matrix(n, (1988, 1989, 1990, 1991))
+    ref = s.copy(order="F")
+    assert O.dpotrf("L", ref) == 0
+    fac = np.zeros((n, n), order="F")
+    for d in res:
+        fac[:, d["cols"]] = d["lu"]
+        assert int(d["info"]) == 0
+    assert np.all(fac[np.triu_indices(n, 1)] == -1.0e10)              # the other triangle was never touched
+    assert np.max(np.abs(np.tril(fac) - np.tril(ref))) < 1e-11
+    assert O.dpot01("L", s, np.asfortranarray(np.tril(fac))) < O.THRESH
+
+
+def test_ppotrf_gloo_not_positive_definite():
+    n, iz = 96, 41
+    res = _spawn(2, n, 16, 1, "potrf", extra=(iz,))
+    for d in res:
+        assert int(d["info"]) == iz                                   # dchkpo.f:313-344: INFO = IZERO
+
+
+@pytest.mark.parametrize("world,n,nb,lookahead", [(2, 96, 16, 1), (3, 100, 16, 0), (2, 130, 32, 1)])
+def test_pgeqrf_gloo_matches_oracle(world, n, nb, lookahead):
+    res = _spawn(world, n, nb, lookahead, "geqrf")
+    a, _ = O.random_matrix(n, n, (1988, 1989, 1990, 1991))
+    af = np.zeros((n, n), order="F")
+    for d in res:
+        af[:, d["cols"]] = d["lu"]
+        assert np.array_equal(d["tau"], res[0]["tau"])                # tau is replicated
+    tau = res[0]["tau"]
+    r1, r2 = O.dqrt01(a, af, tau)
+    assert r1 < O.THRESH and r2 < O.THRESH
+    ref = a.copy(order="F")
+    O.set_nb(geqrf=nb, nx=1)
+    try:
+        tau_ref, _, _ = O.dgeqrf(ref)
+    finally:
+        O.set_nb()
+    assert np.max(np.abs(tau - tau_ref)) < 1e-11
+    assert np.max(np.abs(af - ref)) < 1e-10
+
+
+def test_pgetrf_gloo_singular_info():
+    n, iz = 96, 23
+    res = _spawn(2, n, 16, 1, "getrf", extra=(iz,))
+    a, _ = O.random_matrix(n, n, (1988, 1989, 1990, 1991))
+    a[:, iz - 1] = 0.0
+    ref = a.copy(order="F")
+    ipiv_ref, info_ref = O.dgetrf(ref)
+    assert info_ref == iz
+    for d in res:
+        assert int(d["info"]) == iz
+        assert np.array_equal(d["ipiv"], ipiv_ref)
