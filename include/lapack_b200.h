@@ -74,6 +74,10 @@ int lb200_dlarft(void* stream, int n, int k, const double* dV, long long ldv, co
                  long long ldt);
 int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const double* dV, long long ldv,
                  const double* dT, long long ldt, double* dC, long long ldc);
+/* SRC/dormqr.f:165, SRC/dorgqr.f:126 on device pointers */
+int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
+                 double* dC, long long ldc);
+int lb200_dorgqr(void* stream, int m, int n, int k, double* dA, long long lda, const double* dtau);
 /* batched 32x32 (config C5b): matrices contiguous, stride 1024 doubles; ipiv 32 ints per matrix */
 int lb200_dgetrf_batched32(void* stream, long long batch, double* dA, int* dipiv, int* dinfo);
 int lb200_dpotrf_batched32(void* stream, char uplo, long long batch, double* dA, int* dinfo);

@@ -62,6 +62,16 @@ lapack_int LAPACKE_dgeqrf_work(int matrix_layout, lapack_int m, lapack_int n, do
 lapack_int LAPACKE_dgeqr2(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
 lapack_int LAPACKE_dgeqr2_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
                                double* work);
+/* lapacke.h:2664, 8163 (DORGQR), 2729, 8246 (DORMQR) -- SURVEY 8f rank 1 */
+lapack_int LAPACKE_dorgqr(int matrix_layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda,
+                          const double* tau);
+lapack_int LAPACKE_dorgqr_work(int matrix_layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda,
+                               const double* tau, double* work, lapack_int lwork);
+lapack_int LAPACKE_dormqr(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k,
+                          const double* a, lapack_int lda, const double* tau, double* c, lapack_int ldc);
+lapack_int LAPACKE_dormqr_work(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k,
+                               const double* a, lapack_int lda, const double* tau, double* c, lapack_int ldc, double* work,
+                               lapack_int lwork);
 /* lapacke.h:2495, 7976 */
 lapack_int LAPACKE_dlarft(int matrix_layout, char direct, char storev, lapack_int n, lapack_int k, const double* v,
                           lapack_int ldv, const double* tau, double* t, lapack_int ldt);

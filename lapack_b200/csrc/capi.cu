@@ -119,6 +119,15 @@ int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const
     lb::larfb(S(stream), side, trans, m, n, k, dV, ldv, dT, ldt, dC, ldc);
     return rc();
 }
+int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
+                 double* dC, long long ldc) {
+    lb::ormqr(S(stream), side, trans, m, n, k, dA, lda, dtau, dC, ldc);
+    return rc();
+}
+int lb200_dorgqr(void* stream, int m, int n, int k, double* dA, long long lda, const double* dtau) {
+    lb::orgqr(S(stream), m, n, k, dA, lda, dtau);
+    return rc();
+}
 int lb200_dgetrf_batched32(void* stream, long long batch, double* dA, int* dipiv, int* dinfo) {
     lb::getrf_batched_32(S(stream), batch, dA, dipiv, dinfo);
     return rc();

@@ -660,4 +660,66 @@ void dlarfb_(const char* side, const char* trans, const char* direct, const char
     c.finish();
 }
 
+// DORGQR / DORMQR.  Reference block sizes for the WORK(1) protocol: ilaenv.f:416-436 (NB=32),
+// dormqr.f:189-190 (NBMAX=64, LDT=65).
+void dorgqr_(const int* m, const int* n, const int* k, double* A, const int* lda, const double* tau, double* work,
+             const int* lwork, int* info) {
+    *info = 0;
+    const int nb = 32, nx = 128;
+    const bool lquery = (*lwork == -1);
+    if (*m < 0) *info = -1;
+    else if (*n < 0 || *n > *m) *info = -2;
+    else if (*k < 0 || *k > *n) *info = -3;
+    else if (*lda < imax(1, *m)) *info = -5;
+    else if (*lwork < imax(1, *n) && !lquery) *info = -8;
+    if (*info != 0) { call_xerbla("DORGQR", -*info); return; }
+    if (lquery) { work[0] = (double)(imax(1, *n) * nb); return; }                   // dorgqr.f:163-165
+    if (*n <= 0) { work[0] = 1.0; return; }
+    if (!device_ok(info)) return;
+    {
+        std::lock_guard<std::mutex> lock(g_abi_mutex);
+        Ctx c; c.scan({A, tau});
+        lb::i64 la;
+        double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+        const double* dt = c.vec<double>(const_cast<double*>(tau), (size_t)*k, true, false);
+        lb::orgqr(c.s, *m, *n, *k, dA, la, dt);
+        int r = c.finish();
+        if (r) *info = r;
+    }
+    int iws = *n;
+    if (nb > 1 && nb < *k && nx < *k) iws = *n * nb;                               // dorgqr.f:200-207,277
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)iws;
+}
+
+void dormqr_(const char* side, const char* trans, const int* m, const int* n, const int* k, const double* A, const int* lda,
+             const double* tau, double* C, const int* ldc, double* work, const int* lwork, int* info, size_t, size_t) {
+    *info = 0;
+    const bool left = same(side, 'L'), notran = same(trans, 'N');
+    const bool lquery = (*lwork == -1);
+    const int nq = left ? *m : *n, nw = left ? imax(1, *n) : imax(1, *m);
+    if (!left && !same(side, 'R')) *info = -1;
+    else if (!notran && !same(trans, 'T')) *info = -2;
+    else if (*m < 0) *info = -3;
+    else if (*n < 0) *info = -4;
+    else if (*k < 0 || *k > nq) *info = -5;
+    else if (*lda < imax(1, nq)) *info = -7;
+    else if (*ldc < imax(1, *m)) *info = -10;
+    else if (*lwork < nw && !lquery) *info = -12;
+    const int lwkopt = nw * 32 + 65 * 32;                                          // dormqr.f:240-244
+    if (*info != 0) { call_xerbla("DORMQR", -*info); return; }
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)lwkopt;
+    if (lquery) return;
+    if (*m == 0 || *n == 0 || *k == 0) { if (ptr_kind(work) != PK_DEVICE) work[0] = 1.0; return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, tau, C});
+    lb::i64 la, lc;
+    const double* dA = c.mat(const_cast<double*>(A), nq, *k, *lda, true, false, &la);
+    const double* dt = c.vec<double>(const_cast<double*>(tau), (size_t)*k, true, false);
+    double* dC = c.mat(C, *m, *n, *ldc, true, true, &lc);
+    lb::ormqr(c.s, left ? 'L' : 'R', notran ? 'N' : 'T', *m, *n, *k, dA, la, dt, dC, lc);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
 }  // extern "C"

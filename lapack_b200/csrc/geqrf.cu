@@ -813,4 +813,70 @@ void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const dou
     ws_free(s, Vc); ws_free(s, E);
 }
 
+// ------------------------------------------------------------------------------------------------
+// DORMQR (SRC/dormqr.f:283-333): C := Q C, Q^T C, C Q or C Q^T with Q = H(1)...H(k) from DGEQRF.  Same block loop as
+// the reference (forward for (L,T) and (R,N), backward otherwise) with NB = 256 instead of 32: DLARFT + DLARFB per block.
+void ormqr(cudaStream_t s, char side, char trans, int m, int n, int k, const double* A, i64 lda, const double* tau,
+           double* C, i64 ldc) {
+    if (m <= 0 || n <= 0 || k <= 0) return;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const int nq = left ? m : n;
+    const int nb = 256;
+    const bool forward = (left && !notran) || (!left && notran);
+    const i64 ldt = nb;
+    double* T = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    const int nblk = ceil_div(k, nb);
+    for (int b = 0; b < nblk; ++b) {
+        const int i = forward ? b * nb : (nblk - 1 - b) * nb;
+        const int ib = min(nb, k - i);
+        const double* Aii = A + i + (i64)i * lda;
+        larft(s, nq - i, ib, Aii, lda, tau + i, T, ldt);
+        if (left) larfb(s, 'L', trans, m - i, n, ib, Aii, lda, T, ldt, C + i, ldc);
+        else larfb(s, 'R', trans, m, n - i, ib, Aii, lda, T, ldt, C + (i64)i * ldc, ldc);
+    }
+    ws_free(s, T);
+}
+
+__global__ void add_diag_kernel(int n, double* A, i64 lda, double v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i + (i64)i * lda] += v;
+}
+
+// DORGQR (SRC/dorgqr.f:220-281): the first n columns of Q = H(1)...H(k), in place over the reflectors.  Blocks are
+// processed backwards like the reference; for each block H is applied to the columns on its right (DLARFB 'L','N'),
+// then the block's own columns become  H [I; 0] = [I; 0] - V (T V1^T)  (what DORG2R computes column by column).
+void orgqr(cudaStream_t s, int m, int n, int k, double* A, i64 lda, const double* tau) {
+    if (n <= 0) return;
+    if (n > k) {
+        // columns k..n-1 start as columns of the unit matrix (dorg2r.f:151-158)
+        laset(s, 'A', k, n - k, 0.0, 0.0, A + (i64)k * lda, lda);
+        laset(s, 'A', m - k, n - k, 0.0, 1.0, A + k + (i64)k * lda, lda);
+    }
+    if (k <= 0) return;
+    const int nb = 256;
+    const i64 ldt = nb, ldvc = ((i64)m + 1) & ~1LL;
+    double* T = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    double* E = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    double* W = (double*)ws_alloc(s, sizeof(double) * ldt * nb);
+    double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * nb);
+    const int nblk = ceil_div(k, nb);
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int i = b * nb;
+        const int ib = min(nb, k - i);
+        const int mi = m - i;
+        double* Aii = A + i + (i64)i * lda;
+        larft(s, mi, ib, Aii, lda, tau + i, T, ldt);
+        if (i + ib < n) larfb(s, 'L', 'N', mi, n - i - ib, ib, Aii, lda, T, ldt, A + i + (i64)(i + ib) * lda, lda);
+        clean_v(s, mi, ib, Aii, lda, Vc, ldvc);
+        expand_tri(s, ib, T, ldt, true, false, E, ldt);
+        gemm(s, 'N', 'T', ib, ib, ib, 1.0, E, ldt, Vc, ldvc, 0.0, W, ldt);          // W = T V1^T
+        gemm(s, 'N', 'N', mi, ib, ib, -1.0, Vc, ldvc, W, ldt, 0.0, Aii, lda);       // block := -V W
+        add_diag_kernel<<<ceil_div(ib, 128), 128, 0, s>>>(ib, Aii, lda, 1.0);       //          + [I; 0]
+        count_launch();
+        if (i > 0) laset(s, 'A', i, ib, 0.0, 0.0, A + (i64)i * lda, lda);           // rows above the block (dorgqr.f:270-274)
+    }
+    ws_free(s, T); ws_free(s, E); ws_free(s, W); ws_free(s, Vc);
+}
+
 }  // namespace lb

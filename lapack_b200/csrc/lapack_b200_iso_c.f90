@@ -59,5 +59,20 @@ module lapack_b200
        real(c_double), value :: alpha, beta
        integer(c_long_long), value :: lda, ldb, ldc
      end function
+     ! SRC/dormqr.f:165  C := Q C, Q**T C, C Q or C Q**T with the reflectors of DGEQRF (device pointers)
+     integer(c_int) function lb200_dormqr(stream, side, trans, m, n, k, dA, lda, dtau, dC, ldc) bind(C, name="lb200_dormqr")
+       import :: c_int, c_long_long, c_ptr, c_char
+       type(c_ptr), value :: stream, dA, dtau, dC
+       character(kind=c_char), value :: side, trans
+       integer(c_int), value :: m, n, k
+       integer(c_long_long), value :: lda, ldc
+     end function
+     ! SRC/dorgqr.f:126  first N columns of Q in place over the reflectors
+     integer(c_int) function lb200_dorgqr(stream, m, n, k, dA, lda, dtau) bind(C, name="lb200_dorgqr")
+       import :: c_int, c_long_long, c_ptr
+       type(c_ptr), value :: stream, dA, dtau
+       integer(c_int), value :: m, n, k
+       integer(c_long_long), value :: lda
+     end function
   end interface
 end module lapack_b200

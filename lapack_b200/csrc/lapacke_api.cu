@@ -400,6 +400,95 @@ lapack_int LAPACKE_dgeqr2(int layout, lapack_int m, lapack_int n, double* a, lap
     return info;
 }
 
+// ------------------------------------------------------------------------------------------------ dorgqr / dormqr
+// LAPACKE/src/lapacke_dorgqr_work.c:41-88, lapacke_dorgqr.c:36-78, lapacke_dormqr_work.c:41-110, lapacke_dormqr.c:36-90
+lapack_int LAPACKE_dorgqr_work(int layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda, const double* tau,
+                               double* work, lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dorgqr_(&m, &n, &k, a, &lda, tau, work, &lwork, &info);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        lapack_int lda_t = imax(1, m);
+        if (lda < n) { info = -6; lapacke_xerbla("LAPACKE_dorgqr_work", info); return info; }
+        if (lwork == -1) {
+            dorgqr_(&m, &n, &k, a, &lda_t, tau, work, &lwork, &info);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor r;
+        if (!r.in(a, m, n, lda)) { info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dorgqr_work", info); return info; }
+        lda_t = imax(1, (int)r.ldc);
+        dorgqr_(&m, &n, &k, r.dev_cm ? r.dev_cm : a, &lda_t, tau, work, &lwork, &info);
+        LB_ADJ(info);
+        r.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dorgqr_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dorgqr(int layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda, const double* tau) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dorgqr", -1); return -1; }
+    if (get_nancheck()) {
+        if (dge_nan(layout, m, n, a, lda)) return -5;
+        if (nan_scan(tau, k, 1, imax(1, k), 0)) return -7;
+    }
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dorgqr_work(layout, m, n, k, a, lda, tau, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dorgqr", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dorgqr_work(layout, m, n, k, a, lda, tau, work, lwork);
+    free(work);
+    return info;
+}
+lapack_int LAPACKE_dormqr_work(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, const double* a,
+                               lapack_int lda, const double* tau, double* c, lapack_int ldc, double* work, lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dormqr_(&side, &trans, &m, &n, &k, a, &lda, tau, c, &ldc, work, &lwork, &info, 1, 1);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        const lapack_int r = lsame(side, 'l') ? m : n;
+        lapack_int lda_t = imax(1, r), ldc_t = imax(1, m);
+        if (lda < k) { info = -8; lapacke_xerbla("LAPACKE_dormqr_work", info); return info; }
+        if (ldc < n) { info = -11; lapacke_xerbla("LAPACKE_dormqr_work", info); return info; }
+        if (lwork == -1) {
+            dormqr_(&side, &trans, &m, &n, &k, a, &lda_t, tau, c, &ldc_t, work, &lwork, &info, 1, 1);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor ra, rc;
+        if (!ra.in(a, r, k, lda) || !rc.in(c, m, n, ldc)) {
+            info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dormqr_work", info); return info;
+        }
+        lda_t = imax(1, (int)ra.ldc); ldc_t = imax(1, (int)rc.ldc);
+        dormqr_(&side, &trans, &m, &n, &k, ra.dev_cm ? ra.dev_cm : a, &lda_t, tau, rc.dev_cm ? rc.dev_cm : c, &ldc_t, work, &lwork,
+                &info, 1, 1);
+        LB_ADJ(info);
+        rc.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dormqr_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dormqr(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, const double* a,
+                          lapack_int lda, const double* tau, double* c, lapack_int ldc) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dormqr", -1); return -1; }
+    if (get_nancheck()) {
+        const lapack_int r = lsame(side, 'l') ? m : n;
+        if (dge_nan(layout, r, k, a, lda)) return -7;
+        if (dge_nan(layout, m, n, c, ldc)) return -10;
+        if (nan_scan(tau, k, 1, imax(1, k), 0)) return -9;
+    }
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dormqr_work(layout, side, trans, m, n, k, a, lda, tau, c, ldc, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dormqr", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dormqr_work(layout, side, trans, m, n, k, a, lda, tau, c, ldc, work, lwork);
+    free(work);
+    return info;
+}
+
 // ------------------------------------------------------------------------------------------------ dlarft / dlarfb (Forward, Columnwise)
 lapack_int LAPACKE_dlarft_work(int layout, char direct, char storev, lapack_int n, lapack_int k, const double* v,
                                lapack_int ldv, const double* tau, double* t, lapack_int ldt) {

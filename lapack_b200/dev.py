@@ -128,6 +128,17 @@ def larfb(side, trans, v, t, c):
                             c.data_ptr(), ld(c)))
 
 
+def ormqr(side, trans, a, tau, c):
+    m, n = c.shape
+    _chk(lib().lb200_dormqr(stream(), _c(side), _c(trans), m, n, tau.shape[0], a.data_ptr(), ld(a), tau.data_ptr(),
+                            c.data_ptr(), ld(c)))
+
+
+def orgqr(a, tau):
+    m, n = a.shape
+    _chk(lib().lb200_dorgqr(stream(), m, n, tau.shape[0], a.data_ptr(), ld(a), tau.data_ptr()))
+
+
 def getrf_batched32(a):
     """a: (batch, 32, 32) tensor whose [b] slices are column-major, i.e. a contiguous (batch, 32(col), 32(row)) buffer"""
     torch = _torch()

@@ -163,6 +163,40 @@ def geqrf(a):
     return tau[:min(m, n)], info, work[0]
 
 
+def dorgqr(m, n, k, a, lda, tau, work, lwork):
+    info = _i(0)
+    lib().dorgqr_(_r(m), _r(n), _r(k), _p(a), _r(lda), _p(tau), _p(work), _r(lwork), C.byref(info))
+    return info.value
+
+
+def dormqr(side, trans, m, n, k, a, lda, tau, c, ldc, work, lwork):
+    info = _i(0)
+    lib().dormqr_(_c(side), _c(trans), _r(m), _r(n), _r(k), _p(a), _r(lda), _p(tau), _p(c), _r(ldc), _p(work), _r(lwork),
+                  C.byref(info), C.c_size_t(1), C.c_size_t(1))
+    return info.value
+
+
+def orgqr(a, tau):
+    """a (m x n, holding the reflectors) := first n columns of Q; workspace query protocol like the reference"""
+    m, n = a.shape
+    wq = np.zeros(1)
+    info = dorgqr(m, n, len(tau), a, _ld(a), tau, wq, -1)
+    if info != 0:
+        return info
+    work = np.zeros(max(1, int(wq[0])))
+    return dorgqr(m, n, len(tau), a, _ld(a), tau, work, len(work))
+
+
+def ormqr(side, trans, a, tau, c):
+    m, n = c.shape
+    wq = np.zeros(1)
+    info = dormqr(side, trans, m, n, len(tau), a, _ld(a), tau, c, _ld(c), wq, -1)
+    if info != 0:
+        return info
+    work = np.zeros(max(1, int(wq[0])))
+    return dormqr(side, trans, m, n, len(tau), a, _ld(a), tau, c, _ld(c), work, len(work))
+
+
 def geqr2(a):
     m, n = a.shape
     tau = np.zeros(max(1, min(m, n)))

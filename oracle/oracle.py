@@ -246,6 +246,19 @@ def dorgqr(a, tau, k=None):
 THRESH = 30.0
 
 
+def dormqr(side, trans, a, tau, c, k=None):
+    """C := Q C, Q^T C, C Q or C Q^T with Q from dgeqrf(a, tau) (SRC/dormqr.f); c is overwritten"""
+    m, n = c.shape
+    k = len(tau) if k is None else k
+    nw = max(1, n) if side.upper() == "L" else max(1, m)
+    lwork = nw * 64 + 65 * 64
+    work = np.zeros(lwork)
+    info = C.c_int(0)
+    lib().ora_dormqr(_c(side), _c(trans), m, n, k, _d(a), _ld(a), _d(np.ascontiguousarray(tau)), _d(c), _ld(c),
+                     _d(work), lwork, C.byref(info))
+    return info.value
+
+
 def dget01(a, afac, ipiv):
     m, n = a.shape
     af = np.array(afac, order="F", copy=True)

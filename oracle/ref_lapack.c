@@ -46,7 +46,7 @@ int ora_ilaenv_nb(const char *name)
 {
     if (!strcmp(name, "DGETRF")) return g_nb_getrf;
     if (!strcmp(name, "DPOTRF")) return g_nb_potrf;
-    if (!strcmp(name, "DGEQRF") || !strcmp(name, "DORGQR")) return g_nb_geqrf;
+    if (!strcmp(name, "DGEQRF") || !strcmp(name, "DORGQR") || !strcmp(name, "DORMQR")) return g_nb_geqrf;   /* ilaenv.f:416-436: 32 */
     return 1;
 }
 
@@ -647,6 +647,63 @@ void ora_dorg2r(int m, int n, int k, double *a, int lda, const double *tau, doub
         A_(i, i) = 1.0 - tau[i];
         for (int l = 0; l < i; ++l) A_(l, i) = 0.0;
     }
+}
+
+/* SRC/dorm2r.f:195-271 -- unblocked application of Q or Q**T from DGEQRF (work: n if SIDE='L', m if 'R'). */
+void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
+                double *work, int *info)
+{
+    int left = ora_lsame(side, 'L'), notran = ora_lsame(trans, 'N');
+    int nq = left ? m : n;
+    *info = 0;
+    if (!left && !ora_lsame(side, 'R')) *info = -1; else if (!notran && !ora_lsame(trans, 'T')) *info = -2;
+    else if (m < 0) *info = -3; else if (n < 0) *info = -4; else if (k < 0 || k > nq) *info = -5;
+    else if (lda < imax(1, nq)) *info = -7; else if (ldc < imax(1, m)) *info = -10;
+    if (*info != 0) return;
+    if (m == 0 || n == 0 || k == 0) return;
+    int forward = (left && !notran) || (!left && notran);          /* dorm2r.f:226-235 */
+    for (int t = 0; t < k; ++t) {
+        int i = forward ? t : k - 1 - t;                           /* 0-based reflector index */
+        if (left) ora_dlarf1f('L', m - i, n, &A_(i, i), 1, tau[i], &c[i], ldc, work);                  /* C(i:m,1:n) */
+        else ora_dlarf1f('R', m, n - i, &A_(i, i), 1, tau[i], &c[(size_t)i * ldc], ldc, work);         /* C(1:m,i:n) */
+    }
+}
+
+/* SRC/dormqr.f:203-336 (NB = min(64, ILAENV) = 32, LDT = 65; blocked DLARFT + DLARFB, DORM2R when NB >= K). */
+void ora_dormqr(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
+                double *work, int lwork, int *info)
+{
+    const int nbmax = 64, ldt = nbmax + 1;
+    int left = ora_lsame(side, 'L'), notran = ora_lsame(trans, 'N');
+    int lquery = (lwork == -1);
+    int nq = left ? m : n, nw = left ? imax(1, n) : imax(1, m);
+    *info = 0;
+    if (!left && !ora_lsame(side, 'R')) *info = -1; else if (!notran && !ora_lsame(trans, 'T')) *info = -2;
+    else if (m < 0) *info = -3; else if (n < 0) *info = -4; else if (k < 0 || k > nq) *info = -5;
+    else if (lda < imax(1, nq)) *info = -7; else if (ldc < imax(1, m)) *info = -10;
+    else if (lwork < nw && !lquery) *info = -12;
+    int nb = imin(nbmax, ora_ilaenv_nb("DORMQR"));
+    int lwkopt = nw * nb + ldt * nb;
+    if (*info == 0) work[0] = (double)lwkopt;
+    if (*info != 0 || lquery) return;
+    if (m == 0 || n == 0 || k == 0) { work[0] = 1.0; return; }
+    int nbmin = 2, ldwork = nw, iinfo;
+    if (nb > 1 && nb < k && lwork < lwkopt) { nb = lwork / (ldwork + ldt); nbmin = 2; }
+    if (nb < nbmin || nb >= k) {
+        ora_dorm2r(side, trans, m, n, k, a, lda, tau, c, ldc, work, &iinfo);
+    } else {
+        double *tw = work + (size_t)nw * nb;                       /* IWT = 1 + NW*NB */
+        int forward = (left && !notran) || (!left && notran);
+        int nblk = (k + nb - 1) / nb;
+        for (int b = 0; b < nblk; ++b) {
+            int i = forward ? b * nb : (nblk - 1 - b) * nb;
+            int ib = imin(nb, k - i);
+            ora_dlarft('F', 'C', nq - i, ib, &A_(i, i), lda, tau + i, tw, ldt);
+            if (left) ora_dlarfb('L', trans, 'F', 'C', m - i, n, ib, &A_(i, i), lda, tw, ldt, &c[i], ldc, work, ldwork);
+            else ora_dlarfb('R', trans, 'F', 'C', m, n - i, ib, &A_(i, i), lda, tw, ldt, &c[(size_t)i * ldc], ldc, work, ldwork);
+        }
+    }
+    work[0] = (double)lwkopt;
 }
 
 /* SRC/dorgqr.f:160-277 (NB=32, NX=128 from ilaenv.f for xORGQR; work >= n*nb). */

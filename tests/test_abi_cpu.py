@@ -126,6 +126,28 @@ def test_qr_error_exits_and_query(lb):
     assert f.dgeqrf(0, 5, A, 1, TAU, wq, -1) == 0 and wq[0] == 1
 
 
+def test_orgqr_ormqr_error_exits_and_query(lb):
+    """TESTING/LIN/derrqr.f:177-259: XERBLA positions of DORGQR and DORMQR."""
+    f = lb.f77
+    X, AF = TAU, B
+    for args, pos in (((-1, 0, 0, A, 1, X, W, 1), 1), ((0, -1, 0, A, 1, X, W, 1), 2), ((1, 2, 0, A, 1, X, W, 2), 2),
+                      ((0, 0, -1, A, 1, X, W, 1), 3), ((1, 1, 2, A, 1, X, W, 1), 3), ((2, 2, 0, A, 1, X, W, 2), 5),
+                      ((2, 2, 0, A, 2, X, W, 1), 8)):
+        assert expect(lb, lambda a=args: f.dorgqr(*a), "DORGQR", pos) == -pos
+    for args, pos in ((("/", "N", 0, 0, 0, A, 1, X, AF, 1, W, 1), 1), (("L", "/", 0, 0, 0, A, 1, X, AF, 1, W, 1), 2),
+                      (("L", "N", -1, 0, 0, A, 1, X, AF, 1, W, 1), 3), (("L", "N", 0, -1, 0, A, 1, X, AF, 1, W, 1), 4),
+                      (("L", "N", 0, 0, -1, A, 1, X, AF, 1, W, 1), 5), (("L", "N", 0, 1, 1, A, 1, X, AF, 1, W, 1), 5),
+                      (("R", "N", 1, 0, 1, A, 1, X, AF, 1, W, 1), 5), (("L", "N", 2, 1, 0, A, 1, X, AF, 2, W, 1), 7),
+                      (("R", "N", 1, 2, 0, A, 1, X, AF, 1, W, 1), 7), (("L", "N", 2, 1, 0, A, 2, X, AF, 1, W, 1), 10),
+                      (("L", "N", 1, 2, 0, A, 1, X, AF, 1, W, 1), 12), (("R", "N", 2, 1, 0, A, 1, X, AF, 2, W, 1), 12)):
+        assert expect(lb, lambda a=args: f.dormqr(*a), "DORMQR", pos) == -pos
+    wq = np.zeros(1)
+    assert f.dorgqr(300, 200, 200, A, 300, TAU, wq, -1) == 0 and wq[0] == 200 * 32         # dorgqr.f:163-165
+    assert f.dormqr("L", "T", 300, 7, 200, A, 300, TAU, B, 300, wq, -1) == 0 and wq[0] == 7 * 32 + 65 * 32   # dormqr.f:240-244
+    assert f.dormqr("R", "N", 7, 300, 200, A, 300, TAU, B, 7, wq, -1) == 0 and wq[0] == 7 * 32 + 65 * 32
+    assert f.dormqr("L", "N", 0, 0, 0, A, 1, TAU, B, 1, wq, 1) == 0 and wq[0] == 1             # quick return, no GPU needed
+
+
 def test_quick_returns_need_no_gpu(lb):
     """M==0 or N==0 return before any device work (dgetrf.f:159, dpotrf.f:161, dgeqrf.f:209-212)."""
     f = lb.f77

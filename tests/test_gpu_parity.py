@@ -486,6 +486,77 @@ def test_dlarft_dlarfb_vs_oracle(lb):
             assert rel(got, want) < 1e-11
 
 
+# ------------------------------------------------------------------------------------------- DORGQR / DORMQR
+@pytest.mark.parametrize("shape", [(1, 1), (40, 40), (300, 170), (700, 700), (1500, 520)])
+def test_dorgqr_dormqr_vs_oracle(lb, shape):
+    m, n = shape
+    a, _ = O.random_matrix(m, n, SEED)
+    af = a.copy(order="F")
+    tau, info, _ = lb.f77.geqrf(af)
+    assert info == 0
+    k = min(m, n)
+    # DORGQR: first n columns of Q, vs the oracle on the same reflectors; orthogonality and A = Q R
+    q = af.copy(order="F")
+    assert lb.f77.orgqr(q, tau) == 0
+    q_ref = af.copy(order="F")
+    assert O.dorgqr(q_ref, tau) == 0
+    assert rel(q, q_ref) < 1e-12
+    assert np.max(np.abs(q.T @ q - np.eye(n))) < 1e-12 * max(m, 10)
+    assert rel(q @ np.triu(af[:n, :]), a) < 1e-12 * max(n, 10)
+    # partial generation (n_q < k columns, k_q < n_q reflectors) like dqrt02.f
+    if n >= 8:
+        nq, kq = n - 3, n - 5
+        q2 = af[:, :nq].copy(order="F")
+        assert lb.f77.orgqr(q2, tau[:kq]) == 0
+        q2_ref = af[:, :nq].copy(order="F")
+        assert O.dorgqr(q2_ref, tau[:kq]) == 0
+        assert rel(q2, q2_ref) < 1e-12
+    # DORMQR: all four SIDE/TRANS combinations against the oracle (dqrt03.f checks the same products)
+    nc = 11
+    for side in "LR":
+        c0, _ = O.random_matrix(m if side == "L" else nc, nc if side == "L" else m, (3, 5, 7, 9))
+        for trans in "NT":
+            c = c0.copy(order="F")
+            assert lb.f77.ormqr(side, trans, af, tau, c) == 0
+            c_ref = c0.copy(order="F")
+            assert O.dormqr(side, trans, af, tau, c_ref) == 0
+            assert rel(c, c_ref) < 1e-12, (side, trans)
+    # Q^T A = R: the use the reference's own checker makes of DORMQR (dqrt01.f:191-200 forms it with DORGQR)
+    c = a.copy(order="F")
+    assert lb.f77.ormqr("L", "T", af, tau, c) == 0
+    assert rel(np.triu(c[:k, :]), np.triu(af[:k, :])) < 1e-12 * max(n, 10)
+    assert np.max(np.abs(np.tril(c, -1))) < 1e-12 * max(m, 10) * np.max(np.abs(a))
+
+
+def test_lapacke_dorgqr_dormqr_row_major(lb):
+    import ctypes as C
+    L = lb.lib()
+    m, n, nc = 120, 70, 9
+    a, _ = O.random_matrix(m, n, SEED)
+    af = a.copy(order="F")
+    tau, info, _ = lb.f77.geqrf(af)
+    dp = C.POINTER(C.c_double)
+    ptr = lambda x: x.ctypes.data_as(dp)
+    L.LAPACKE_dorgqr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp]
+    L.LAPACKE_dormqr.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int]
+    q_ref = af.copy(order="F")
+    O.dorgqr(q_ref, tau)
+    q_rm = np.array(af, order="C", copy=True)                       # row-major storage, lda = n
+    assert L.LAPACKE_dorgqr(101, m, n, n, ptr(q_rm), n, ptr(tau)) == 0
+    assert rel(q_rm, q_ref) < 1e-12
+    c0, _ = O.random_matrix(m, nc, (3, 5, 7, 9))
+    c_ref = c0.copy(order="F")
+    O.dormqr("L", "T", af, tau, c_ref)
+    a_rm = np.array(af, order="C", copy=True)
+    c_rm = np.array(c0, order="C", copy=True)
+    assert L.LAPACKE_dormqr(101, b"L", b"T", m, nc, n, ptr(a_rm), n, ptr(tau), ptr(c_rm), nc) == 0
+    assert rel(c_rm, c_ref) < 1e-12
+    c_cm = c0.copy(order="F")
+    assert L.LAPACKE_dormqr(102, b"L", b"T", m, nc, n, ptr(af), m, ptr(tau), ptr(c_cm), m) == 0
+    assert rel(c_cm, c_ref) < 1e-12
+    assert L.LAPACKE_dormqr(101, b"L", b"T", m, nc, n, ptr(a_rm), n - 1, ptr(tau), ptr(c_rm), nc) == -8   # lda < k
+
+
 # ------------------------------------------------------------------------------------------- batched 32x32
 def test_batched_getrf32(lb):
     batch = 3000

@@ -218,3 +218,27 @@ def test_dposv_solution_and_residuals():
         assert O.dpot01(uplo, s, f) < O.THRESH
         assert O.dpot02(uplo, s, x, b) < O.THRESH
         assert np.max(np.abs(x - xact)) / np.max(np.abs(xact)) < 1e-12
+
+
+@pytest.mark.parametrize("tag", ["tall", "sq"])
+def test_dormqr_dorgqr_netlib(tag):
+    """ora_dormqr / ora_dorgqr vs netlib 3.12.0 (tests/golden/make_golden_ormqr.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "netlib_golden_ormqr.npz"))
+    qr, tau = np.asfortranarray(g[f"{tag}_qr"]), g[f"{tag}_tau"]
+    for side, c0 in (("L", g[f"{tag}_cl"]), ("R", g[f"{tag}_cr"])):
+        for trans in "NT":
+            c = np.asfortranarray(c0.copy())
+            assert O.dormqr(side, trans, qr, tau, c) == 0
+            assert np.max(np.abs(c - g[f"{tag}_ormqr_{side}{trans}"])) < 1e-12
+    q = qr.copy(order="F")
+    assert O.dorgqr(q, tau) == 0
+    assert np.max(np.abs(q - g[f"{tag}_q"])) < 1e-12
+    # unblocked path (K <= NB) agrees with the blocked one
+    O.set_nb(geqrf=128)
+    try:
+        c = np.asfortranarray(g[f"{tag}_cl"].copy())
+        assert O.dormqr("L", "T", qr, tau, c) == 0
+        assert np.max(np.abs(c - g[f"{tag}_ormqr_LT"])) < 1e-12
+    finally:
+        O.set_nb()
