@@ -21,12 +21,12 @@ def lb():
 
 def declared_symbols():
     names = set()
-    for h in ("lapack_b200.h", "lapack_b200_f77.h", "lapack_b200_lapacke.h"):
+    for h in ("lapack_b200.h", "lapack_b200_f77.h", "lapack_b200_lapacke.h", "lapack_b200_cblas.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        for m in re.finditer(r"\b(lb200_\w+|LAPACKE_\w+|[a-z0-9]+_)\s*\(", src):
+        for m in re.finditer(r"\b(lb200_\w+|LAPACKE_\w+|cblas_\w+|[a-z0-9]+_)\s*\(", src):
             n = m.group(1)
-            if n.startswith(("lb200_", "LAPACKE_")) or re.fullmatch(r"(d[a-z0-9]+|xerbla|lsame)_", n):
+            if n.startswith(("lb200_", "LAPACKE_", "cblas_")) or re.fullmatch(r"(d[a-z0-9]+|xerbla|lsame)_", n):
                 names.add(n)
     return sorted(names)
 
@@ -205,3 +205,23 @@ def test_lapacke_layer_errors(lb):
     assert L.LAPACKE_dgetrf(102, 2, 2, vp(nan), 2, vp(IP)) == -4                    # NaN pre-check (lapacke_dgetrf.c:42-49)
     assert L.LAPACKE_dpotrf(102, C.c_char(b"L"), 2, vp(nan), 2) == -4
     assert L.LAPACKE_dgesv(102, 2, 1, vp(A), 2, vp(IP), vp(nan), 2) == -7
+
+
+def test_cblas_illegal_enums_need_no_gpu(lb, capfd):
+    """CBLAS/src/cblas_dgemm.c:52-76, cblas_dtrsm.c:46-84: illegal option values are reported and nothing is computed."""
+    L = lb.lib()
+    dp = C.POINTER(C.c_double)
+    L.cblas_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_int, dp, C.c_int,
+                              C.c_double, dp, C.c_int]
+    L.cblas_dtrsm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, dp, C.c_int, dp, C.c_int]
+    L.cblas_dgemm.restype = None
+    L.cblas_dtrsm.restype = None
+    c = np.full((2, 2), 5.0)
+    p = lambda x: x.ctypes.data_as(dp)
+    L.cblas_dgemm(102, 999, 111, 2, 2, 2, 1.0, p(A), 2, p(B), 2, 0.0, p(c), 2)
+    L.cblas_dgemm(100, 111, 111, 2, 2, 2, 1.0, p(A), 2, p(B), 2, 0.0, p(c), 2)
+    L.cblas_dtrsm(101, 141, 121, 111, 555, 2, 2, 1.0, p(A), 2, p(c), 2)
+    err = capfd.readouterr().err
+    assert "Parameter 2 to routine cblas_dgemm" in err and "Parameter 1 to routine cblas_dgemm" in err
+    assert "Parameter 5 to routine cblas_dtrsm" in err
+    assert np.all(c == 5.0)
