@@ -21,6 +21,7 @@
 #include <cfloat>
 #include <math_constants.h>
 #include <mutex>
+#include <vector>
 
 namespace lb {
 
@@ -664,8 +665,43 @@ void getrf2(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* in
     getrf_panel(s, m, n, A, lda, ipiv, info, 0);
 }
 
+// Optional timeline of the blocked driver (LB200_TRACE_LU=1): timing events around every chunk GEMM and every panel;
+// after the factorization the per-step intervals are printed to stderr (the call becomes synchronous).
+struct LuTrace {
+    struct Rec { int step, kind; cudaEvent_t e0, e1; };     // kind 0..3 = GEMM chunk, 4..7 = preparation of chunk, 8 = panel
+    std::vector<Rec> recs;
+    cudaEvent_t origin = nullptr;
+    void mark(cudaStream_t st, int step, int kind, bool begin) {
+        if (begin) {
+            Rec r{step, kind, nullptr, nullptr};
+            cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+            cudaEventRecord(r.e0, st);
+            recs.push_back(r);
+        } else {
+            for (int i = (int)recs.size() - 1; i >= 0; --i)
+                if (recs[i].step == step && recs[i].kind == kind) { cudaEventRecord(recs[i].e1, st); break; }
+        }
+    }
+    void dump() {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "LU_TRACE step kind start_ms end_ms\n");
+        for (auto& r : recs) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, origin, r.e0);
+            cudaEventElapsedTime(&b, origin, r.e1);
+            fprintf(stderr, "LU_TRACE %d %d %.3f %.3f\n", r.step, r.kind, a, b);
+            cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+        }
+        recs.clear();
+    }
+};
+
 void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
     std::lock_guard<std::mutex> lock(g_lib_mutex);
+    static const bool trace_on = getenv("LB200_TRACE_LU") != nullptr;
+    LuTrace trace;
+    LuTrace* tr = trace_on ? &trace : nullptr;
+    if (tr) { cudaEventCreate(&tr->origin); cudaEventRecord(tr->origin, s); }
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     if (m <= 0 || n <= 0) return;
     const int mn = min(m, n);
@@ -676,16 +712,17 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     Aux& ax = aux();
     // Streams (look-ahead on): sp = panel (highest priority), sq = memory-bound preparation of the trailing
     // columns (interchanges + U12 solve, medium priority), su = trailing GEMMs (low priority), sl = interchanges
-    // left of the panel (low priority, off the critical path).  The trailing columns are processed in three
-    // chunks -- next panel's columns, a quarter of the rest, the remainder -- so that the preparation of chunk
-    // c+1 overlaps with the GEMM of chunk c.
+    // left of the panel (low priority, off the critical path).  The trailing columns are processed in four
+    // chunks -- the next panel's columns, the panel after that, a quarter of the rest, the remainder -- so that the
+    // preparation of chunk c+1 overlaps with the GEMM of chunk c, and the preparation of the NEXT step's first chunk
+    // (this step's chunk 1) can start while this step's big chunks are still running.
     cudaStream_t sp = la ? ax.panel_stream : s;
     cudaStream_t sq = la ? ax.prep_stream : s;
     cudaStream_t su = la ? ax.update_stream : s;
     cudaStream_t sl = la ? ax.side_stream : s;
     cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2], ev_plan = ax.ev[8], ev_left = ax.ev[9];
-    cudaEvent_t ev_gemm = ax.ev[10];
-    cudaEvent_t ev_prep[3] = {ax.ev[11], ax.ev[12], ax.ev[13]};
+    cudaEvent_t ev_gemm = ax.ev[10], ev_g1 = ax.ev[15];
+    cudaEvent_t ev_prep[4] = {ax.ev[11], ax.ev[12], ax.ev[13], ax.ev[14]};
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
@@ -696,49 +733,71 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     // first panel
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
-    bool gemm_recorded = false;
+    bool gemm_recorded = false, g1_recorded = false;
+    int g1_end = 0;              // last column (exclusive) covered by the previous step's chunk-1 GEMM
 
     for (int j = 0; j < mn; j += nb) {
         const int jb = min(nb, mn - j);
         const int jn = j + jb;                       // first column after this panel
         double* Ajj = A + j + (i64)j * lda;
         const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
-        if (la) {
-            LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
-            if (gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));   // update j-1 is complete
-        }
-        // one plan for this panel's interchanges (dgetrf.f:193,199), applied to all column ranges
-        void* plan = laswp_plan(sq, j + 1, jn, piv, 1);
+        bool g1_now = false;
+        int g1_end_now = 0;
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
-        // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel)
-        int c[4];
+        // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel),
+        // [c[1],c[2]) = the panel after that, then a quarter of the rest, then the remainder
+        int c[5];
         int nchunk = 0;
         c[0] = jn;
         if (jn < n) {
             const int w1 = (jb2 > 0) ? jb2 : (n - jn);
             c[++nchunk] = jn + w1;
-            const int rest = n - jn - w1;
+            int rest = n - jn - w1;
+            if (rest > 0) {
+                const int w2 = min(nb, rest);
+                c[nchunk + 1] = c[nchunk] + w2;
+                ++nchunk;
+                rest -= w2;
+            }
             if (rest > 0) {
                 int h1 = (rest >= 4096) ? ((rest / 4 + 63) / 64) * 64 : rest;
-                c[++nchunk] = jn + w1 + h1;
+                c[nchunk + 1] = c[nchunk] + h1;
+                ++nchunk;
                 if (h1 < rest) c[++nchunk] = n;
             }
         }
+        if (la) {
+            LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
+            // chunk 0 of this step was (part of) chunk 1 of the previous step: its preparation may start as soon as
+            // THAT GEMM is done, while the big chunks of update j-1 are still running
+            if (g1_recorded && nchunk >= 1 && c[1] <= g1_end) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_g1, 0));
+            else if (gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));
+        }
+        // one plan for this panel's interchanges (dgetrf.f:193,199), applied to all column ranges
+        void* plan = laswp_plan(sq, j + 1, jn, piv, 1);
         // preparation on sq: interchanges + block row of U for every chunk, in order
         for (int q = 0; q < nchunk; ++q) {
             const int w = c[q + 1] - c[q];
+            // every chunk but the first also needs the whole update j-1 (its columns were in the big chunks)
+            if (q == 1 && la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));
+            if (tr) tr->mark(sq, j / nb, 4 + q, true);
             laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);                              // dgetrf.f:199
             trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);         // dgetrf.f:204
+            if (tr) tr->mark(sq, j / nb, 4 + q, false);
             if (la) LB_CUDA_CHECK(cudaEventRecord(ev_prep[q], sq));
         }
+        if (nchunk <= 1 && la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));   // keep sq ordered after update j-1
         if (la) LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
         // GEMMs on su; the next panel is factored right after the first chunk
         for (int q = 0; q < nchunk; ++q) {
             const int w = c[q + 1] - c[q];
             if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(su, ev_prep[q], 0));
+            if (tr) tr->mark(su, j / nb, q, true);
             if (jn < m)
                 gemm(su, 'N', 'N', m - jn, w, jb, -1.0, A + jn + (i64)j * lda, lda, A + j + (i64)c[q] * lda, lda, 1.0,
                      A + jn + (i64)c[q] * lda, lda);                                                   // dgetrf.f:212
+            if (tr) tr->mark(su, j / nb, q, false);
+            if (q == 1 && la) { LB_CUDA_CHECK(cudaEventRecord(ev_g1, su)); g1_now = true; g1_end_now = c[2]; }
             if (q == 0 && jb2 > 0) {
                 if (la) {
                     LB_CUDA_CHECK(cudaEventRecord(ev_next, su));
@@ -746,11 +805,15 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 }
                 // factor the next panel (overlaps with the rest of this update when look-ahead is on)
                 // the leaves write absolute pivot rows (dgetrf.f:187-189 shift applied at the source)
+                if (tr) tr->mark(sp, j / nb, 8, true);
                 getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
+                if (tr) tr->mark(sp, j / nb, 8, false);
                 if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
             }
         }
         if (la) { LB_CUDA_CHECK(cudaEventRecord(ev_gemm, su)); gemm_recorded = true; }
+        g1_recorded = g1_now;
+        g1_end = g1_end_now;
         // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns whose only
         // remaining reader was the trailing GEMM of the previous step (sq waited for it above), so they run on
         // a low-priority side stream concurrently with this step's trailing update.
@@ -768,6 +831,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_plan, 0));
     }
+    if (tr) { tr->dump(); cudaEventDestroy(tr->origin); }
 }
 
 // DGETRS (SRC/dgetrs.f:181-218); argument checks live in the Fortran-ABI layer
