@@ -36,6 +36,8 @@ void lb200_set_gemm_tma(int on);       /* 0 disables the TMA fast path (falls ba
 void lb200_set_getrf_params(int nb, int leaf, int lookahead);
 /* panels of at most ctas*1024 rows are factored by the thread-block-cluster leaf kernel (default 8, 0 = never, max 16) */
 void lb200_set_getrf_cluster_max(int ctas);
+/* panels too tall for one cluster: 1 (default) = 256-thread x 4-row leaf kernel, 0 = 1024-thread x 1-row kernel */
+void lb200_set_getrf_big_leaf(int rows4);
 void lb200_set_geqrf_cluster_max(int ctas);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);

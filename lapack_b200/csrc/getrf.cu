@@ -33,6 +33,8 @@ void laswp_plan_free(cudaStream_t s, void* plan);
 static int g_nb = 512, g_lookahead = 1;
 static int g_cluster_max = 16;      // panels of up to this many 1024-row CTAs use the cluster leaf (0 = never)
 void getrf_set_cluster_max(int c) { g_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
+static int g_big_leaf_rows4 = 1;    // panels too tall for a cluster: 1 = 256 threads x 4 rows kernel, 0 = 1024 x 1 row kernel
+void getrf_set_big_leaf(int v) { g_big_leaf_rows4 = v ? 1 : 0; }
 void getrf_set_params(int nb, int leaf, int lookahead) {
     (void)leaf;
     if (nb > 0) g_nb = nb;
@@ -321,7 +323,7 @@ __device__ __forceinline__ void warp_argmax(double& key, int& krow) {
 // R rows per thread (row = g*R*THREADS + r*THREADS + tid): the per-step bookkeeping (reductions, barriers, the
 // pull of the pivot row) is paid once per thread, so few fat threads beat many thin ones -- the kernel is bound
 // by instruction issue, not by latency.
-template <int W, int THREADS, int R>
+template <int W, int THREADS, int R, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafParams p) {
     constexpr int NWARP = THREADS / 32;
     constexpr int ROWS = THREADS * R;
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafPara
             key = __shfl_sync(0xffffffffu, k2, 0);
             krow = __shfl_sync(0xffffffffu, r2, 0);
         }
+        if (CLUSTER) {
         // (2) publish the CTA's best row (and the top row) in this CTA's shared memory
         if (krow == 0x7fffffff) {
             if (tid == 0) { s_cand[slot].key = -2.0; s_cand[slot].row = 0x7fffffff; }     // no active row here
@@ -450,6 +453,60 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafPara
                 s_trow[lane - W] = ld_dsmem_f64(ta);
             }
             if (lane == 0) s_win_row = r2;
+        }
+        } else {
+        // (2') no cluster (taller panels): tagged packets in global memory, as in getrf_leaf_kernel -- data first, the
+        //      tag {epoch, row} last with st.release; every CTA's warp 0 polls all G tags with ld.acquire
+        const unsigned epoch = p.epoch_base + c + 1;
+        if (krow == 0x7fffffff) {
+            if (tid == 0) {
+                LeafPacket* cp = p.cand + slot * p.G + g;
+                cp->key = -2.0;
+                st_release_u64(&cp->tag, ((unsigned long long)epoch << 32) | 0x7fffffffu);
+            }
+        } else if (((krow - row0) % THREADS) == 0 && krow >= row0 && krow < row0 + R * THREADS) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (krow == row0 + r * THREADS) {
+                    LeafPacket* cp = p.cand + slot * p.G + g;
+                    cp->key = key;
+#pragma unroll
+                    for (int q = 0; q < W; ++q) cp->rowdata[q] = a[r][q];
+                    st_release_u64(&cp->tag, ((unsigned long long)epoch << 32) | (unsigned)krow);
+                }
+        }
+        if (row0 == c) {
+            LeafPacket* tp = p.top + slot;
+#pragma unroll
+            for (int q = 0; q < W; ++q) tp->rowdata[q] = a[0][q];
+            st_release_u64(&tp->tag, ((unsigned long long)epoch << 32));
+        }
+        if (warp == 0) {
+            double k2 = -3.0;
+            int r2 = 0x7fffffff, g2 = 0;
+            for (int q = lane; q < p.G; q += 32) {
+                const LeafPacket* cp = p.cand + slot * p.G + q;
+                unsigned long long tag = poll_tag(&cp->tag, epoch);
+                double ck = __ldcg(&cp->key);
+                int cr = (int)(unsigned)(tag & 0xffffffffu);
+                if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                double ok = __shfl_xor_sync(0xffffffffu, k2, off);
+                int orow = __shfl_xor_sync(0xffffffffu, r2, off);
+                int og = __shfl_xor_sync(0xffffffffu, g2, off);
+                if (cand_better(ok, orow, k2, r2)) { k2 = ok; r2 = orow; g2 = og; }
+            }
+            if (lane < W) {
+                (void)poll_tag(&p.cand[slot * p.G + g2].tag, epoch);        // own acquire for the data below
+                s_prow[lane] = __ldcg(&p.cand[slot * p.G + g2].rowdata[lane]);
+            } else if (lane < 2 * W) {
+                (void)poll_tag(&p.top[slot].tag, epoch);
+                s_trow[lane - W] = __ldcg(&p.top[slot].rowdata[lane - W]);
+            }
+            if (lane == 0) s_win_row = r2;
+        }
         }
         __syncthreads();
         const int prow = s_win_row;
@@ -520,8 +577,10 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafPara
         }
     }
     // nobody may exit while its shared memory can still be read by a peer
-    cluster_arrive_release();
-    cluster_wait_acquire();
+    if (CLUSTER) {
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -566,7 +625,7 @@ struct PanelCtx {
 static int cluster_hw_max() {
     static int hw_max = 0;
     if (!hw_max) {
-        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R>;
+        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R, true>;
         hw_max = 8;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
             cudaLaunchConfig_t q = {};
@@ -604,7 +663,7 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     const int S = ceil_div(pc.width, LEAF_THREADS);
     if (p.G <= g_cluster_max && p.G <= cluster_hw_max()) {
         // one cluster of G work CTAs (+ clusters of interchange CTAs when the panel is wider than the leaf)
-        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R>;
+        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R, true>;
         const bool outside = pc.width > n;
         int nclusters = 1;
         if (outside) nclusters += ceil_div(ceil_div(pc.width, CL_THREADS), p.G);
@@ -620,6 +679,15 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
         LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
         count_launch();
         w.epoch += (unsigned)min(m, n);
+        return;
+    }
+    if (g_big_leaf_rows4) {
+        // taller panels: same 256 x 4-row kernel, exchange through global packets (all CTAs must be co-resident)
+        const int S4 = ceil_div(pc.width, CL_THREADS);
+        getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R, false><<<p.G + (pc.width > n ? S4 : 0), CL_THREADS, 0, s>>>(p);
+        count_launch();
+        w.epoch += (unsigned)min(m, n);
+        LB_CUDA_CHECK(cudaGetLastError());
         return;
     }
     getrf_leaf_kernel<LEAF_W, LEAF_THREADS><<<p.G + S, LEAF_THREADS, 0, s>>>(p);

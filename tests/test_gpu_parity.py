@@ -177,12 +177,13 @@ def test_dgetrf_blocked_lookahead(lb, nb, la):
         L.lb200_set_getrf_params(512, 0, 1)
 
 
-@pytest.mark.parametrize("cluster_max", [0, 2, 8, 16])
-def test_dgetrf_leaf_kernels_agree(lb, cluster_max):
+@pytest.mark.parametrize("cluster_max,big_leaf", [(0, 0), (0, 1), (2, 0), (2, 1), (8, 1), (16, 1)])
+def test_dgetrf_leaf_kernels_agree(lb, cluster_max, big_leaf):
     """The global-exchange leaf (cluster_max=0) and the thread-block-cluster leaf give the same pivots and factors
     as the reference, including panels that span several CTAs, ties, zero columns and NaN entries."""
     L = lb.lib()
     L.lb200_set_getrf_cluster_max(cluster_max)
+    L.lb200_set_getrf_big_leaf(big_leaf)
     try:
         for (m, n) in ((3000, 40), (2500, 300), (1025, 1025), (5000, 17)):
             a, _ = O.random_matrix(m, n, SEED)
@@ -209,6 +210,7 @@ def test_dgetrf_leaf_kernels_agree(lb, cluster_max):
         assert np.array_equal(np.isnan(got), np.isnan(ref))
     finally:
         L.lb200_set_getrf_cluster_max(16)
+        L.lb200_set_getrf_big_leaf(1)
 
 
 def test_dgetrf_pinned_host_streamed(lb):
