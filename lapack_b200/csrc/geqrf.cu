@@ -276,7 +276,7 @@ __device__ __forceinline__ void warp_reduce16(double (&v)[16], int lane) {
     v[0] += __shfl_xor_sync(full, v[0], 1);
 }
 
-template <int W, int THREADS, int R>
+template <int W, int THREADS, int R, bool CLUSTER>
 __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafParams p) {
     static_assert(W == 16, "warp_reduce16 handles 16 values");
     constexpr int NWARP = THREADS / 32;
@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafPa
         warp_reduce16(red, lane);
         if ((lane & 1) == 0) s_red[warp][lane >> 1] = red[0];
         __syncthreads();
+        if (CLUSTER) {
         if (tid < W) {
             double v = 0.0;
 #pragma unroll
@@ -372,6 +373,45 @@ __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafPa
             } else if (main_step) {
                 s_trow[lane - W] = qcl_ld(top_base + (slot * W + (lane - W)) * 8, 0u);
             }
+        }
+        } else {
+        // no cluster (panels taller than 16 CTAs): partial sums and the top row travel through global memory and one
+        // grid barrier per column, as in geqr2_leaf_kernel; all CTAs must be co-resident
+        if (tid < W) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) v += s_red[w][tid];
+            p.part[((i64)slot * p.G + g) * W + tid] = v;
+        }
+        if (main_step && row0 == c) {
+            double* dst = p.toprow + slot * W;
+#pragma unroll
+            for (int q = 0; q < W; ++q) dst[q] = a[0][q];
+        }
+        qr_grid_barrier(p.bar, p.bar_base + (unsigned)(c + 1) * (unsigned)p.G, p.G);
+        if (warp == 0) {
+            if (lane < W) {
+                double v = 0.0;
+                for (int q = 0; q < p.G; ++q) v += __ldcg(p.part + ((i64)slot * p.G + q) * W + lane);
+                s_tot[lane] = v;
+                const double t0 = __shfl_sync(0x0000ffffu, v, 0);
+                const double alpha = main_step ? __ldcg(p.toprow + slot * W) : 0.0;
+                if (lane == 0 && main_step) {
+                    const double xnorm = sqrt(t0);
+                    double tau = 0.0, beta = alpha, scale = 0.0;
+                    if (xnorm != 0.0) {
+                        beta = -copysign(dev_dlapy2(alpha, xnorm), alpha);
+                        tau = (beta - alpha) / beta;
+                        scale = 1.0 / (alpha - beta);
+                    }
+                    s_hh[0] = tau; s_hh[1] = beta; s_hh[2] = scale;
+                    s_tau[c] = tau;
+                    if (g == 0) p.tau[c] = tau;
+                }
+            } else if (main_step) {
+                s_trow[lane - W] = __ldcg(p.toprow + slot * W + (lane - W));
+            }
+        }
         }
         __syncthreads();
         if (c >= 1 && tid < pc) s_G[tid][pc] = s_tot[live + tid];      // position live+i holds v_i
@@ -450,8 +490,10 @@ __global__ void __launch_bounds__(THREADS, 1) geqr2_leaf_cluster_kernel(QrLeafPa
             }
         }
     }
-    qcl_arrive();
-    qcl_wait();
+    if (CLUSTER) {
+        qcl_arrive();
+        qcl_wait();
+    }
 }
 
 struct QrWs {
@@ -480,7 +522,7 @@ void geqrf_set_cluster_max(int c) { g_qr_cluster_max = c < 0 ? 0 : (c > 16 ? 16 
 static int qr_cluster_hw_max() {
     static int hw_max = 0;
     if (!hw_max) {
-        auto kern = geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R>;
+        auto kern = geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R, true>;
         hw_max = 8;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
             cudaLaunchConfig_t q = {};
@@ -504,12 +546,28 @@ static void geqr2_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, double*
     QrLeafParams p;
     p.m = m; p.n = n; p.A = A; p.lda = lda; p.tau = tau; p.Vc = Vc; p.ldvc = ldvc; p.T = T; p.ldt = ldt;
     p.G = ceil_div(m, QTHREADS);
-    if (p.G > w.maxG || p.G > num_sms()) {
-        fprintf(stderr, "lapack_b200: QR panel of %d rows exceeds the cooperative leaf capacity\n", m);
-        record_cuda_error(cudaErrorInvalidValue);
-        return;
-    }
     p.bar = w.bar; p.bar_base = w.base; p.part = w.part; p.toprow = w.toprow;
+    {
+        // all CTAs of a leaf must be co-resident (grid barrier); taller panels use 8 or 16 rows per thread (slower:
+        // the row window spills to local memory), 256 x 16 x 146 = 598,016 rows is the limit
+        const int cap = min(w.maxG, num_sms() - 2);
+        if (p.G > cap) {
+            int rows_per_cta = 2048;
+            if (ceil_div(m, rows_per_cta) > cap) rows_per_cta = 4096;
+            p.G = ceil_div(m, rows_per_cta);
+            if (p.G > cap) {
+                fprintf(stderr, "lapack_b200: QR panel of %d rows exceeds the cooperative leaf capacity (%d rows)\n", m, cap * 4096);
+                record_cuda_error(cudaErrorInvalidValue);
+                return;
+            }
+            if (rows_per_cta == 2048) geqr2_leaf_cluster_kernel<QW, QCL_THREADS, 8, false><<<p.G, QCL_THREADS, 0, s>>>(p);
+            else geqr2_leaf_cluster_kernel<QW, QCL_THREADS, 16, false><<<p.G, QCL_THREADS, 0, s>>>(p);
+            count_launch();
+            if (p.G > 1) w.base += (unsigned)(min(m, n) + 1) * (unsigned)p.G;
+            LB_CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+    }
     if (p.G <= g_qr_cluster_max && p.G <= qr_cluster_hw_max()) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)p.G);
@@ -519,7 +577,7 @@ static void geqr2_leaf(cudaStream_t s, int m, int n, double* A, i64 lda, double*
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)p.G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R>, p));
+        LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, geqr2_leaf_cluster_kernel<QW, QCL_THREADS, QCL_R, true>, p));
         count_launch();
         return;
     }

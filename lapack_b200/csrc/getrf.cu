@@ -651,16 +651,34 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     p.piv_base = pc.piv_base + off;
     p.sfmin = DBL_MIN;   // DLAMCH('S') (INSTALL/dlamch.f:111-122)
     p.G = ceil_div(m, LEAF_THREADS);
-    if (p.G > w.maxG || p.G > num_sms()) {
-        fprintf(stderr, "lapack_b200: panel of %d rows exceeds the cooperative leaf capacity\n", m);
-        record_cuda_error(cudaErrorInvalidValue);
-        return;
-    }
     p.epoch_base = w.epoch; p.cand = w.cand; p.top = w.top; p.hist = w.hist;
     p.SW = pc.P + off;
     p.sw_left = off;
     p.sw_right = pc.width - off - n;
     const int S = ceil_div(pc.width, LEAF_THREADS);
+    // All work CTAs of a leaf must be co-resident (they spin on each other's packets).  Panels taller than
+    // (#SMs - interchange CTAs) x 1024 rows use 8 or 16 rows per thread -- slower (the row window spills to local
+    // memory) but the same algorithm and results; 256 x 16 x 146 = 598,016 rows is the limit.
+    {
+        const int S4 = (pc.width > n) ? ceil_div(pc.width, CL_THREADS) : 0;
+        const int cap = min(w.maxG, num_sms() - S4 - 2);
+        if (p.G > cap) {
+            int rows_per_cta = 2048;
+            if (ceil_div(m, rows_per_cta) > cap) rows_per_cta = 4096;
+            p.G = ceil_div(m, rows_per_cta);
+            if (p.G > cap) {
+                fprintf(stderr, "lapack_b200: panel of %d rows exceeds the cooperative leaf capacity (%d rows)\n", m, cap * 4096);
+                record_cuda_error(cudaErrorInvalidValue);
+                return;
+            }
+            if (rows_per_cta == 2048) getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, 8, false><<<p.G + S4, CL_THREADS, 0, s>>>(p);
+            else getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, 16, false><<<p.G + S4, CL_THREADS, 0, s>>>(p);
+            count_launch();
+            w.epoch += (unsigned)min(m, n);
+            LB_CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+    }
     if (p.G <= g_cluster_max && p.G <= cluster_hw_max()) {
         // one cluster of G work CTAs (+ clusters of interchange CTAs when the panel is wider than the leaf)
         auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, CL_R, true>;

@@ -246,6 +246,27 @@ def test_dgetrf_pinned_host_streamed(lb):
     assert lb.f77.dgetrf(n, n, h, lda, ipiv) == 5001
 
 
+@pytest.mark.parametrize("m,n", [(200000, 24), (400000, 20)])
+def test_very_tall_panels(lb, m, n):
+    """Panels taller than (#SMs x 1024) rows: the 8- and 16-rows-per-thread leaf kernels (LU and QR)."""
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    ipiv_ref, info_ref = O.dgetrf2(ref)
+    got = a.copy(order="F")
+    ipiv, info = lb.f77.getrf(got)
+    assert info == info_ref == 0
+    assert np.array_equal(ipiv, ipiv_ref)
+    assert rel(got, ref) < 1e-10
+    qr_ref = a.copy(order="F")
+    tau_ref, _, _ = O.dgeqrf(qr_ref)
+    qr = a.copy(order="F")
+    tau, info, _ = lb.f77.geqrf(qr)
+    assert info == 0
+    assert rel(tau, tau_ref) < 1e-10
+    assert rel(np.triu(qr[:n, :]), np.triu(qr_ref[:n, :])) < 1e-10
+    assert rel(qr, qr_ref) < 1e-9
+
+
 def test_dgetrf_singular_info(lb):
     """TESTING/LIN/dchkge.f:328-347: zero a column -> INFO = that column, factorization completes."""
     n = 120
