@@ -425,24 +425,53 @@ void dgesv_(const int* n, const int* nrhs, double* A, const int* lda, int* ipiv,
 // Host-resident Cholesky with transfer/compute overlap: only the UPLO triangle crosses PCIe (block-column
 // trapezoids), and every finished block column of the factor is downloaded on a copy stream while the rest of
 // the factorization is still running (lb::StreamOut).  Needs pinned host memory for truly asynchronous copies.
-// upload only the UPLO triangle of a host matrix, as block-column trapezoids
-static void upload_triangle(cudaStream_t s, bool upper, int n, const double* A, int lda, double* dA, lb::i64 ldd, int cb) {
-    for (int j0 = 0; j0 < n; j0 += cb) {
-        const int w = imin(cb, n - j0);
-        const int r0 = upper ? 0 : j0, r1 = upper ? j0 + w : n;
+// upload the UPLO triangle of columns [c0, c1) of a host matrix as block-column trapezoids; rows are clipped to
+// [rlo, rhi) (used to send the top block row / the trailing block separately)
+static void upload_triangle(cudaStream_t s, bool upper, int n, const double* A, int lda, double* dA, lb::i64 ldd, int cb,
+                            int c0, int c1, int rlo, int rhi) {
+    for (int j0 = c0; j0 < c1; j0 += cb) {
+        const int w = imin(cb, c1 - j0);
+        int r0 = upper ? 0 : j0, r1 = upper ? j0 + w : n;
+        if (r0 < rlo) r0 = rlo;
+        if (r1 > rhi) r1 = rhi;
+        if (r1 <= r0) continue;
         LB_CUDA_CHECK(cudaMemcpy2DAsync(dA + r0 + (lb::i64)j0 * ldd, ldd * 8, A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8,
                                         (size_t)(r1 - r0) * 8, w, cudaMemcpyHostToDevice, s));
     }
 }
 
-// DPOTRF, or DPOSV when nrhs > 0 (factor, then solve only if INFO = 0, dposv.f:176-183)
+// one streamed factorization of the nn x nn diagonal block at (o, o): lb::potrf with the StreamOut hook, then whatever
+// the hook did not send (small blocks), in upload-shaped trapezoids
+static void potrf_streamed_block(cudaStream_t s, cudaStream_t copy_stream, cudaEvent_t ev, bool upper, int nn, int o, double* A,
+                                 int lda, double* dA, lb::i64 ldd, int* dinfo, int cb) {
+    lb::StreamOut so;
+    so.host = A + o + (lb::i64)o * lda; so.ldh = lda; so.copy_stream = copy_stream; so.ev = ev; so.done_cols = 0;
+    lb::stream_out() = &so;
+    lb::potrf(s, upper ? 'U' : 'L', nn, dA + o + (lb::i64)o * ldd, ldd, dinfo);
+    lb::stream_out() = nullptr;
+    for (int j0 = so.done_cols; j0 < nn; j0 += cb) {
+        const int w = imin(cb, nn - j0);
+        const int r0 = upper ? so.done_cols : j0, r1 = upper ? j0 + w : nn;
+        LB_CUDA_CHECK(cudaMemcpy2DAsync(A + (o + r0) + (lb::i64)(o + j0) * lda, (size_t)lda * 8,
+                                        dA + (o + r0) + (lb::i64)(o + j0) * ldd, ldd * 8, (size_t)(r1 - r0) * 8, w,
+                                        cudaMemcpyDeviceToHost, s));
+    }
+}
+
+// DPOTRF, or DPOSV when nrhs > 0 (factor, then solve only if INFO = 0, dposv.f:176-183), for a pinned host matrix.
+// Only the UPLO triangle crosses PCIe.  n >= 8192: one level of the DPOTRF2 recursion (dpotrf2.f:181-228) at the top --
+// the leading n1 block columns (rows, for 'U') are uploaded first and factored / solved while the trailing block is
+// still in flight; then ONE large-K DSYRK and the factorization of the trailing block.  Every finished block column
+// of the factor is downloaded while the rest is still being computed (lb::StreamOut).
 static int potrf_host_streamed(bool upper, int n, double* A, int lda, int nrhs = 0, double* B = nullptr, int ldb = 0) {
-    static cudaStream_t copy_stream = nullptr;
-    static cudaEvent_t ev = nullptr, ev_up = nullptr;
+    static cudaStream_t copy_stream = nullptr, up_stream = nullptr;
+    static cudaEvent_t ev = nullptr, ev_up = nullptr, ev_x = nullptr;
     if (!copy_stream) {
         LB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        LB_CUDA_CHECK(cudaStreamCreateWithFlags(&up_stream, cudaStreamNonBlocking));
         LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+        LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_x, cudaEventDisableTiming));
     }
     cudaStream_t s = host_stream();
     const lb::i64 ldd = ((lb::i64)n + 1) & ~1LL;
@@ -450,32 +479,65 @@ static int potrf_host_streamed(bool upper, int n, double* A, int lda, int nrhs =
     double* dB = nrhs > 0 ? (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * nrhs) : nullptr;
     int* dinfo = (int*)lb::ws_alloc(s, 64);
     const int cb = 2048;
-    upload_triangle(s, upper, n, A, lda, dA, ldd, cb);
-    if (nrhs > 0)
-        LB_CUDA_CHECK(cudaMemcpy2DAsync(dB, ldd * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, s));
-    lb::StreamOut so;
-    so.host = A; so.ldh = lda; so.copy_stream = copy_stream; so.ev = ev; so.done_cols = 0;
-    lb::stream_out() = &so;
-    lb::potrf(s, upper ? 'U' : 'L', n, dA, ldd, dinfo);
-    lb::stream_out() = nullptr;
-    // whatever the factorization did not stream out itself, in the same trapezoids as the upload (the squares on
-    // the diagonal hold the caller's own data in the other triangle, so copying them back changes nothing)
-    for (int j0 = so.done_cols; j0 < n; j0 += cb) {
-        const int w = imin(cb, n - j0);
-        const int r0 = upper ? so.done_cols : j0, r1 = upper ? j0 + w : n;
-        LB_CUDA_CHECK(cudaMemcpy2DAsync(A + r0 + (lb::i64)j0 * lda, (size_t)lda * 8, dA + r0 + (lb::i64)j0 * ldd, ldd * 8,
-                                        (size_t)(r1 - r0) * 8, w, cudaMemcpyDeviceToHost, s));
+    const char ul = upper ? 'U' : 'L';
+    int n1 = n;
+    if (n >= 8192) n1 = imin(n - cb, ((n / 4 + cb - 1) / cb) * cb);
+    const int n2 = n - n1;
+    if (n2 == 0) {
+        upload_triangle(s, upper, n, A, lda, dA, ldd, cb, 0, n, 0, n);
+        if (nrhs > 0)
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(dB, ldd * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, s));
+        potrf_streamed_block(s, copy_stream, ev, upper, n, 0, A, lda, dA, ldd, dinfo, cb);
+    } else {
+        // the scratch must exist before the upload stream touches it
+        LB_CUDA_CHECK(cudaEventRecord(ev_x, s));
+        LB_CUDA_CHECK(cudaStreamWaitEvent(up_stream, ev_x, 0));
+        if (!upper) {
+            upload_triangle(s, false, n, A, lda, dA, ldd, cb, 0, n1, 0, n);                 // block columns 0..n1 (L11, A21)
+            upload_triangle(up_stream, false, n, A, lda, dA, ldd, cb, n1, n, 0, n);         // A22
+        } else {
+            upload_triangle(s, true, n, A, lda, dA, ldd, cb, 0, n, 0, n1);                  // rows 0..n1 (U11, A12)
+            upload_triangle(up_stream, true, n, A, lda, dA, ldd, cb, n1, n, n1, n);         // A22
+        }
+        if (nrhs > 0)
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(dB, ldd * 8, B, (size_t)ldb * 8, (size_t)n * 8, nrhs, cudaMemcpyHostToDevice, up_stream));
+        LB_CUDA_CHECK(cudaEventRecord(ev_up, up_stream));
+        potrf_streamed_block(s, copy_stream, ev, upper, n1, 0, A, lda, dA, ldd, dinfo, cb);                 // dpotrf2.f:185
+        double* dA22 = dA + n1 + (lb::i64)n1 * ldd;
+        if (!upper) {
+            double* dA21 = dA + n1;
+            lb::trsm(s, 'R', 'L', 'T', 'N', n2, n1, 1.0, dA, ldd, dA21, ldd);                               // dpotrf2.f:217
+            LB_CUDA_CHECK(cudaEventRecord(ev_x, s));
+            LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_x, 0));
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(A + n1, (size_t)lda * 8, dA21, ldd * 8, (size_t)n2 * 8, n1, cudaMemcpyDeviceToHost,
+                                            copy_stream));                                                 // L21 is final
+            LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
+            lb::syrk(s, 'L', 'N', n2, n1, -1.0, dA21, ldd, 1.0, dA22, ldd);                                 // dpotrf2.f:222
+        } else {
+            double* dA12 = dA + (lb::i64)n1 * ldd;
+            lb::trsm(s, 'L', 'U', 'T', 'N', n1, n2, 1.0, dA, ldd, dA12, ldd);                               // dpotrf2.f:201
+            LB_CUDA_CHECK(cudaEventRecord(ev_x, s));
+            LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_x, 0));
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(A + (lb::i64)n1 * lda, (size_t)lda * 8, dA12, ldd * 8, (size_t)n1 * 8, n2,
+                                            cudaMemcpyDeviceToHost, copy_stream));                         // U12 is final
+            LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
+            lb::syrk(s, 'U', 'T', n2, n1, -1.0, dA12, ldd, 1.0, dA22, ldd);                                 // dpotrf2.f:206
+        }
+        potrf_streamed_block(s, copy_stream, ev, upper, n2, n1, A, lda, dA, ldd, dinfo + 8, cb);            // dpotrf2.f:227
+        lb::info_max_offset(s, dinfo, dinfo + 8, n1);                                                       // dpotrf2.f:228-231
     }
     int hinfo = 0;
     LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (nrhs > 0) {
         LB_CUDA_CHECK(cudaStreamSynchronize(s));               // INFO decides whether the solve happens
         if (hinfo == 0 && lb::last_cuda_error() == 0) {
-            lb::potrs(s, upper ? 'U' : 'L', n, nrhs, dA, ldd, dB, ldd);
+            LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
+            lb::potrs(s, ul, n, nrhs, dA, ldd, dB, ldd);
             LB_CUDA_CHECK(cudaMemcpy2DAsync(B, (size_t)ldb * 8, dB, ldd * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, s));
         }
     }
     LB_CUDA_CHECK(cudaStreamSynchronize(copy_stream));
+    LB_CUDA_CHECK(cudaStreamSynchronize(up_stream));
     lb::ws_free(s, dA);
     if (dB) lb::ws_free(s, dB);
     lb::ws_free(s, dinfo);

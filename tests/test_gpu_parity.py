@@ -408,6 +408,48 @@ def test_dpotrf_pinned_host_streamed(lb, uplo):
     assert np.array_equal(b2, b_ref)
 
 
+@pytest.mark.parametrize("uplo", "LU")
+def test_dpotrf_pinned_host_split_upload(lb, uplo):
+    """Pinned host caller, n >= 8192: leading block factored while the trailing block is still uploading (one level of
+    the DPOTRF2 recursion), streamed download; compared with the device-resident factorization."""
+    n, lda = 8300, 8304
+    dev = torch.device("cuda")
+    s_dev = lb.dev.larnv_matrix(n, n, SEED)
+    lb.dev.make_spd(s_dev, float(n))
+    s = dev_to_np(s_dev)
+    buf = torch.empty((n, lda), dtype=torch.float64).pin_memory()
+    h = buf.numpy().T
+    mask = np.triu(np.ones((n, n), bool), 1) if uplo == "L" else np.tril(np.ones((n, n), bool), -1)
+    h[:] = 7.0
+    h[:n, :] = s
+    h[:n, :][mask] = -1.0e10
+    assert lb.f77.dpotrf(uplo, n, h, lda) == 0
+    got = np.asfortranarray(h[:n, :])
+    assert np.all(got[mask] == -1.0e10) and np.all(h[n:, :] == 7.0)
+    ref_dev = s_dev.clone()
+    assert int(lb.dev.potrf(uplo, ref_dev).item()) == 0
+    ref = dev_to_np(ref_dev)
+    tri = np.tril if uplo == "L" else np.triu
+    assert rel(tri(got), tri(ref)) < 1e-11
+    f = torch.from_numpy(tri(got)).to(dev)
+    prod = f @ f.T if uplo == "L" else f.T @ f
+    resid = float((prod - s_dev).abs().sum(dim=0).max()) / (n * float(s_dev.abs().sum(dim=0).max()) * EPS)
+    assert resid < O.THRESH
+    # failure inside the trailing block: INFO is shifted by the size of the leading block (dpotrf2.f:228-231)
+    h[:n, :] = s
+    h[5000, 5000] = -3.0
+    assert lb.f77.dpotrf(uplo, n, h, lda) == 5001
+    h[:n, :] = s
+    h[100, 100] = -3.0
+    assert lb.f77.dpotrf(uplo, n, h, lda) == 101
+    # DPOSV through the same path
+    h[:n, :] = s
+    x_true, _ = O.random_matrix(n, 2, (7, 8, 9, 11))
+    b = np.asfortranarray(s @ x_true)
+    assert lb.f77.dposv(uplo, n, 2, h, lda, b, n) == 0
+    assert rel(b, x_true) < 1e-10
+
+
 def test_dpotrf_not_positive_definite(lb):
     """TESTING/LIN/dchkpo.f:313-344: zero row+column IZERO -> INFO = IZERO."""
     n = 150
