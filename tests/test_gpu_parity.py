@@ -688,3 +688,40 @@ def test_device_api_getrf_getrs(lb):
     b0 = dev_to_np(b)
     lb.dev.getrs("N", a, ipiv, b)
     assert O.dget02("N", want, dev_to_np(b), b0) < O.THRESH
+
+
+def test_fortran_abi_from_several_host_threads(lb):
+    """SURVEY 8b 'Threading': the replacement must be callable from multiple host threads and synchronous on return.
+    ctypes releases the GIL during the call, so these calls really overlap; the library serialises them."""
+    import threading
+    n = 700
+    mats = [O.random_matrix(n, n, (11 + 2 * t, 3, 5, 7))[0] for t in range(6)]
+    refs = []
+    for a in mats:
+        r = a.copy(order="F")
+        refs.append((r, O.dgetrf(r)[0]))
+    out = [None] * len(mats)
+
+    def work(t):
+        got = mats[t].copy(order="F")
+        if t % 2 == 0:
+            ipiv, info = lb.f77.getrf(got)
+            out[t] = (got, ipiv, info)
+        else:
+            s = np.asfortranarray(mats[t] @ mats[t].T + n * np.eye(n))
+            f = s.copy(order="F")
+            info = lb.f77.potrf("L", f)
+            out[t] = (s, f, info)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(len(mats))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    for t in range(len(mats)):
+        if t % 2 == 0:
+            got, ipiv, info = out[t]
+            assert info == 0 and np.array_equal(ipiv, refs[t][1]) and rel(got, refs[t][0]) < 1e-10
+        else:
+            s, f, info = out[t]
+            assert info == 0 and O.dpot01("L", s, f) < O.THRESH
