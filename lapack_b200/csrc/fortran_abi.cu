@@ -260,12 +260,14 @@ void dtrmm_(const char* side, const char* uplo, const char* transa, const char* 
 // Host-resident square DGETRF with transfer/compute overlap: one level of the DGETRF2 recursion (dgetrf2.f:216-263)
 // at the top.  The left n1 columns are uploaded first and factored (blocked DGETRF) while the right n - n1 columns
 // are still crossing PCIe; then A12/A22 get the accumulated interchanges, the triangular solve and ONE large-K GEMM,
-// A22 is factored, and its interchanges go back to the left columns.  U12 is downloaded while A22 is factored.
+// A22 is factored, and its interchanges go back to the left columns.  Everything that is final early (L11/U11, U12,
+// the block rows of U inside A22) is downloaded while the factorization continues.
 static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
-    static cudaStream_t copy_stream = nullptr;
+    static cudaStream_t copy_stream = nullptr, up_stream = nullptr;
     static cudaEvent_t ev_up = nullptr, ev_u12 = nullptr;
     if (!copy_stream) {
         LB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        LB_CUDA_CHECK(cudaStreamCreateWithFlags(&up_stream, cudaStreamNonBlocking));
         LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
         LB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_u12, cudaEventDisableTiming));
     }
@@ -274,17 +276,23 @@ static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
     double* dA = (double*)lb::ws_alloc(s, sizeof(double) * (size_t)ldd * n);
     int* dp = (int*)lb::ws_alloc(s, sizeof(int) * (size_t)n);
     int* dinfo = (int*)lb::ws_alloc(s, 64);          // dinfo[0] = left part / result, dinfo[8] = A22
-    const int n1 = imin(n - 512, ((n / 4 + 511) / 512) * 512), n2 = n - n1;
+    // split so that factoring the left part takes about as long as uploading the right part (measured: 3n/8)
+    const int n1 = imin(n - 512, (int)((((lb::i64)n * 3 / 8) + 511) / 512) * 512), n2 = n - n1;
     double* dA12 = dA + (lb::i64)n1 * ldd;
     double* dA22 = dA12 + n1;
     // make sure the scratch exists before the copy stream touches it
     LB_CUDA_CHECK(cudaEventRecord(ev_up, s));
+    LB_CUDA_CHECK(cudaStreamWaitEvent(up_stream, ev_up, 0));
     LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_up, 0));
     LB_CUDA_CHECK(cudaMemcpy2DAsync(dA, ldd * 8, A, (size_t)lda * 8, (size_t)n * 8, n1, cudaMemcpyHostToDevice, s));
     LB_CUDA_CHECK(cudaMemcpy2DAsync(dA12, ldd * 8, A + (lb::i64)n1 * lda, (size_t)lda * 8, (size_t)n * 8, n2,
-                                    cudaMemcpyHostToDevice, copy_stream));
-    LB_CUDA_CHECK(cudaEventRecord(ev_up, copy_stream));
+                                    cudaMemcpyHostToDevice, up_stream));
+    LB_CUDA_CHECK(cudaEventRecord(ev_up, up_stream));
     lb::getrf(s, n, n1, dA, ldd, dp, dinfo);                                            // dgetrf2.f:231
+    // rows 0..n1 of the left part (L11 and U11) are final: later interchanges only touch rows >= n1
+    LB_CUDA_CHECK(cudaEventRecord(ev_u12, s));
+    LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, ldd * 8, (size_t)n1 * 8, n1, cudaMemcpyDeviceToHost, copy_stream));
     LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
     lb::laswp(s, n2, dA12, ldd, 1, n1, dp, 1);                                          // dgetrf2.f:236
     lb::trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, dA, ldd, dA12, ldd);                   // dgetrf2.f:240
@@ -293,15 +301,32 @@ static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
     LB_CUDA_CHECK(cudaMemcpy2DAsync(A + (lb::i64)n1 * lda, (size_t)lda * 8, dA12, ldd * 8, (size_t)n1 * 8, n2,
                                     cudaMemcpyDeviceToHost, copy_stream));              // U12 is final
     lb::gemm(s, 'N', 'N', n2, n2, n1, -1.0, dA + n1, ldd, dA12, ldd, 1.0, dA22, ldd);   // dgetrf2.f:245
+    // A22: the blocked driver streams every finished block row of U itself (lb::StreamOut)
+    lb::StreamOut so;
+    so.host = A + n1 + (lb::i64)n1 * lda; so.ldh = lda; so.copy_stream = copy_stream; so.ev = ev_u12; so.done_cols = 0;
+    lb::stream_out() = &so;
     lb::getrf(s, n2, n2, dA22, ldd, dp + n1, dinfo + 8);                                // dgetrf2.f:250
-    LB_CUDA_CHECK(cudaEventRecord(ev_u12, s));                                          // A22 is final
-    LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
+    lb::stream_out() = nullptr;
     lb::info_max_offset(s, dinfo, dinfo + 8, n1);                                       // dgetrf2.f:251-252
     lb::iadd(s, n2, dp + n1, n1);                                                       // dgetrf2.f:257-259
     lb::laswp(s, n1, dA, ldd, n1 + 1, n, dp, 1);                                        // dgetrf2.f:263
-    LB_CUDA_CHECK(cudaMemcpy2DAsync(A + n1 + (lb::i64)n1 * lda, (size_t)lda * 8, dA22, ldd * 8, (size_t)n2 * 8, n2,
-                                    cudaMemcpyDeviceToHost, copy_stream));
-    LB_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, ldd * 8, (size_t)n * 8, n1, cudaMemcpyDeviceToHost, s));
+    // what is left of A22: the block lower trapezoids (L and the diagonal blocks), or everything if nothing was streamed
+    {
+        const int nb = lb::getrf_block();
+        if (so.done_cols == 0) {
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(A + n1 + (lb::i64)n1 * lda, (size_t)lda * 8, dA22, ldd * 8, (size_t)n2 * 8, n2,
+                                            cudaMemcpyDeviceToHost, s));
+        } else {
+            for (int j0 = 0; j0 < n2; j0 += nb) {
+                const int w = imin(nb, n2 - j0);
+                LB_CUDA_CHECK(cudaMemcpy2DAsync(A + (n1 + j0) + (lb::i64)(n1 + j0) * lda, (size_t)lda * 8,
+                                                dA22 + j0 + (lb::i64)j0 * ldd, ldd * 8, (size_t)(n2 - j0) * 8, w,
+                                                cudaMemcpyDeviceToHost, s));
+            }
+        }
+    }
+    // rows n1..n of the left part (L21 after the interchanges of A22)
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(A + n1, (size_t)lda * 8, dA + n1, ldd * 8, (size_t)n2 * 8, n1, cudaMemcpyDeviceToHost, s));
     LB_CUDA_CHECK(cudaMemcpyAsync(ipiv, dp, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
     int hinfo = 0;
     LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));

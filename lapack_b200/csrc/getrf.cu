@@ -32,6 +32,7 @@ void laswp_plan_free(cudaStream_t s, void* plan);
 
 static int g_nb = 512, g_lookahead = 1;
 static int g_cluster_max = 16;      // panels of up to this many 1024-row CTAs use the cluster leaf (0 = never)
+int getrf_block() { return min(g_nb, 2048); }
 void getrf_set_cluster_max(int c) { g_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
 static int g_big_leaf_rows4 = 1;    // panels too tall for a cluster: 1 = 256 threads x 4 rows kernel, 0 = 1024 x 1 row kernel
 void getrf_set_big_leaf(int v) { g_big_leaf_rows4 = v ? 1 : 0; }
@@ -796,6 +797,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
 
     const bool la = g_lookahead != 0;
     Aux& ax = aux();
+    StreamOut* so = stream_out();
     // Streams (look-ahead on): sp = panel (highest priority), sq = memory-bound preparation of the trailing
     // columns (interchanges + U12 solve, medium priority), su = trailing GEMMs (low priority), sl = interchanges
     // left of the panel (low priority, off the critical path).  The trailing columns are processed in four
@@ -874,6 +876,14 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         }
         if (nchunk <= 1 && la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));   // keep sq ordered after update j-1
         if (la) LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
+        if (so && la && jn < n) {
+            // block row j of U (rows j..jn, columns jn..n) is final once every chunk has been prepared: start its
+            // download now (host-resident callers, lb::StreamOut)
+            LB_CUDA_CHECK(cudaStreamWaitEvent(so->copy_stream, ev_plan, 0));
+            LB_CUDA_CHECK(cudaMemcpy2DAsync(so->host + j + (i64)jn * so->ldh, so->ldh * 8, A + j + (i64)jn * lda, lda * 8,
+                                            (size_t)jb * 8, n - jn, cudaMemcpyDeviceToHost, so->copy_stream));
+            so->done_cols = jn;
+        }
         // GEMMs on su; the next panel is factored right after the first chunk
         for (int q = 0; q < nchunk; ++q) {
             const int w = c[q + 1] - c[q];

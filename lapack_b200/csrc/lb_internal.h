@@ -88,9 +88,11 @@ struct StreamOut {
     i64 ldh = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev = nullptr;
-    int done_cols = 0;           // columns [0, done_cols) (or rows for UPLO='U') have been queued for download
+    int done_cols = 0;           // potrf: columns [0, done_cols) (rows for UPLO='U') have been queued for download;
+                                 // getrf: block rows [0, done_cols) of U (right of their diagonal blocks)
 };
 StreamOut*& stream_out();         // nullptr when no streaming download is requested
+int getrf_block();                // outer block size of getrf (host path: which U block rows were streamed)
 int potrf_block();                // outer block size of potrf (streamed host path needs it to divide its upload chunk)
 
 // launch counter (bench.py's gpu_launches claim)

@@ -10,6 +10,7 @@
 // held in shared memory (broadcast reads) and the right-hand side held in registers; divisions by the
 // diagonal are kept as divisions like the reference (dtrsm.f:282,294,...).
 #include "lb_internal.h"
+#include <cfloat>
 
 namespace lb {
 
@@ -254,6 +255,245 @@ static void trsm_right_rec(cudaStream_t s, bool upper, bool trans, bool unit, in
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Few right-hand sides (DGETRS / DPOTRS with NRHS <= 8): the solve is memory-bound (the triangle is read once, 8n^2
+// bytes) and latency-bound along the diagonal; the generic recursion would issue thousands of tiny launches and run
+// its off-diagonal updates as 64-column GEMM tiles with one useful column.  Here
+//   * the recursion stops at FR_LEAF = 128 rows; a leaf is ONE CTA that first pulls its whole diagonal block and its
+//     right-hand sides into shared memory (all loads in flight at once), then walks the block in 32-row steps: warp 0
+//     substitutes inside the 32 x 32 sub-block (lane = row, right-hand sides in registers), the other warps update
+//     the rest of the leaf;
+//   * the off-diagonal updates are streaming GEMV kernels (coalesced, all SMs, fixed summation order).
+constexpr int FR_LEAF = 128, FR_MAXRHS = 8;
+
+template <bool eff_lower>     // (L,N) / (U,T): forward substitution; otherwise backward
+__global__ void __launch_bounds__(256) trsm_left_fewrhs_kernel(int m, int nrhs, const double* __restrict__ A, i64 lda,
+                                                               bool trans, bool unit, double* __restrict__ B, i64 ldb) {
+    extern __shared__ double fr_smem[];
+    double (*S)[FR_LEAF + 1] = reinterpret_cast<double (*)[FR_LEAF + 1]>(fr_smem);          // S[i][j] = T(i,j), T = op(A)
+    double (*bs)[FR_MAXRHS] = reinterpret_cast<double (*)[FR_MAXRHS]>(fr_smem + FR_LEAF * (FR_LEAF + 1));
+    double* rinv = fr_smem + FR_LEAF * (FR_LEAF + 1) + FR_LEAF * FR_MAXRHS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- one shot: the m x m block and the right-hand sides
+    {
+        // thread = (row of A, column parity): every warp-level load is 32 consecutive rows of one column of A; sixteen
+        // loads are in flight per thread before the first store
+        const int ar = tid & (FR_LEAF - 1), ac0 = tid >> 7;
+        if (ar < m) {
+            const double* src = A + ar;
+#pragma unroll 1
+            for (int c0 = ac0; c0 < m; c0 += 32) {
+                double v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = (c0 + 2 * u < m) ? __ldg(src + (i64)(c0 + 2 * u) * lda) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int ac = c0 + 2 * u;
+                    if (ac < m) { if (!trans) S[ar][ac] = v[u]; else S[ac][ar] = v[u]; }      // T(i,j) = A(j,i)
+                }
+            }
+        }
+        for (int idx = tid; idx < FR_LEAF * FR_MAXRHS; idx += 256) {
+            const int i = idx & (FR_LEAF - 1), r = idx >> 7;
+            if (i < m && r < nrhs) bs[i][r] = B[i + (i64)r * ldb];
+        }
+    }
+    __syncthreads();
+    if (tid < m) rinv[tid] = 1.0 / S[tid][tid];
+    __syncthreads();
+    const int nsb = (m + 31) / 32;
+    for (int sidx = 0; sidx < nsb; ++sidx) {
+        const int sb = eff_lower ? sidx : nsb - 1 - sidx;
+        const int r0 = sb * 32;
+        const int rows = min(32, m - r0);
+        if (warp == 0) {
+            double x[FR_MAXRHS];
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r) x[r] = (r < nrhs && lane < rows) ? bs[r0 + lane][r] : 0.0;
+            const int li = min(lane, rows - 1);
+#pragma unroll 4
+            for (int jj = 0; jj < rows; ++jj) {
+                const int j = eff_lower ? jj : rows - 1 - jj;
+                const double tij = S[r0 + li][r0 + j];
+                const double d = S[r0 + j][r0 + j], ri = rinv[r0 + j];
+                const bool use_rcp = fabs(d) >= DBL_MIN;
+                const bool below = eff_lower ? (lane > j) : (lane < j);
+#pragma unroll
+                for (int r = 0; r < FR_MAXRHS; ++r) {
+                    if (r < nrhs) {
+                        double xj = __shfl_sync(0xffffffffu, x[r], j);
+                        // dtrsm.f: B(k,j) = B(k,j)/A(k,k).  The n divisions of a solve form one dependent chain, so the
+                        // reciprocal (computed off the chain) is used unless it could overflow -- DGETRF2's own rule
+                        // (dgetrf2.f:204-210); at most one extra rounding per entry
+                        if (!unit) xj = use_rcp ? xj * ri : xj / d;
+                        if (lane == j) x[r] = xj;
+                        else if (below) x[r] = x[r] - xj * tij;       // dtrsm.f: B(i,j) = B(i,j) - B(k,j)*A(i,k)
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r)
+                if (r < nrhs && lane < rows) bs[r0 + lane][r] = x[r];
+        }
+        __syncthreads();
+        // rest of the leaf: rows after (forward) or before (backward) the sub-block
+        const int lo = eff_lower ? r0 + rows : 0, hi = eff_lower ? m : r0;
+        const int i = lo + tid - 32;
+        if (warp != 0 && i < hi) {
+            double acc[FR_MAXRHS];
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r) acc[r] = 0.0;
+            for (int j = 0; j < rows; ++j) {
+                const double t = S[i][r0 + j];
+#pragma unroll
+                for (int r = 0; r < FR_MAXRHS; ++r)
+                    if (r < nrhs) acc[r] = fma(t, bs[r0 + j][r], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r)
+                if (r < nrhs) bs[i][r] -= acc[r];
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < FR_LEAF * FR_MAXRHS; idx += 256) {
+        const int i = idx & (FR_LEAF - 1), r = idx >> 7;
+        if (i < m && r < nrhs) B[i + (i64)r * ldb] = bs[i][r];
+    }
+}
+
+// C(m x nr) -= A(m x k) X(k x nr), A column-major: a CTA owns 32 rows, its 8 warps take the columns k0, k0+8, ... (every
+// warp-level load is 32 consecutive rows of one column), partial sums are combined in warp order.
+__global__ void __launch_bounds__(256) gemv_n_fewrhs_kernel(int m, int k, int nr, const double* __restrict__ A, i64 lda,
+                                                            const double* __restrict__ X, i64 ldx, double* __restrict__ C, i64 ldc) {
+    __shared__ double part[8][32][FR_MAXRHS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    double acc[FR_MAXRHS];
+#pragma unroll
+    for (int r = 0; r < FR_MAXRHS; ++r) acc[r] = 0.0;
+    if (i < m) {
+        const double* a = A + i;
+        int j = warp;
+        for (; j + 56 < k; j += 64) {                 // 8 loads in flight per thread
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(a + (i64)(j + 8 * u) * lda);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int r = 0; r < FR_MAXRHS; ++r)
+                    if (r < nr) acc[r] = fma(v[u], __ldg(X + (j + 8 * u) + (i64)r * ldx), acc[r]);
+            }
+        }
+        for (; j < k; j += 8) {
+            const double v = __ldcs(a + (i64)j * lda);
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r)
+                if (r < nr) acc[r] = fma(v, __ldg(X + j + (i64)r * ldx), acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < FR_MAXRHS; ++r) part[warp][lane][r] = acc[r];
+    __syncthreads();
+    if (warp == 0 && i < m) {
+#pragma unroll
+        for (int r = 0; r < FR_MAXRHS; ++r) {
+            if (r < nr) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += part[w][lane][r];
+                C[i + (i64)r * ldc] -= t;
+            }
+        }
+    }
+}
+
+// C(m x nr) -= A^T X with A stored k x m (column i of A is contiguous): one warp per output row, lanes stride the
+// column, fixed-order shuffle reduction.
+__global__ void __launch_bounds__(256) gemv_t_fewrhs_kernel(int m, int k, int nr, const double* __restrict__ A, i64 lda,
+                                                            const double* __restrict__ X, i64 ldx, double* __restrict__ C, i64 ldc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= m) return;
+    const double* a = A + (i64)i * lda;
+    double acc[FR_MAXRHS];
+#pragma unroll
+    for (int r = 0; r < FR_MAXRHS; ++r) acc[r] = 0.0;
+    int j = lane;
+    for (; j + 96 < k; j += 128) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(a + j + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int r = 0; r < FR_MAXRHS; ++r)
+                if (r < nr) acc[r] = fma(v[u], __ldg(X + (j + 32 * u) + (i64)r * ldx), acc[r]);
+        }
+    }
+    for (; j < k; j += 32) {
+        const double v = __ldcs(a + j);
+#pragma unroll
+        for (int r = 0; r < FR_MAXRHS; ++r)
+            if (r < nr) acc[r] = fma(v, __ldg(X + j + (i64)r * ldx), acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < FR_MAXRHS; ++r) {
+        if (r < nr) {
+            double t = acc[r];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+            if (lane == 0) C[i + (i64)r * ldc] -= t;
+        }
+    }
+}
+
+static void gemv_fewrhs(cudaStream_t s, bool a_trans, int m, int k, int nr, const double* A, i64 lda, const double* X, i64 ldx,
+                        double* C, i64 ldc) {
+    if (m <= 0 || k <= 0) return;
+    if (!a_trans) gemv_n_fewrhs_kernel<<<ceil_div(m, 32), 256, 0, s>>>(m, k, nr, A, lda, X, ldx, C, ldc);
+    else gemv_t_fewrhs_kernel<<<ceil_div(m, 8), 256, 0, s>>>(m, k, nr, A, lda, X, ldx, C, ldc);
+    count_launch();
+}
+
+static void trsm_left_fewrhs_rec(cudaStream_t s, bool upper, bool trans, bool unit, int m, int n, const double* A, i64 lda,
+                                 double* B, i64 ldb) {
+    const bool eff_lower = (upper == trans);
+    if (m <= FR_LEAF) {
+        const size_t smem = sizeof(double) * (FR_LEAF * (FR_LEAF + 1) + FR_LEAF * FR_MAXRHS + FR_LEAF);
+        static bool attr = false;
+        if (!attr) {
+            LB_CUDA_CHECK(cudaFuncSetAttribute(trsm_left_fewrhs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            LB_CUDA_CHECK(cudaFuncSetAttribute(trsm_left_fewrhs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        if (eff_lower) trsm_left_fewrhs_kernel<true><<<1, 256, smem, s>>>(m, n, A, lda, trans, unit, B, ldb);
+        else trsm_left_fewrhs_kernel<false><<<1, 256, smem, s>>>(m, n, A, lda, trans, unit, B, ldb);
+        count_launch();
+        return;
+    }
+    int m1 = FR_LEAF;
+    while (m1 * 2 < m) m1 *= 2;
+    const int m2 = m - m1;
+    const double* A11 = A;
+    const double* A22 = A + m1 + (i64)m1 * lda;
+    const double* A21 = A + m1;                    // stored m2 x m1
+    const double* A12 = A + (i64)m1 * lda;         // stored m1 x m2
+    double* B1 = B;
+    double* B2 = B + m1;
+    if (eff_lower) {
+        trsm_left_fewrhs_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb);
+        if (!trans) gemv_fewrhs(s, false, m2, m1, n, A21, lda, B1, ldb, B2, ldb);       // B2 -= A21 B1
+        else gemv_fewrhs(s, true, m2, m1, n, A12, lda, B1, ldb, B2, ldb);               // B2 -= A12^T B1
+        trsm_left_fewrhs_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb);
+    } else {
+        trsm_left_fewrhs_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb);
+        if (!trans) gemv_fewrhs(s, false, m1, m2, n, A12, lda, B2, ldb, B1, ldb);       // B1 -= A12 B2
+        else gemv_fewrhs(s, true, m1, m2, n, A21, lda, B2, ldb, B1, ldb);               // B1 -= A21^T B2
+        trsm_left_fewrhs_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb);
+    }
+}
+
 void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, double alpha, const double* A,
           i64 lda, double* B, i64 ldb) {
     if (m <= 0 || n <= 0) return;
@@ -266,6 +506,8 @@ void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, in
         // latency-critical in-panel solve: one fused kernel instead of the recursion
         trsm_left_lower_small_kernel<<<ceil_div(n, TS_COLS), 256, 0, s>>>(m, n, A, lda, unit, B, ldb);
         count_launch();
+    } else if (left && n <= FR_MAXRHS && m > FR_LEAF) {
+        trsm_left_fewrhs_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     } else if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     else trsm_right_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     LB_CUDA_CHECK(cudaGetLastError());
