@@ -176,6 +176,23 @@ def bench_batched(lb, torch, dev, batch, reps=5):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
             "nonzero_info": int((info != 0).sum().item())}
 
+OUT = None
+
+
+class StdoutToStderr:
+    """Route everything written to file descriptor 1 (NCCL's version banner, library chatter) to stderr while the
+    benchmark runs; `emit` writes the ONE JSON line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
 # ----------------------------------------------------------------------------------------------- GPU leg
 def run_dist(args, rank, world, local_rank):
     """N > 1: ONE DGETRF of order n_dist block-column-cyclic over the N GPUs (BASELINE configs[4]); NCCL panel broadcast."""
@@ -252,7 +269,7 @@ def run_dist(args, rank, world, local_rank):
             "checks": {"randomized_residual_ratio": resid, "info": int(info)},
             "batched_dgetrf_32x32": batched,
         }
-        print(json.dumps(line))
+        OUT.emit(json.dumps(line))
     dist.destroy_process_group()
 
 
@@ -441,7 +458,7 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
         "batched_dgetrf_32x32": batched,
     }
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
 
 
 def main():
@@ -464,6 +481,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+    global OUT
+    OUT = StdoutToStderr()          # from here on only OUT.emit() reaches stdout
     if world > 1 and not args.replicas:
         run_dist(args, rank, world, local_rank)
         return
