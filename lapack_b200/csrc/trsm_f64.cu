@@ -167,12 +167,14 @@ __global__ void __launch_bounds__(256) trsm_left_lower_small_kernel(int m, int n
 #pragma unroll
             for (int c = 0; c < TS_COLS; ++c) acc[c] = 0.0;
             const double* trow = A + r + (i64)kb * lda;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
-                if (k < bs) {
-                    double t = trow[(i64)k * lda];
+            double tv[32];                                   // the whole 32-entry strip in flight before the first FMA
 #pragma unroll
-                    for (int c = 0; c < TS_COLS; ++c) acc[c] = fma(t, sB[c][kb + k], acc[c]);
+            for (int k = 0; k < 32; ++k) tv[k] = (k < bs) ? __ldg(trow + (i64)k * lda) : 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < bs) {                                // rows beyond the block are uninitialised shared memory
+#pragma unroll
+                    for (int c = 0; c < TS_COLS; ++c) acc[c] = fma(tv[k], sB[c][kb + k], acc[c]);
                 }
             }
 #pragma unroll
