@@ -102,3 +102,53 @@ def test_cblas_dtrsm_dtrmm_both_layouts(L, side, uplo, trans, diag):
             b = b0.copy(order="F") if layout == COL else np.array(b0, order="C", copy=True)
             fn(layout, side, uplo, trans, diag, m, n, 1.5, P(aa), na, P(b), m if layout == COL else n)
             assert rel(b, want) < 1e-11, (layout, fn)
+
+
+def test_reference_cblas_wrappers_give_identical_results(L):
+    """The reference's own CBLAS wrappers (CBLAS/src/cblas_dgemm.c etc., compiled in place into oracle/_ref/libcblas_ref.so,
+    their dgemm_/dsyrk_/dtrmm_/dtrsm_ resolved by liblapack_b200.so) must issue exactly the Fortran call ours does:
+    results bit-identical in both layouts."""
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcblas_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libcblas_ref.so not built (reference tree absent at build time)")
+    R = C.CDLL(so)
+    R.cblas_dgemm.argtypes = L.cblas_dgemm.argtypes
+    R.cblas_dsyrk.argtypes = L.cblas_dsyrk.argtypes
+    R.cblas_dtrsm.argtypes = L.cblas_dtrsm.argtypes
+    R.cblas_dtrmm.argtypes = L.cblas_dtrmm.argtypes
+    for f in (R.cblas_dgemm, R.cblas_dsyrk, R.cblas_dtrsm, R.cblas_dtrmm):
+        f.restype = None
+    m, n, k = 77, 53, 91
+    for layout in (ROW, COL):
+        order = "C" if layout == ROW else "F"
+        ld = (lambda x: x.shape[1]) if layout == ROW else (lambda x: x.shape[0])
+        for ta in (NOTR, TR):
+            for tb in (NOTR, TR):
+                a = np.array(rnd(m, k, (1, 2, 3, 5)) if ta == NOTR else rnd(k, m, (1, 2, 3, 5)), order=order)
+                b = np.array(rnd(k, n, (7, 2, 3, 5)) if tb == NOTR else rnd(n, k, (7, 2, 3, 5)), order=order)
+                c0 = np.array(rnd(m, n, (9, 2, 3, 5)), order=order)
+                c1, c2 = c0.copy(order=order), c0.copy(order=order)
+                L.cblas_dgemm(layout, ta, tb, m, n, k, 0.7, P(a), ld(a), P(b), ld(b), -1.3, P(c1), ld(c1))
+                R.cblas_dgemm(layout, ta, tb, m, n, k, 0.7, P(a), ld(a), P(b), ld(b), -1.3, P(c2), ld(c2))
+                assert np.array_equal(c1, c2), (layout, ta, tb)
+        for uplo in (UP, LO):
+            for trans in (NOTR, TR):
+                a = np.array(rnd(n, k, (1, 2, 3, 5)) if trans == NOTR else rnd(k, n, (1, 2, 3, 5)), order=order)
+                c0 = np.array(rnd(n, n, (9, 2, 3, 5)), order=order)
+                c1, c2 = c0.copy(order=order), c0.copy(order=order)
+                L.cblas_dsyrk(layout, uplo, trans, n, k, 0.5, P(a), ld(a), 2.0, P(c1), n)
+                R.cblas_dsyrk(layout, uplo, trans, n, k, 0.5, P(a), ld(a), 2.0, P(c2), n)
+                assert np.array_equal(c1, c2), (layout, uplo, trans)
+        for side in (LEFT, RIGHT):
+            na = m if side == LEFT else n
+            a = np.array(rnd(na, na, (1, 2, 3, 5)) + 4.0 * np.eye(na), order=order)
+            for uplo in (UP, LO):
+                for trans in (NOTR, TR):
+                    for diag in (NONUNIT, UNIT):
+                        for ours, theirs in ((L.cblas_dtrsm, R.cblas_dtrsm), (L.cblas_dtrmm, R.cblas_dtrmm)):
+                            b0 = np.array(rnd(m, n, (9, 2, 3, 5)), order=order)
+                            b1, b2 = b0.copy(order=order), b0.copy(order=order)
+                            ours(layout, side, uplo, trans, diag, m, n, 1.5, P(a), na, P(b1), ld(b1))
+                            theirs(layout, side, uplo, trans, diag, m, n, 1.5, P(a), na, P(b2), ld(b2))
+                            assert np.array_equal(b1, b2), (layout, side, uplo, trans, diag)
