@@ -105,3 +105,33 @@ def test_lapacke_nancheck_and_singular(libs):
         buf = a.copy(order="F")
         buf[3, 4] = np.nan
         assert L.LAPACKE_dgetrf(COL, 50, 50, vp(buf), 50, vp(ipiv)) == -4, name        # NaN pre-check
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dorgqr_dormqr(libs, layout):
+    """LAPACKE_dorgqr / LAPACKE_dormqr (ours, and the reference's wrappers bound to our dorgqr_ / dormqr_) vs the oracle."""
+    dp = C.POINTER(C.c_double)
+    m, n, nc = 130, 70, 9
+    a, _ = O.random_matrix(m, n, SEED)
+    af = a.copy(order="F")
+    tau, info, _ = O.dgeqrf(af)
+    q_ref = af.copy(order="F")
+    assert O.dorgqr(q_ref, tau) == 0
+    c0, _ = O.random_matrix(m, nc, (3, 5, 7, 9))
+    order = "C" if layout == ROW else "F"
+    for name, L in libs:
+        L.LAPACKE_dorgqr.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp]
+        L.LAPACKE_dormqr.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int]
+        q = np.array(af, order=order, copy=True)
+        assert L.LAPACKE_dorgqr(layout, m, n, n, q.ctypes.data_as(dp), n if layout == ROW else m, tau.ctypes.data_as(dp)) == 0, name
+        assert np.max(np.abs(q - q_ref)) < 1e-12, name
+        for side, trans in (("L", "T"), ("L", "N")):
+            c_ref = c0.copy(order="F")
+            assert O.dormqr(side, trans, af, tau, c_ref) == 0
+            abuf = np.array(af, order=order, copy=True)
+            cbuf = np.array(c0, order=order, copy=True)
+            rc = L.LAPACKE_dormqr(layout, side.encode(), trans.encode(), m, nc, n, abuf.ctypes.data_as(dp),
+                                  n if layout == ROW else m, tau.ctypes.data_as(dp), cbuf.ctypes.data_as(dp),
+                                  nc if layout == ROW else m)
+            assert rc == 0, name
+            assert np.max(np.abs(cbuf - c_ref)) < 1e-12, (name, side, trans)
