@@ -76,6 +76,8 @@ int lb200_dlarft(void* stream, int n, int k, const double* dV, long long ldv, co
                  long long ldt);
 int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const double* dV, long long ldv,
                  const double* dT, long long ldt, double* dC, long long ldc);
+/* SRC/dgetri.f:114 DGETRI on device pointers: A holds the DGETRF factors, overwritten by inv(A); *dinfo = i if U(i,i) == 0 */
+int lb200_dgetri(void* stream, int n, double* dA, long long lda, const int* dipiv, int* dinfo);
 /* SRC/dormqr.f:165, SRC/dorgqr.f:126 on device pointers */
 int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
                  double* dC, long long ldc);

@@ -52,6 +52,8 @@ void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const in
 /* lapack.h:2991 (dgeqrf), dgeqr2, :10946 (dlarft), :10847 (dlarfb) */
 void dgeqrf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info);
 void dgeqr2_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, int* info);
+/* SRC/dgetri.f:114 DGETRI(N,A,LDA,IPIV,WORK,LWORK,INFO) (lapack.h LAPACK_dgetri) */
+void dgetri_(const int* n, double* A, const int* lda, const int* ipiv, double* work, const int* lwork, int* info);
 /* SRC/dorgqr.f:126 DORGQR(M,N,K,A,LDA,TAU,WORK,LWORK,INFO); SRC/dormqr.f:165 DORMQR(SIDE,TRANS,M,N,K,A,LDA,TAU,C,LDC,WORK,
    LWORK,INFO) (lapack.h:11807-11813, 12061-12078) */
 void dorgqr_(const int* m, const int* n, const int* k, double* A, const int* lda, const double* tau, double* work,

@@ -62,6 +62,10 @@ lapack_int LAPACKE_dgeqrf_work(int matrix_layout, lapack_int m, lapack_int n, do
 lapack_int LAPACKE_dgeqr2(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
 lapack_int LAPACKE_dgeqr2_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
                                double* work);
+/* lapacke.h:1153, 6216 (DGETRI) -- SURVEY 8f rank 2 */
+lapack_int LAPACKE_dgetri(int matrix_layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv);
+lapack_int LAPACKE_dgetri_work(int matrix_layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv,
+                               double* work, lapack_int lwork);
 /* lapacke.h:2664, 8163 (DORGQR), 2729, 8246 (DORMQR) -- SURVEY 8f rank 1 */
 lapack_int LAPACKE_dorgqr(int matrix_layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda,
                           const double* tau);

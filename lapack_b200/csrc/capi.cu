@@ -121,6 +121,10 @@ int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const
     lb::larfb(S(stream), side, trans, m, n, k, dV, ldv, dT, ldt, dC, ldc);
     return rc();
 }
+int lb200_dgetri(void* stream, int n, double* dA, long long lda, const int* dipiv, int* dinfo) {
+    lb::getri(S(stream), n, dA, lda, dipiv, dinfo);
+    return rc();
+}
 int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
                  double* dC, long long ldc) {
     lb::ormqr(S(stream), side, trans, m, n, k, dA, lda, dtau, dC, ldc);

@@ -809,4 +809,31 @@ void dormqr_(const char* side, const char* trans, const int* m, const int* n, co
     if (r) *info = r;
 }
 
+// DGETRI (SRC/dgetri.f:114).  WORK(1) protocol with the reference block size 64 (ilaenv.f:361-367).
+void dgetri_(const int* n, double* A, const int* lda, const int* ipiv, double* work, const int* lwork, int* info) {
+    *info = 0;
+    const int nb = 64;
+    const bool lquery = (*lwork == -1);
+    if (*n < 0) *info = -1;
+    else if (*lda < imax(1, *n)) *info = -3;
+    else if (*lwork < imax(1, *n) && !lquery) *info = -6;
+    if (*info != 0) { call_xerbla("DGETRI", -*info); return; }
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)imax(1, *n * nb);          // dgetri.f:153-155
+    if (lquery || *n == 0) return;
+    if (!device_ok(info)) return;
+    {
+        std::lock_guard<std::mutex> lock(g_abi_mutex);
+        Ctx c; c.scan({A, ipiv});
+        lb::i64 la;
+        double* dA = c.mat(A, *n, *n, *lda, true, true, &la);
+        const int* dp = c.vec<int>(ipiv, (size_t)*n, true, false);
+        int* dinfo = c.dev_info();
+        lb::getri(c.s, *n, dA, la, dp, dinfo);
+        *info = c.finish(dinfo);
+    }
+    int iws = *n;
+    if (nb > 1 && nb < *n) iws = imax(*n * nb, 1);                                 // dgetri.f:186-196,257
+    if (*info == 0 && ptr_kind(work) != PK_DEVICE) work[0] = (double)iws;
+}
+
 }  // extern "C"

@@ -945,4 +945,54 @@ void getrs(cudaStream_t s, char trans, int n, int nrhs, const double* A, i64 lda
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// DGETRI (SRC/dgetri.f:150-259): inverse from the LU factors.  The reference forms inv(U) in place
+// (DTRTRI) and then solves inv(A)*L = inv(U) block column by block column; on the GPU both steps are triangular
+// solves against the identity in a scratch matrix W (they run as DMMA GEMMs through the recursive DTRSM):
+//     W = I;  U W = W  (W = inv(U));  W L = W  (W = inv(U) inv(L));  A(:, c) = W(:, perm(c))
+// where perm composes the column interchanges of dgetri.f:250-255 (reverse order).  As in DTRTRI, an exactly zero
+// U(i,i) gives INFO = i and leaves A untouched (dtrtri.f:169-175, dgetri.f:181-183) -- decided on the device.
+__global__ void getri_diag_check_kernel(int n, const double* __restrict__ A, i64 lda, int* info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && A[i + (i64)i * lda] == 0.0) atomicMin((unsigned*)info, (unsigned)(i + 1));
+}
+__global__ void getri_info_init_kernel(int* info) { *info = 0x7fffffff; }
+__global__ void getri_info_fix_kernel(int* info) { if (*info == 0x7fffffff) *info = 0; }
+__global__ void getri_perm_kernel(int n, const int* __restrict__ ipiv, int* __restrict__ perm) {
+    // single thread: the interchanges are applied sequentially, last to first (dgetri.f:250-255)
+    for (int c = 0; c < n; ++c) perm[c] = c;
+    for (int j = n - 2; j >= 0; --j) {
+        const int jp = ipiv[j] - 1;
+        if (jp != j) { int t = perm[j]; perm[j] = perm[jp]; perm[jp] = t; }
+    }
+}
+__global__ void getri_gather_kernel(int n, const double* __restrict__ W, i64 ldw, const int* __restrict__ perm,
+                                    const int* __restrict__ info, double* __restrict__ A, i64 lda) {
+    if (*info != 0) return;                                  // singular: A keeps the LU factors
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int c = blockIdx.y; c < n; c += gridDim.y) A[i + (i64)c * lda] = W[i + (i64)perm[c] * ldw];
+}
+
+void getri(cudaStream_t s, int n, double* A, i64 lda, const int* ipiv, int* info) {
+    if (n <= 0) { LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s)); return; }
+    const i64 ldw = ((i64)n + 1) & ~1LL;
+    double* W = (double*)ws_alloc(s, sizeof(double) * (size_t)ldw * n);
+    int* perm = (int*)ws_alloc(s, sizeof(int) * (size_t)n);
+    getri_info_init_kernel<<<1, 1, 0, s>>>(info);
+    getri_diag_check_kernel<<<ceil_div(n, 256), 256, 0, s>>>(n, A, lda, info);
+    getri_info_fix_kernel<<<1, 1, 0, s>>>(info);
+    getri_perm_kernel<<<1, 1, 0, s>>>(n, ipiv, perm);
+    count_launch(4);
+    laset(s, 'A', n, n, 0.0, 1.0, W, ldw);
+    trsm(s, 'L', 'U', 'N', 'N', n, n, 1.0, A, lda, W, ldw);              // W = inv(U)          (dgetri.f:181)
+    trsm(s, 'R', 'L', 'N', 'U', n, n, 1.0, A, lda, W, ldw);              // W = inv(U) inv(L)   (dgetri.f:198-248)
+    dim3 grid(ceil_div(n, 256), (unsigned)min(n, 4096));
+    getri_gather_kernel<<<grid, 256, 0, s>>>(n, W, ldw, perm, info, A, lda);
+    count_launch();
+    ws_free(s, W);
+    ws_free(s, perm);
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace lb

@@ -400,6 +400,45 @@ lapack_int LAPACKE_dgeqr2(int layout, lapack_int m, lapack_int n, double* a, lap
     return info;
 }
 
+// ------------------------------------------------------------------------------------------------ dgetri
+// LAPACKE/src/lapacke_dgetri_work.c:40-88, lapacke_dgetri.c:36-75
+lapack_int LAPACKE_dgetri_work(int layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv, double* work,
+                               lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dgetri_(&n, a, &lda, ipiv, work, &lwork, &info);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        lapack_int lda_t = imax(1, n);
+        if (lda < n) { info = -4; lapacke_xerbla("LAPACKE_dgetri_work", info); return info; }
+        if (lwork == -1) {
+            dgetri_(&n, a, &lda_t, ipiv, work, &lwork, &info);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor r;
+        if (!r.in(a, n, n, lda)) { info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dgetri_work", info); return info; }
+        lda_t = imax(1, (int)r.ldc);
+        dgetri_(&n, r.dev_cm ? r.dev_cm : a, &lda_t, ipiv, work, &lwork, &info);
+        LB_ADJ(info);
+        r.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dgetri_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dgetri(int layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dgetri", -1); return -1; }
+    if (get_nancheck() && dge_nan(layout, n, n, a, lda)) return -3;
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dgetri_work(layout, n, a, lda, ipiv, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dgetri", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dgetri_work(layout, n, a, lda, ipiv, work, lwork);
+    free(work);
+    return info;
+}
+
 // ------------------------------------------------------------------------------------------------ dorgqr / dormqr
 // LAPACKE/src/lapacke_dorgqr_work.c:41-88, lapacke_dorgqr.c:36-78, lapacke_dormqr_work.c:41-110, lapacke_dormqr.c:36-90
 lapack_int LAPACKE_dorgqr_work(int layout, lapack_int m, lapack_int n, lapack_int k, double* a, lapack_int lda, const double* tau,

@@ -61,6 +61,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
 void getrf2(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info);
 void getrs(cudaStream_t s, char trans, int n, int nrhs, const double* A, i64 lda, const int* ipiv,
            double* B, i64 ldb);
+void getri(cudaStream_t s, int n, double* A, i64 lda, const int* ipiv, int* info);   // info: device word, set inside
 void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info);
 void potrf2(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info);
 void potrs(cudaStream_t s, char uplo, int n, int nrhs, const double* A, i64 lda, double* B, i64 ldb);

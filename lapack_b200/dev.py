@@ -128,6 +128,14 @@ def larfb(side, trans, v, t, c):
                             c.data_ptr(), ld(c)))
 
 
+def getri(a, ipiv):
+    """a (DGETRF factors) := inv(A) in place; returns the device INFO word"""
+    torch = _torch()
+    info = torch.zeros(1, dtype=torch.int32, device=a.device)
+    _chk(lib().lb200_dgetri(stream(), a.shape[0], a.data_ptr(), ld(a), ipiv.data_ptr(), info.data_ptr()))
+    return info
+
+
 def ormqr(side, trans, a, tau, c):
     m, n = c.shape
     _chk(lib().lb200_dormqr(stream(), _c(side), _c(trans), m, n, tau.shape[0], a.data_ptr(), ld(a), tau.data_ptr(),

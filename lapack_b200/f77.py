@@ -163,6 +163,24 @@ def geqrf(a):
     return tau[:min(m, n)], info, work[0]
 
 
+def dgetri(n, a, lda, ipiv, work, lwork):
+    info = _i(0)
+    lib().dgetri_(_r(n), _p(a), _r(lda), _p(ipiv), _p(work), _r(lwork), C.byref(info))
+    return info.value
+
+
+def getri(a, ipiv):
+    """a (DGETRF factors) := inv(A); workspace query protocol like the reference"""
+    n = a.shape[0]
+    ipiv = np.ascontiguousarray(ipiv, dtype=np.int32)
+    wq = np.zeros(1)
+    info = dgetri(n, a, _ld(a), ipiv, wq, -1)
+    if info != 0:
+        return info
+    work = np.zeros(max(1, int(wq[0])))
+    return dgetri(n, a, _ld(a), ipiv, work, len(work))
+
+
 def dorgqr(m, n, k, a, lda, tau, work, lwork):
     info = _i(0)
     lib().dorgqr_(_r(m), _r(n), _r(k), _p(a), _r(lda), _p(tau), _p(work), _r(lwork), C.byref(info))

@@ -87,6 +87,10 @@ void ora_dlarfb(char side, char trans, char direct, char storev, int m, int n, i
                 double *work, int ldwork);
 void ora_dgeqrf(int m, int n, double *a, int lda, double *tau, double *work, int lwork, int *info);
 void ora_dorg2r(int m, int n, int k, double *a, int lda, const double *tau, double *work, int *info);
+void ora_dtrti2(char uplo, char diag, int n, double *a, int lda, int *info);
+void ora_dtrtri(char uplo, char diag, int n, double *a, int lda, int *info);
+void ora_dgetri(int n, double *a, int lda, const int *ipiv, double *work, int lwork, int *info);
+void ora_set_nb_getri(int nb);
 void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
                 double *work, int *info);
 void ora_dormqr(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,

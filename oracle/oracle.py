@@ -246,6 +246,28 @@ def dorgqr(a, tau, k=None):
 THRESH = 30.0
 
 
+def dtrtri(uplo, diag, a):
+    info = C.c_int(0)
+    lib().ora_dtrtri(_c(uplo), _c(diag), a.shape[0], _d(a), _ld(a), C.byref(info))
+    return info.value
+
+
+def dgetri(a, ipiv, nb=None):
+    """inverse from dgetrf(a) output, in place (SRC/dgetri.f)"""
+    n = a.shape[0]
+    if nb is not None:
+        lib().ora_set_nb_getri(nb)
+    try:
+        lwork = max(1, n) * 64
+        work = np.zeros(lwork)
+        info = C.c_int(0)
+        lib().ora_dgetri(n, _d(a), _ld(a), _i(np.ascontiguousarray(ipiv, dtype=np.int32)), _d(work), lwork, C.byref(info))
+    finally:
+        if nb is not None:
+            lib().ora_set_nb_getri(64)
+    return info.value
+
+
 def dormqr(side, trans, a, tau, c, k=None):
     """C := Q C, Q^T C, C Q or C Q^T with Q from dgeqrf(a, tau) (SRC/dormqr.f); c is overwritten"""
     m, n = c.shape

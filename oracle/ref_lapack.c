@@ -37,7 +37,8 @@ double ora_dlamch(char cmach)
 }
 
 /* SRC/ilaenv.f:289-302,374-380 (NB) and :623-630 (NX); overridable like TESTING/LIN/xlaenv.f:101. */
-static int g_nb_getrf = 64, g_nb_potrf = 64, g_nb_geqrf = 32, g_nx_geqrf = 128;
+static int g_nb_getrf = 64, g_nb_potrf = 64, g_nb_geqrf = 32, g_nx_geqrf = 128, g_nb_getri = 64;
+void ora_set_nb_getri(int nb) { g_nb_getri = nb; }
 void ora_set_nb(int nb_getrf, int nb_potrf, int nb_geqrf, int nx_geqrf)
 {
     g_nb_getrf = nb_getrf; g_nb_potrf = nb_potrf; g_nb_geqrf = nb_geqrf; g_nx_geqrf = nx_geqrf;
@@ -47,6 +48,7 @@ int ora_ilaenv_nb(const char *name)
     if (!strcmp(name, "DGETRF")) return g_nb_getrf;
     if (!strcmp(name, "DPOTRF")) return g_nb_potrf;
     if (!strcmp(name, "DGEQRF") || !strcmp(name, "DORGQR") || !strcmp(name, "DORMQR")) return g_nb_geqrf;   /* ilaenv.f:416-436: 32 */
+    if (!strcmp(name, "DGETRI") || !strcmp(name, "DTRTRI")) return g_nb_getri;                               /* ilaenv.f:361-367, 475-481: 64 */
     return 1;
 }
 
@@ -743,6 +745,107 @@ void ora_dorgqr(int m, int n, int k, double *a, int lda, const double *tau, doub
             ora_dorg2r(m - i, ib, ib, &A_(i, i), lda, tau + i, work, &iinfo);
             for (int j = i; j < i + ib; ++j) for (int l = 0; l < i; ++l) A_(l, j) = 0.0;
         }
+    }
+    work[0] = (double)iws;
+}
+
+/* SRC/dtrti2.f:150-213 -- unblocked inverse of a triangular matrix. */
+void ora_dtrti2(char uplo, char diag, int n, double *a, int lda, int *info)
+{
+    int upper = ora_lsame(uplo, 'U'), nounit = ora_lsame(diag, 'N');
+    *info = 0;
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1; else if (!nounit && !ora_lsame(diag, 'U')) *info = -2;
+    else if (n < 0) *info = -3; else if (lda < imax(1, n)) *info = -5;
+    if (*info != 0) return;
+    if (upper) {
+        for (int j = 0; j < n; ++j) {
+            double ajj;
+            if (nounit) { A_(j, j) = 1.0 / A_(j, j); ajj = -A_(j, j); } else ajj = -1.0;
+            ora_dtrmv('U', 'N', diag, j, a, lda, &A_(0, j), 1);               /* elements 1:j-1 of column j */
+            ora_dscal(j, ajj, &A_(0, j), 1);
+        }
+    } else {
+        for (int j = n - 1; j >= 0; --j) {
+            double ajj;
+            if (nounit) { A_(j, j) = 1.0 / A_(j, j); ajj = -A_(j, j); } else ajj = -1.0;
+            if (j < n - 1) {
+                ora_dtrmv('L', 'N', diag, n - 1 - j, &A_(j + 1, j + 1), lda, &A_(j + 1, j), 1);
+                ora_dscal(n - 1 - j, ajj, &A_(j + 1, j), 1);
+            }
+        }
+    }
+}
+
+/* SRC/dtrtri.f:150-243 (NB = 64, ilaenv.f:475-481); INFO = i if A(i,i) is exactly zero (nothing is computed then). */
+void ora_dtrtri(char uplo, char diag, int n, double *a, int lda, int *info)
+{
+    int upper = ora_lsame(uplo, 'U'), nounit = ora_lsame(diag, 'N');
+    *info = 0;
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1; else if (!nounit && !ora_lsame(diag, 'U')) *info = -2;
+    else if (n < 0) *info = -3; else if (lda < imax(1, n)) *info = -5;
+    if (*info != 0 || n == 0) return;
+    if (nounit) {
+        for (int i = 0; i < n; ++i) if (A_(i, i) == 0.0) { *info = i + 1; return; }
+    }
+    int nb = ora_ilaenv_nb("DTRTRI");
+    if (nb <= 1 || nb >= n) { ora_dtrti2(uplo, diag, n, a, lda, info); return; }
+    if (upper) {
+        for (int j = 0; j < n; j += nb) {
+            int jb = imin(nb, n - j);
+            ora_dtrmm('L', 'U', 'N', diag, j, jb, 1.0, a, lda, &A_(0, j), lda);
+            ora_dtrsm('R', 'U', 'N', diag, j, jb, -1.0, &A_(j, j), lda, &A_(0, j), lda);
+            ora_dtrti2('U', diag, jb, &A_(j, j), lda, info);
+        }
+    } else {
+        int nn = ((n - 1) / nb) * nb;                                       /* 0-based start of the last block */
+        for (int j = nn; j >= 0; j -= nb) {
+            int jb = imin(nb, n - j);
+            if (j + jb < n) {
+                ora_dtrmm('L', 'L', 'N', diag, n - j - jb, jb, 1.0, &A_(j + jb, j + jb), lda, &A_(j + jb, j), lda);
+                ora_dtrsm('R', 'L', 'N', diag, n - j - jb, jb, -1.0, &A_(j, j), lda, &A_(j + jb, j), lda);
+            }
+            ora_dtrti2('L', diag, jb, &A_(j, j), lda, info);
+        }
+    }
+}
+
+/* SRC/dgetri.f:150-259 -- inverse from the LU factors: inv(U), then inv(A)*L = inv(U), then column interchanges.
+   work: at least n*nb doubles for the blocked path (lwork honoured like the reference). */
+void ora_dgetri(int n, double *a, int lda, const int *ipiv, double *work, int lwork, int *info)
+{
+    *info = 0;
+    int nb = ora_ilaenv_nb("DGETRI");
+    int lquery = (lwork == -1);
+    work[0] = (double)imax(1, n * nb);
+    if (n < 0) *info = -1; else if (lda < imax(1, n)) *info = -3; else if (lwork < imax(1, n) && !lquery) *info = -6;
+    if (*info != 0 || lquery) return;
+    if (n == 0) return;
+    ora_dtrtri('U', 'N', n, a, lda, info);
+    if (*info > 0) return;
+    int nbmin = 2, ldwork = n, iws;
+    if (nb > 1 && nb < n) {
+        iws = imax(ldwork * nb, 1);
+        if (lwork < iws) { nb = lwork / ldwork; nbmin = 2; }
+    } else iws = n;
+    if (nb < nbmin || nb >= n) {
+        for (int j = n - 1; j >= 0; --j) {
+            for (int i = j + 1; i < n; ++i) { work[i] = A_(i, j); A_(i, j) = 0.0; }
+            if (j < n - 1) ora_dgemv('N', n, n - 1 - j, -1.0, &A_(0, j + 1), lda, &work[j + 1], 1, 1.0, &A_(0, j), 1);
+        }
+    } else {
+        int nn = ((n - 1) / nb) * nb;
+        for (int j = nn; j >= 0; j -= nb) {
+            int jb = imin(nb, n - j);
+            for (int jj = j; jj < j + jb; ++jj)
+                for (int i = jj + 1; i < n; ++i) { work[i + (size_t)(jj - j) * ldwork] = A_(i, jj); A_(i, jj) = 0.0; }
+            if (j + jb < n)
+                ora_dgemm('N', 'N', n, jb, n - j - jb, -1.0, &A_(0, j + jb), lda, &work[j + jb], ldwork, 1.0, &A_(0, j), lda);
+            ora_dtrsm('R', 'L', 'N', 'U', n, jb, 1.0, &work[j], ldwork, &A_(0, j), lda);
+        }
+    }
+    for (int j = n - 2; j >= 0; --j) {
+        int jp = ipiv[j] - 1;
+        if (jp != j) ora_dswap(n, &A_(0, j), 1, &A_(0, jp), 1);
     }
     work[0] = (double)iws;
 }

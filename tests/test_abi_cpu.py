@@ -148,6 +148,17 @@ def test_orgqr_ormqr_error_exits_and_query(lb):
     assert f.dormqr("L", "N", 0, 0, 0, A, 1, TAU, B, 1, wq, 1) == 0 and wq[0] == 1             # quick return, no GPU needed
 
 
+def test_getri_error_exits_and_query(lb):
+    """TESTING/LIN/derrge.f:157-165 (positions 1 and 3) plus the LWORK check and query of dgetri.f:152-170."""
+    f = lb.f77
+    assert expect(lb, lambda: f.dgetri(-1, A, 1, IP, W, 1), "DGETRI", 1) == -1
+    assert expect(lb, lambda: f.dgetri(2, A, 1, IP, W, 2), "DGETRI", 3) == -3
+    assert expect(lb, lambda: f.dgetri(2, A, 2, IP, W, 1), "DGETRI", 6) == -6
+    wq = np.zeros(1)
+    assert f.dgetri(300, A, 300, IP, wq, -1) == 0 and wq[0] == 300 * 64
+    assert f.dgetri(0, A, 1, IP, wq, 1) == 0 and wq[0] == 1
+
+
 def test_quick_returns_need_no_gpu(lb):
     """M==0 or N==0 return before any device work (dgetrf.f:159, dpotrf.f:161, dgeqrf.f:209-212)."""
     f = lb.f77

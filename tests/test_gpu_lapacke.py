@@ -135,3 +135,17 @@ def test_lapacke_dorgqr_dormqr(libs, layout):
                                   nc if layout == ROW else m)
             assert rc == 0, name
             assert np.max(np.abs(cbuf - c_ref)) < 1e-12, (name, side, trans)
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dgetri(libs, layout):
+    n = 180
+    a, _ = O.random_matrix(n, n, SEED)
+    lu = a.copy(order="F")
+    ipiv, _ = O.dgetrf(lu)
+    ref = lu.copy(order="F")
+    assert O.dgetri(ref, ipiv) == 0
+    for name, L in libs:
+        buf = np.array(lu, order="C" if layout == ROW else "F", copy=True)
+        assert L.LAPACKE_dgetri(layout, n, vp(buf), n, vp(ipiv)) == 0, name
+        assert np.max(np.abs(buf - ref)) < 1e-10 * np.max(np.abs(ref)), name

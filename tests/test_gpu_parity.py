@@ -551,6 +551,33 @@ def test_dlarft_dlarfb_vs_oracle(lb):
             assert rel(got, want) < 1e-11
 
 
+# ------------------------------------------------------------------------------------------- DGETRI
+@pytest.mark.parametrize("n", [1, 33, 300, 1100])
+def test_dgetri_vs_oracle(lb, n):
+    a, _ = O.random_matrix(n, n, SEED)
+    lu = a.copy(order="F")
+    ipiv, info = O.dgetrf(lu)
+    ref = lu.copy(order="F")
+    assert O.dgetri(ref, ipiv) == 0
+    got = lu.copy(order="F")
+    assert lb.f77.getri(got, ipiv) == 0
+    scale = float(np.max(np.abs(ref)))
+    assert np.max(np.abs(got - ref)) < 1e-10 * scale
+    assert np.max(np.abs(got @ a - np.eye(n))) < 1e-9
+    # factor + invert entirely on the device
+    d = np_to_dev(lb, a)
+    piv_d, _ = lb.dev.getrf(d)
+    assert int(lb.dev.getri(d, piv_d).item()) == 0
+    assert np.max(np.abs(dev_to_np(d) - ref)) < 1e-10 * scale
+    if n >= 33:
+        # exactly singular U: INFO = i and A keeps its factors (dtrtri.f:169-175, dgetri.f:181-183)
+        sing = lu.copy(order="F")
+        sing[20, 20] = 0.0
+        before = sing.copy()
+        assert lb.f77.getri(sing, ipiv) == 21
+        assert np.array_equal(sing, before)
+
+
 # ------------------------------------------------------------------------------------------- DORGQR / DORMQR
 @pytest.mark.parametrize("shape", [(1, 1), (40, 40), (300, 170), (700, 700), (1500, 520)])
 def test_dorgqr_dormqr_vs_oracle(lb, shape):

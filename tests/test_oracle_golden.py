@@ -242,3 +242,27 @@ def test_dormqr_dorgqr_netlib(tag):
         assert np.max(np.abs(c - g[f"{tag}_ormqr_LT"])) < 1e-12
     finally:
         O.set_nb()
+
+
+@pytest.mark.parametrize("n", [7, 70])
+def test_dgetri_dtrtri_netlib(n):
+    """ora_dgetri / ora_dtrtri vs netlib 3.12.0 (tests/golden/make_golden_getri.py); blocked and unblocked paths."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "netlib_golden_getri.npz"))
+    lu, ipiv, inv_ref, a = np.asfortranarray(g[f"lu{n}"]), g[f"ipiv{n}"], g[f"inv{n}"], g[f"a{n}"]
+    scale = np.max(np.abs(inv_ref))
+    for nb in (None, 1, 8):
+        x = lu.copy(order="F")
+        assert O.dgetri(x, ipiv, nb=nb) == 0
+        assert np.max(np.abs(x - inv_ref)) < 1e-11 * scale
+        assert np.max(np.abs(x @ a - np.eye(n))) < 1e-10
+    for uplo in "UL":
+        t = np.asfortranarray(g[f"tri{uplo}{n}"].copy())
+        assert O.dtrtri(uplo, "N", t) == 0
+        assert np.max(np.abs(t - g[f"triinv{uplo}{n}"])) < 1e-12
+    # exactly singular U: INFO = i, nothing computed (dtrtri.f:169-175, dgetri.f:181-183)
+    x = lu.copy(order="F")
+    x[3, 3] = 0.0
+    before = x.copy()
+    assert O.dgetri(x, ipiv) == 4
+    assert np.array_equal(x, before)
