@@ -78,6 +78,10 @@ int lb200_dlarfb(void* stream, char side, char trans, int m, int n, int k, const
                  const double* dT, long long ldt, double* dC, long long ldc);
 /* SRC/dgetri.f:114 DGETRI on device pointers: A holds the DGETRF factors, overwritten by inv(A); *dinfo = i if U(i,i) == 0 */
 int lb200_dgetri(void* stream, int n, double* dA, long long lda, const int* dipiv, int* dinfo);
+/* SRC/dgeqrt.f:139 DGEQRT (T is nb x min(m,n)), SRC/dgemqrt.f:166 DGEMQRT on device pointers */
+int lb200_dgeqrt(void* stream, int m, int n, int nb, double* dA, long long lda, double* dT, long long ldt);
+int lb200_dgemqrt(void* stream, char side, char trans, int m, int n, int k, int nb, const double* dV, long long ldv,
+                  const double* dT, long long ldt, double* dC, long long ldc);
 /* SRC/dormqr.f:165, SRC/dorgqr.f:126 on device pointers */
 int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
                  double* dC, long long ldc);

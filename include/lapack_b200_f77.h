@@ -52,6 +52,11 @@ void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const in
 /* lapack.h:2991 (dgeqrf), dgeqr2, :10946 (dlarft), :10847 (dlarfb) */
 void dgeqrf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info);
 void dgeqr2_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, int* info);
+/* SRC/dgeqrt.f:139 DGEQRT(M,N,NB,A,LDA,T,LDT,WORK,INFO); SRC/dgemqrt.f:166 DGEMQRT(SIDE,TRANS,M,N,K,NB,V,LDV,T,LDT,C,LDC,WORK,INFO) */
+void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* lda, double* T, const int* ldt, double* work,
+             int* info);
+void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, const int* k, const int* nb, const double* V,
+              const int* ldv, const double* T, const int* ldt, double* C, const int* ldc, double* work, int* info, size_t, size_t);
 /* SRC/dgetri.f:114 DGETRI(N,A,LDA,IPIV,WORK,LWORK,INFO) (lapack.h LAPACK_dgetri) */
 void dgetri_(const int* n, double* A, const int* lda, const int* ipiv, double* work, const int* lwork, int* info);
 /* SRC/dorgqr.f:126 DORGQR(M,N,K,A,LDA,TAU,WORK,LWORK,INFO); SRC/dormqr.f:165 DORMQR(SIDE,TRANS,M,N,K,A,LDA,TAU,C,LDC,WORK,

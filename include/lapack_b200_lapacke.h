@@ -62,6 +62,16 @@ lapack_int LAPACKE_dgeqrf_work(int matrix_layout, lapack_int m, lapack_int n, do
 lapack_int LAPACKE_dgeqr2(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
 lapack_int LAPACKE_dgeqr2_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
                                double* work);
+/* lapacke.h:11369, 11526 (DGEQRT), 11348, 11505 (DGEMQRT) -- SURVEY 8f rank 4; row-major T is nb x k, ldt >= k */
+lapack_int LAPACKE_dgeqrt(int matrix_layout, lapack_int m, lapack_int n, lapack_int nb, double* a, lapack_int lda, double* t,
+                          lapack_int ldt);
+lapack_int LAPACKE_dgeqrt_work(int matrix_layout, lapack_int m, lapack_int n, lapack_int nb, double* a, lapack_int lda,
+                               double* t, lapack_int ldt, double* work);
+lapack_int LAPACKE_dgemqrt(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, lapack_int nb,
+                           const double* v, lapack_int ldv, const double* t, lapack_int ldt, double* c, lapack_int ldc);
+lapack_int LAPACKE_dgemqrt_work(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k,
+                                lapack_int nb, const double* v, lapack_int ldv, const double* t, lapack_int ldt, double* c,
+                                lapack_int ldc, double* work);
 /* lapacke.h:1153, 6216 (DGETRI) -- SURVEY 8f rank 2 */
 lapack_int LAPACKE_dgetri(int matrix_layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv);
 lapack_int LAPACKE_dgetri_work(int matrix_layout, lapack_int n, double* a, lapack_int lda, const lapack_int* ipiv,

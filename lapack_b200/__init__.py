@@ -69,6 +69,8 @@ def _declare(L):
     L.lb200_dlarft.argtypes = [VP, i, i, VP, LL, VP, VP, LL]
     L.lb200_dlarfb.argtypes = [VP, ch, ch, i, i, i, VP, LL, VP, LL, VP, LL]
     L.lb200_dgetri.argtypes = [VP, i, VP, LL, VP, VP]
+    L.lb200_dgeqrt.argtypes = [VP, i, i, i, VP, LL, VP, LL]
+    L.lb200_dgemqrt.argtypes = [VP, ch, ch, i, i, i, i, VP, LL, VP, LL, VP, LL]
     L.lb200_dormqr.argtypes = [VP, ch, ch, i, i, i, VP, LL, VP, VP, LL]
     L.lb200_dorgqr.argtypes = [VP, i, i, i, VP, LL, VP]
     L.lb200_dgetrf_batched32.argtypes = [VP, LL, VP, VP, VP]

@@ -125,6 +125,15 @@ int lb200_dgetri(void* stream, int n, double* dA, long long lda, const int* dipi
     lb::getri(S(stream), n, dA, lda, dipiv, dinfo);
     return rc();
 }
+int lb200_dgeqrt(void* stream, int m, int n, int nb, double* dA, long long lda, double* dT, long long ldt) {
+    lb::geqrt(S(stream), m, n, nb, dA, lda, dT, ldt);
+    return rc();
+}
+int lb200_dgemqrt(void* stream, char side, char trans, int m, int n, int k, int nb, const double* dV, long long ldv,
+                  const double* dT, long long ldt, double* dC, long long ldc) {
+    lb::gemqrt(S(stream), side, trans, m, n, k, nb, dV, ldv, dT, ldt, dC, ldc);
+    return rc();
+}
 int lb200_dormqr(void* stream, char side, char trans, int m, int n, int k, const double* dA, long long lda, const double* dtau,
                  double* dC, long long ldc) {
     lb::ormqr(S(stream), side, trans, m, n, k, dA, lda, dtau, dC, ldc);

@@ -836,4 +836,57 @@ void dgetri_(const int* n, double* A, const int* lda, const int* ipiv, double* w
     if (*info == 0 && ptr_kind(work) != PK_DEVICE) work[0] = (double)iws;
 }
 
+// DGEQRT / DGEMQRT (SRC/dgeqrt.f:139, SRC/dgemqrt.f:166).  WORK is not used (device scratch).
+void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* lda, double* T, const int* ldt, double* work,
+             int* info) {
+    (void)work;
+    *info = 0;
+    const int k = imin(*m, *n);
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nb < 1 || (*nb > k && k > 0)) *info = -3;
+    else if (*lda < imax(1, *m)) *info = -5;
+    else if (*ldt < *nb) *info = -7;
+    if (*info != 0) { call_xerbla("DGEQRT", -*info); return; }
+    if (k == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, T});
+    lb::i64 la, lt;
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    double* dT = c.mat(T, *nb, k, *ldt, true, true, &lt);          // in + out: the strictly lower parts of the T blocks stay
+    lb::geqrt(c.s, *m, *n, *nb, dA, la, dT, lt);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, const int* k, const int* nb, const double* V,
+              const int* ldv, const double* T, const int* ldt, double* C, const int* ldc, double* work, int* info, size_t, size_t) {
+    (void)work;
+    *info = 0;
+    const bool left = same(side, 'L'), right = same(side, 'R'), tran = same(trans, 'T'), notran = same(trans, 'N');
+    const int q = left ? *m : *n;
+    if (!left && !right) *info = -1;
+    else if (!tran && !notran) *info = -2;
+    else if (*m < 0) *info = -3;
+    else if (*n < 0) *info = -4;
+    else if (*k < 0 || *k > q) *info = -5;
+    else if (*nb < 1 || (*nb > *k && *k > 0)) *info = -6;
+    else if (*ldv < imax(1, q)) *info = -8;
+    else if (*ldt < *nb) *info = -10;
+    else if (*ldc < imax(1, *m)) *info = -12;
+    if (*info != 0) { call_xerbla("DGEMQRT", -*info); return; }
+    if (*m == 0 || *n == 0 || *k == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({V, T, C});
+    lb::i64 lv, lt, lc;
+    const double* dV = c.mat(const_cast<double*>(V), q, *k, *ldv, true, false, &lv);
+    const double* dT = c.mat(const_cast<double*>(T), *nb, *k, *ldt, true, false, &lt);
+    double* dC = c.mat(C, *m, *n, *ldc, true, true, &lc);
+    lb::gemqrt(c.s, left ? 'L' : 'R', notran ? 'N' : 'T', *m, *n, *k, *nb, dV, lv, dT, lt, dC, lc);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
 }  // extern "C"

@@ -672,11 +672,14 @@ static void apply_block_reflector(cudaStream_t s, int m, int nc, int k, const do
     gemm(s, 'N', 'N', m, nc, k, -1.0, Vc, ldvc, W2, ldw, 1.0, C, ldc);      // C -= V W2
 }
 
-static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, int nb, bool lookahead) {
+// Tout != nullptr (DGEQRT): the block size is the caller's and the upper triangle of every panel's T factor is copied to
+// Tout(1:jb, j:j+jb) -- the layout of SRC/dgeqrt.f:196-198.
+static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau, int nb, bool lookahead,
+                       double* Tout = nullptr, i64 ldtout = 0) {
     if (m <= 0 || n <= 0) return;
     const int k = min(m, n);
     nb = min(nb, k);
-    if (nb < QW) nb = min(QW, k);
+    if (!Tout && nb < QW) nb = min(QW, k);
     const bool la = lookahead && k > nb;
     // scratch: two (Vc, T) sets so that panel j+1 can be built while update j still reads set j
     const i64 ldvc = (m + 1) & ~1;
@@ -715,6 +718,7 @@ static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double*
     auto panel = [&](int j, int jb, int set) {
         LB_CUDA_CHECK(cudaMemsetAsync(T[set], 0, sizeof(double) * ldt * nb, sp));
         geqrf_panel(sp, m - j, jb, A + j + (i64)j * lda, lda, tau + j, Vc[set], ldvc, T[set], ldt, W1p, W2p);
+        if (Tout) lacpy(sp, 'U', jb, jb, T[set], ldt, Tout + (i64)j * ldtout, ldtout);
     };
     panel(0, min(nb, k), 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
@@ -935,6 +939,35 @@ void orgqr(cudaStream_t s, int m, int n, int k, double* A, i64 lda, const double
         if (i > 0) laset(s, 'A', i, ib, 0.0, 0.0, A + (i64)i * lda, lda);           // rows above the block (dorgqr.f:270-274)
     }
     ws_free(s, T); ws_free(s, E); ws_free(s, W); ws_free(s, Vc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DGEQRT / DGEMQRT (SRC/dgeqrt.f:166-211, SRC/dgemqrt.f:199-287): the blocked QR above with the
+// caller's block size, keeping the T factors; and the application of Q / Q^T from those stored factors.
+void geqrt(cudaStream_t s, int m, int n, int nb, double* A, i64 lda, double* T, i64 ldt) {
+    const int k = min(m, n);
+    if (k <= 0) return;
+    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    double* tau = (double*)ws_alloc(s, sizeof(double) * (size_t)k);
+    geqrf_impl(s, m, n, A, lda, tau, nb, g_qr_lookahead != 0, T, ldt);
+    ws_free(s, tau);
+}
+
+void gemqrt(cudaStream_t s, char side, char trans, int m, int n, int k, int nb, const double* V, i64 ldv, const double* T,
+            i64 ldt, double* C, i64 ldc) {
+    if (m <= 0 || n <= 0 || k <= 0) return;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const bool forward = (left && !notran) || (!left && notran);               // dgemqrt.f:242-285
+    const int nblk = ceil_div(k, nb);
+    for (int b = 0; b < nblk; ++b) {
+        const int i = forward ? b * nb : (nblk - 1 - b) * nb;
+        const int ib = min(nb, k - i);
+        const double* Vi = V + i + (i64)i * ldv;
+        const double* Ti = T + (i64)i * ldt;
+        if (left) larfb(s, 'L', trans, m - i, n, ib, Vi, ldv, Ti, ldt, C + i, ldc);
+        else larfb(s, 'R', trans, m, n - i, ib, Vi, ldv, Ti, ldt, C + (i64)i * ldc, ldc);
+    }
 }
 
 }  // namespace lb

@@ -21,6 +21,7 @@
 namespace {
 
 inline int imax(int a, int b) { return a > b ? a : b; }
+inline int imin(int a, int b) { return a < b ? a : b; }
 inline bool lsame(char a, char b) {
     if (a >= 'a' && a <= 'z') a = (char)(a - 32);
     if (b >= 'a' && b <= 'z') b = (char)(b - 32);
@@ -435,6 +436,82 @@ lapack_int LAPACKE_dgetri(int layout, lapack_int n, double* a, lapack_int lda, c
     double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
     if (!work) { lapacke_xerbla("LAPACKE_dgetri", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
     info = LAPACKE_dgetri_work(layout, n, a, lda, ipiv, work, lwork);
+    free(work);
+    return info;
+}
+
+// ------------------------------------------------------------------------------------------------ dgeqrt / dgemqrt
+// LAPACKE/src/lapacke_dgeqrt_work.c:40-98, lapacke_dgeqrt.c:36-68, lapacke_dgemqrt_work.c:40-115, lapacke_dgemqrt.c:36-80.
+// Row-major operands are transposed on the GPU; row-major T is nb x k with ldt >= k (for DGEMQRT the reference checks
+// ldt < nb and transposes an "ldt x nb" array, lapacke_dgemqrt_work.c:62-66,90 -- the consistent layout is used here).
+lapack_int LAPACKE_dgeqrt_work(int layout, lapack_int m, lapack_int n, lapack_int nb, double* a, lapack_int lda, double* t,
+                               lapack_int ldt, double* work) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dgeqrt_(&m, &n, &nb, a, &lda, t, &ldt, work, &info);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        const lapack_int k = imin(m, n);
+        if (lda < n) { info = -6; lapacke_xerbla("LAPACKE_dgeqrt_work", info); return info; }
+        if (ldt < k) { info = -8; lapacke_xerbla("LAPACKE_dgeqrt_work", info); return info; }
+        RowMajor ra, rt;
+        if (!ra.in(a, m, n, lda) || !rt.in(t, nb, k, ldt)) {
+            info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dgeqrt_work", info); return info;
+        }
+        lapack_int lda_t = imax(1, (int)ra.ldc), ldt_t = imax(1, (int)rt.ldc);
+        dgeqrt_(&m, &n, &nb, ra.dev_cm ? ra.dev_cm : a, &lda_t, rt.dev_cm ? rt.dev_cm : t, &ldt_t, work, &info);
+        LB_ADJ(info);
+        ra.out();
+        rt.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dgeqrt_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dgeqrt(int layout, lapack_int m, lapack_int n, lapack_int nb, double* a, lapack_int lda, double* t,
+                          lapack_int ldt) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dgeqrt", -1); return -1; }
+    if (get_nancheck() && dge_nan(layout, m, n, a, lda)) return -5;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, nb) * (size_t)imax(1, n));
+    if (!work) { lapacke_xerbla("LAPACKE_dgeqrt", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    lapack_int info = LAPACKE_dgeqrt_work(layout, m, n, nb, a, lda, t, ldt, work);
+    free(work);
+    return info;
+}
+lapack_int LAPACKE_dgemqrt_work(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, lapack_int nb,
+                                const double* v, lapack_int ldv, const double* t, lapack_int ldt, double* c, lapack_int ldc,
+                                double* work) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dgemqrt_(&side, &trans, &m, &n, &k, &nb, v, &ldv, t, &ldt, c, &ldc, work, &info, 1, 1);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        const lapack_int q = lsame(side, 'l') ? m : n;
+        if (ldc < n) { info = -13; lapacke_xerbla("LAPACKE_dgemqrt_work", info); return info; }
+        if (ldt < k) { info = -11; lapacke_xerbla("LAPACKE_dgemqrt_work", info); return info; }
+        if (ldv < k) { info = -9; lapacke_xerbla("LAPACKE_dgemqrt_work", info); return info; }
+        RowMajor rv, rt, rc;
+        if (!rv.in(v, q, k, ldv) || !rt.in(t, nb, k, ldt) || !rc.in(c, m, n, ldc)) {
+            info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dgemqrt_work", info); return info;
+        }
+        lapack_int ldv_t = imax(1, (int)rv.ldc), ldt_t = imax(1, (int)rt.ldc), ldc_t = imax(1, (int)rc.ldc);
+        dgemqrt_(&side, &trans, &m, &n, &k, &nb, rv.dev_cm ? rv.dev_cm : v, &ldv_t, rt.dev_cm ? rt.dev_cm : t, &ldt_t,
+                 rc.dev_cm ? rc.dev_cm : c, &ldc_t, work, &info, 1, 1);
+        LB_ADJ(info);
+        rc.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dgemqrt_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dgemqrt(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, lapack_int nb,
+                           const double* v, lapack_int ldv, const double* t, lapack_int ldt, double* c, lapack_int ldc) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dgemqrt", -1); return -1; }
+    if (get_nancheck()) {
+        const lapack_int q = lsame(side, 'l') ? m : (lsame(side, 'r') ? n : 0);
+        if (dge_nan(layout, m, n, c, ldc)) return -12;
+        if (dge_nan(layout, nb, k, t, ldt)) return -10;
+        if (dge_nan(layout, q, k, v, ldv)) return -8;
+    }
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, m) * (size_t)imax(1, nb));
+    if (!work) { lapacke_xerbla("LAPACKE_dgemqrt", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    lapack_int info = LAPACKE_dgemqrt_work(layout, side, trans, m, n, k, nb, v, ldv, t, ldt, c, ldc, work);
     free(work);
     return info;
 }

@@ -163,6 +163,34 @@ def geqrf(a):
     return tau[:min(m, n)], info, work[0]
 
 
+def dgeqrt(m, n, nb, a, lda, t, ldt, work):
+    info = _i(0)
+    lib().dgeqrt_(_r(m), _r(n), _r(nb), _p(a), _r(lda), _p(t), _r(ldt), _p(work), C.byref(info))
+    return info.value
+
+
+def dgemqrt(side, trans, m, n, k, nb, v, ldv, t, ldt, c, ldc, work):
+    info = _i(0)
+    lib().dgemqrt_(_c(side), _c(trans), _r(m), _r(n), _r(k), _r(nb), _p(v), _r(ldv), _p(t), _r(ldt), _p(c), _r(ldc), _p(work),
+                   C.byref(info), C.c_size_t(1), C.c_size_t(1))
+    return info.value
+
+
+def geqrt(a, nb):
+    """blocked QR keeping the T factors (DGEQRT); returns (t [nb x min(m,n)], info)"""
+    m, n = a.shape
+    t = np.zeros((nb, max(1, min(m, n))), order="F")
+    work = np.zeros(max(1, nb * n))
+    return t, dgeqrt(m, n, nb, a, _ld(a), t, _ld(t), work)
+
+
+def gemqrt(side, trans, v, t, c, nb, k=None):
+    m, n = c.shape
+    k = t.shape[1] if k is None else k
+    work = np.zeros(max(1, (n if side.upper() == "L" else m) * nb))
+    return dgemqrt(side, trans, m, n, k, nb, v, _ld(v), t, _ld(t), c, _ld(c), work)
+
+
 def dgetri(n, a, lda, ipiv, work, lwork):
     info = _i(0)
     lib().dgetri_(_r(n), _p(a), _r(lda), _p(ipiv), _p(work), _r(lwork), C.byref(info))

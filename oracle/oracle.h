@@ -91,6 +91,10 @@ void ora_dtrti2(char uplo, char diag, int n, double *a, int lda, int *info);
 void ora_dtrtri(char uplo, char diag, int n, double *a, int lda, int *info);
 void ora_dgetri(int n, double *a, int lda, const int *ipiv, double *work, int lwork, int *info);
 void ora_set_nb_getri(int nb);
+void ora_dgeqrt3(int m, int n, double *a, int lda, double *t, int ldt, int *info);
+void ora_dgeqrt(int m, int n, int nb, double *a, int lda, double *t, int ldt, double *work, int *info);
+void ora_dgemqrt(char side, char trans, int m, int n, int k, int nb, const double *v, int ldv, const double *t, int ldt,
+                 double *c, int ldc, double *work, int *info);
 void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
                 double *work, int *info);
 void ora_dormqr(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,

@@ -246,6 +246,25 @@ def dorgqr(a, tau, k=None):
 THRESH = 30.0
 
 
+def dgeqrt(a, nb):
+    """blocked QR with stored T factors (SRC/dgeqrt.f); returns (t [nb x min(m,n)], info)"""
+    m, n = a.shape
+    t = fmat(nb, max(1, min(m, n)))
+    work = np.zeros(max(1, nb * n))
+    info = C.c_int(0)
+    lib().ora_dgeqrt(m, n, nb, _d(a), _ld(a), _d(t), _ld(t), _d(work), C.byref(info))
+    return t, info.value
+
+
+def dgemqrt(side, trans, v, t, c, nb, k=None):
+    m, n = c.shape
+    k = t.shape[1] if k is None else k
+    work = np.zeros(max(1, (n if side.upper() == "L" else m) * nb))
+    info = C.c_int(0)
+    lib().ora_dgemqrt(_c(side), _c(trans), m, n, k, nb, _d(v), _ld(v), _d(t), _ld(t), _d(c), _ld(c), _d(work), C.byref(info))
+    return info.value
+
+
 def dtrtri(uplo, diag, a):
     info = C.c_int(0)
     lib().ora_dtrtri(_c(uplo), _c(diag), a.shape[0], _d(a), _ld(a), C.byref(info))

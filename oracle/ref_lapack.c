@@ -849,3 +849,74 @@ void ora_dgetri(int n, double *a, int lda, const int *ipiv, double *work, int lw
     }
     work[0] = (double)iws;
 }
+
+/* SRC/dgeqrt3.f:157-250 -- recursive QR of an m x n (m >= n) block with the compact-WY factor T (n x n upper). */
+void ora_dgeqrt3(int m, int n, double *a, int lda, double *t, int ldt, int *info)
+{
+    *info = 0;
+    if (n < 0) *info = -2; else if (m < n) *info = -1; else if (lda < imax(1, m)) *info = -4; else if (ldt < imax(1, n)) *info = -6;
+    if (*info != 0) return;
+    if (n == 1) {
+        ora_dlarfg(m, &A_(0, 0), &A_(imin(1, m - 1), 0), 1, &T_(0, 0));
+        return;
+    }
+    int n1 = n / 2, n2 = n - n1, j1 = imin(n1, n - 1), i1 = imin(n, m - 1), iinfo;     /* 0-based J1, I1 */
+    ora_dgeqrt3(m, n1, a, lda, t, ldt, &iinfo);
+    /* A(1:M,J1:N) = Q1^T A(1:M,J1:N), workspace T(1:N1,J1:N) */
+    for (int j = 0; j < n2; ++j) for (int i = 0; i < n1; ++i) T_(i, j + n1) = A_(i, j + n1);
+    ora_dtrmm('L', 'L', 'T', 'U', n1, n2, 1.0, a, lda, &T_(0, j1), ldt);
+    ora_dgemm('T', 'N', n1, n2, m - n1, 1.0, &A_(j1, 0), lda, &A_(j1, j1), lda, 1.0, &T_(0, j1), ldt);
+    ora_dtrmm('L', 'U', 'T', 'N', n1, n2, 1.0, t, ldt, &T_(0, j1), ldt);
+    ora_dgemm('N', 'N', m - n1, n2, n1, -1.0, &A_(j1, 0), lda, &T_(0, j1), ldt, 1.0, &A_(j1, j1), lda);
+    ora_dtrmm('L', 'L', 'N', 'U', n1, n2, 1.0, a, lda, &T_(0, j1), ldt);
+    for (int j = 0; j < n2; ++j) for (int i = 0; i < n1; ++i) A_(i, j + n1) = A_(i, j + n1) - T_(i, j + n1);
+    ora_dgeqrt3(m - n1, n2, &A_(j1, j1), lda, &T_(j1, j1), ldt, &iinfo);
+    /* T3 = T(1:N1,J1:N) = -T1 Y1^T Y2 T2 */
+    for (int i = 0; i < n1; ++i) for (int j = 0; j < n2; ++j) T_(i, j + n1) = A_(j + n1, i);
+    ora_dtrmm('R', 'L', 'N', 'U', n1, n2, 1.0, &A_(j1, j1), lda, &T_(0, j1), ldt);
+    ora_dgemm('T', 'N', n1, n2, m - n, 1.0, &A_(i1, 0), lda, &A_(i1, j1), lda, 1.0, &T_(0, j1), ldt);
+    ora_dtrmm('L', 'U', 'N', 'N', n1, n2, -1.0, t, ldt, &T_(0, j1), ldt);
+    ora_dtrmm('R', 'U', 'N', 'N', n1, n2, 1.0, &T_(j1, j1), ldt, &T_(0, j1), ldt);
+}
+
+/* SRC/dgeqrt.f:166-211 (USE_RECURSIVE_QR = .TRUE.): blocked QR keeping the T factors, T is nb x min(m,n). work: nb*n. */
+void ora_dgeqrt(int m, int n, int nb, double *a, int lda, double *t, int ldt, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2;
+    else if (nb < 1 || (nb > imin(m, n) && imin(m, n) > 0)) *info = -3;
+    else if (lda < imax(1, m)) *info = -5; else if (ldt < nb) *info = -7;
+    if (*info != 0) return;
+    int k = imin(m, n), iinfo;
+    if (k == 0) return;
+    for (int i = 0; i < k; i += nb) {
+        int ib = imin(k - i, nb);
+        ora_dgeqrt3(m - i, ib, &A_(i, i), lda, &T_(0, i), ldt, &iinfo);
+        if (i + ib < n)
+            ora_dlarfb('L', 'T', 'F', 'C', m - i, n - i - ib, ib, &A_(i, i), lda, &T_(0, i), ldt, &A_(i, i + ib), lda, work,
+                       n - i - ib);
+    }
+}
+
+/* SRC/dgemqrt.f:199-287 -- apply Q or Q^T from DGEQRT.  work: n*nb (SIDE='L') or m*nb ('R'). */
+void ora_dgemqrt(char side, char trans, int m, int n, int k, int nb, const double *v, int ldv, const double *t, int ldt,
+                 double *c, int ldc, double *work, int *info)
+{
+    int left = ora_lsame(side, 'L'), right = ora_lsame(side, 'R'), tran = ora_lsame(trans, 'T'), notran = ora_lsame(trans, 'N');
+    int ldwork = left ? imax(1, n) : imax(1, m), q = left ? m : n;
+    *info = 0;
+    if (!left && !right) *info = -1; else if (!tran && !notran) *info = -2; else if (m < 0) *info = -3; else if (n < 0) *info = -4;
+    else if (k < 0 || k > q) *info = -5; else if (nb < 1 || (nb > k && k > 0)) *info = -6;
+    else if (ldv < imax(1, q)) *info = -8; else if (ldt < nb) *info = -10; else if (ldc < imax(1, m)) *info = -12;
+    if (*info != 0) return;
+    if (m == 0 || n == 0 || k == 0) return;
+    int forward = (left && tran) || (right && notran);
+    int nblk = (k + nb - 1) / nb;
+    for (int b = 0; b < nblk; ++b) {
+        int i = forward ? b * nb : (nblk - 1 - b) * nb;
+        int ib = imin(nb, k - i);
+        const double *vi = v + (size_t)i + (size_t)i * ldv, *ti = t + (size_t)i * ldt;
+        if (left) ora_dlarfb('L', trans, 'F', 'C', m - i, n, ib, vi, ldv, ti, ldt, &c[i], ldc, work, ldwork);
+        else ora_dlarfb('R', trans, 'F', 'C', m, n - i, ib, vi, ldv, ti, ldt, &c[(size_t)i * ldc], ldc, work, ldwork);
+    }
+}

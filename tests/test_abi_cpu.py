@@ -148,6 +148,22 @@ def test_orgqr_ormqr_error_exits_and_query(lb):
     assert f.dormqr("L", "N", 0, 0, 0, A, 1, TAU, B, 1, wq, 1) == 0 and wq[0] == 1             # quick return, no GPU needed
 
 
+def test_geqrt_gemqrt_error_exits(lb):
+    """TESTING/LIN/derrqrt.f:117-130 (DGEQRT) and :168-199 (DGEMQRT)."""
+    f = lb.f77
+    T = np.zeros((4, 4), order="F")
+    for args, pos in (((-1, 0, 1, A, 1, T, 1, W), 1), ((0, -1, 1, A, 1, T, 1, W), 2), ((0, 0, 0, A, 1, T, 1, W), 3),
+                      ((2, 1, 1, A, 1, T, 1, W), 5), ((2, 2, 2, A, 2, T, 1, W), 7)):
+        assert expect(lb, lambda a=args: f.dgeqrt(*a), "DGEQRT", pos) == -pos
+    for args, pos in ((("/", "N", 0, 0, 0, 1, A, 1, T, 1, B, 1, W), 1), (("L", "/", 0, 0, 0, 1, A, 1, T, 1, B, 1, W), 2),
+                      (("L", "N", -1, 0, 0, 1, A, 1, T, 1, B, 1, W), 3), (("L", "N", 0, -1, 0, 1, A, 1, T, 1, B, 1, W), 4),
+                      (("L", "N", 0, 0, -1, 1, A, 1, T, 1, B, 1, W), 5), (("R", "N", 0, 0, -1, 1, A, 1, T, 1, B, 1, W), 5),
+                      (("L", "N", 0, 0, 0, 0, A, 1, T, 1, B, 1, W), 6), (("R", "N", 1, 2, 1, 1, A, 1, T, 1, B, 1, W), 8),
+                      (("L", "N", 2, 1, 1, 1, A, 1, T, 1, B, 1, W), 8), (("R", "N", 1, 1, 1, 1, A, 1, T, 0, B, 1, W), 10),
+                      (("L", "N", 1, 1, 1, 1, A, 1, T, 1, B, 0, W), 12)):
+        assert expect(lb, lambda a=args: f.dgemqrt(*a), "DGEMQRT", pos) == -pos
+
+
 def test_getri_error_exits_and_query(lb):
     """TESTING/LIN/derrge.f:157-165 (positions 1 and 3) plus the LWORK check and query of dgetri.f:152-170."""
     f = lb.f77

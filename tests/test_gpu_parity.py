@@ -551,6 +551,36 @@ def test_dlarft_dlarfb_vs_oracle(lb):
             assert rel(got, want) < 1e-11
 
 
+# ------------------------------------------------------------------------------------------- DGEQRT / DGEMQRT
+@pytest.mark.parametrize("m,n,nb", [(40, 40, 40), (300, 170, 32), (700, 700, 100), (1500, 520, 7), (200, 350, 64)])
+def test_dgeqrt_dgemqrt_vs_oracle(lb, m, n, nb):
+    a, _ = O.random_matrix(m, n, SEED)
+    k = min(m, n)
+    ref = a.copy(order="F")
+    t_ref, info = O.dgeqrt(ref, nb)
+    assert info == 0
+    got = a.copy(order="F")
+    t = np.full((nb, k), -1.0e10, order="F")
+    work = np.zeros(nb * n)
+    assert lb.f77.dgeqrt(m, n, nb, got, m, t, nb, work) == 0
+    assert rel(got, ref) < 1e-11
+    for i in range(0, k, nb):                                        # upper triangles of the T blocks; the rest is untouched
+        ib = min(nb, k - i)
+        blk, blk_ref = t[:ib, i:i + ib], t_ref[:ib, i:i + ib]
+        assert rel(np.triu(blk), np.triu(blk_ref)) < 1e-11
+        assert np.all(blk[np.tril_indices(ib, -1)] == -1.0e10)
+    nc = 9
+    for side in "LR":
+        c0, _ = O.random_matrix(m if side == "L" else nc, nc if side == "L" else m, (3, 5, 7, 9))
+        kk = k
+        for trans in "NT":
+            c = c0.copy(order="F")
+            assert lb.f77.gemqrt(side, trans, got, t, c, nb, kk) == 0
+            c_ref = c0.copy(order="F")
+            assert O.dgemqrt(side, trans, ref, t_ref, c_ref, nb, kk) == 0
+            assert rel(c, c_ref) < 1e-11, (side, trans)
+
+
 # ------------------------------------------------------------------------------------------- DGETRI
 @pytest.mark.parametrize("n", [1, 33, 300, 1100])
 def test_dgetri_vs_oracle(lb, n):

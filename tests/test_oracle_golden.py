@@ -266,3 +266,29 @@ def test_dgetri_dtrtri_netlib(n):
     before = x.copy()
     assert O.dgetri(x, ipiv) == 4
     assert np.array_equal(x, before)
+
+
+@pytest.mark.parametrize("tag", ["tall", "sq", "wide"])
+def test_dgeqrt_dgemqrt_netlib(tag):
+    """ora_dgeqrt (recursive DGEQRT3 panels) / ora_dgemqrt vs netlib 3.12.0 (tests/golden/make_golden_geqrt.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "netlib_golden_geqrt.npz"))
+    a, nb = np.asfortranarray(g[f"{tag}_a"]), int(g[f"{tag}_nb"])
+    m, n = a.shape
+    k = min(m, n)
+    x = a.copy(order="F")
+    t, info = O.dgeqrt(x, nb)
+    assert info == 0
+    assert np.max(np.abs(x - g[f"{tag}_qr"])) < 1e-12
+    for i in range(0, k, nb):                                    # only the upper triangles of the T blocks are defined
+        ib = min(nb, k - i)
+        assert np.max(np.abs(np.triu(t[:ib, i:i + ib]) - np.triu(g[f"{tag}_t"][:ib, i:i + ib]))) < 1e-12
+    for side, c0 in (("L", g[f"{tag}_cl"]), ("R", g[f"{tag}_cr"])):
+        for trans in "NT":
+            c = np.asfortranarray(c0.copy())
+            assert O.dgemqrt(side, trans, x, t, c, nb, k) == 0
+            assert np.max(np.abs(c - g[f"{tag}_gemqrt_{side}{trans}"])) < 1e-12
+    # same R, V as DGEQRF (the factorization is unique up to rounding)
+    y = a.copy(order="F")
+    tau, _, _ = O.dgeqrf(y)
+    assert np.max(np.abs(x - y)) < 1e-12
