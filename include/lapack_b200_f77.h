@@ -52,6 +52,12 @@ void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const in
 /* lapack.h:2991 (dgeqrf), dgeqr2, :10946 (dlarft), :10847 (dlarfb) */
 void dgeqrf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info);
 void dgeqr2_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, int* info);
+/* SRC/dgelqf.f:142 DGELQF, SRC/dormlq.f:165 DORMLQ, SRC/dgels.f:189 DGELS(TRANS,M,N,NRHS,A,LDA,B,LDB,WORK,LWORK,INFO) */
+void dgelqf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info);
+void dormlq_(const char* side, const char* trans, const int* m, const int* n, const int* k, const double* A, const int* lda,
+             const double* tau, double* C, const int* ldc, double* work, const int* lwork, int* info, size_t, size_t);
+void dgels_(const char* trans, const int* m, const int* n, const int* nrhs, double* A, const int* lda, double* B, const int* ldb,
+            double* work, const int* lwork, int* info, size_t);
 /* SRC/dgeqrt.f:139 DGEQRT(M,N,NB,A,LDA,T,LDT,WORK,INFO); SRC/dgemqrt.f:166 DGEMQRT(SIDE,TRANS,M,N,K,NB,V,LDV,T,LDT,C,LDC,WORK,INFO) */
 void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* lda, double* T, const int* ldt, double* work,
              int* info);

@@ -62,6 +62,11 @@ lapack_int LAPACKE_dgeqrf_work(int matrix_layout, lapack_int m, lapack_int n, do
 lapack_int LAPACKE_dgeqr2(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
 lapack_int LAPACKE_dgeqr2_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
                                double* work);
+/* LAPACKE_dgels / LAPACKE_dgels_work (LAPACKE/src/lapacke_dgels.c, lapacke_dgels_work.c) -- SURVEY 8f rank 4 */
+lapack_int LAPACKE_dgels(int matrix_layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a, lapack_int lda,
+                         double* b, lapack_int ldb);
+lapack_int LAPACKE_dgels_work(int matrix_layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a,
+                              lapack_int lda, double* b, lapack_int ldb, double* work, lapack_int lwork);
 /* lapacke.h:11369, 11526 (DGEQRT), 11348, 11505 (DGEMQRT) -- SURVEY 8f rank 4; row-major T is nb x k, ldt >= k */
 lapack_int LAPACKE_dgeqrt(int matrix_layout, lapack_int m, lapack_int n, lapack_int nb, double* a, lapack_int lda, double* t,
                           lapack_int ldt);

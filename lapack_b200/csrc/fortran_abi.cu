@@ -889,4 +889,187 @@ void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, c
     if (r) *info = r;
 }
 
+// ---- DGELQF / DORMLQ / DGELS (the main consumer of the QR path) ------------------------------------
+void dgelqf_(const int* m, const int* n, double* A, const int* lda, double* tau, double* work, const int* lwork, int* info) {
+    const int k = imin(*m, *n), nb = 32;
+    *info = 0;
+    const bool lquery = (*lwork == -1);
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *m)) *info = -4;
+    else if (!lquery) { if (*lwork <= 0 || (*n > 0 && *lwork < imax(1, *m))) *info = -7; }
+    if (*info != 0) { call_xerbla("DGELQF", -*info); return; }
+    if (lquery) { work[0] = (k == 0) ? 1.0 : (double)*m * nb; return; }              // dgelqf.f:189-197
+    if (k == 0) { work[0] = 1.0; return; }
+    if (!device_ok(info)) return;
+    {
+        std::lock_guard<std::mutex> lock(g_abi_mutex);
+        Ctx c; c.scan({A, tau});
+        lb::i64 la;
+        double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+        double* dt = c.vec<double>(tau, (size_t)k, false, true);
+        lb::gelqf(c.s, *m, *n, dA, la, dt);
+        int r = c.finish();
+        if (r) *info = r;
+    }
+    int iws = *m;
+    if (nb > 1 && nb < k && 128 < k) iws = *m * nb;                                     // dgelqf.f:207-231, NX = 128
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)iws;
+}
+
+void dormlq_(const char* side, const char* trans, const int* m, const int* n, const int* k, const double* A, const int* lda,
+             const double* tau, double* C, const int* ldc, double* work, const int* lwork, int* info, size_t, size_t) {
+    *info = 0;
+    const bool left = same(side, 'L'), notran = same(trans, 'N');
+    const bool lquery = (*lwork == -1);
+    const int nq = left ? *m : *n, nw = left ? imax(1, *n) : imax(1, *m);
+    if (!left && !same(side, 'R')) *info = -1;
+    else if (!notran && !same(trans, 'T')) *info = -2;
+    else if (*m < 0) *info = -3;
+    else if (*n < 0) *info = -4;
+    else if (*k < 0 || *k > nq) *info = -5;
+    else if (*lda < imax(1, *k)) *info = -7;
+    else if (*ldc < imax(1, *m)) *info = -10;
+    else if (*lwork < nw && !lquery) *info = -12;
+    if (*info != 0) { call_xerbla("DORMLQ", -*info); return; }
+    if (ptr_kind(work) != PK_DEVICE) work[0] = (double)(nw * 32 + 65 * 32);            // dormlq.f:238-242
+    if (lquery) return;
+    if (*m == 0 || *n == 0 || *k == 0) { if (ptr_kind(work) != PK_DEVICE) work[0] = 1.0; return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, tau, C});
+    lb::i64 la, lc;
+    const double* dA = c.mat(const_cast<double*>(A), *k, nq, *lda, true, false, &la);
+    const double* dt = c.vec<double>(const_cast<double*>(tau), (size_t)*k, true, false);
+    double* dC = c.mat(C, *m, *n, *ldc, true, true, &lc);
+    lb::ormlq(c.s, left ? 'L' : 'R', notran ? 'N' : 'T', *m, *n, *k, dA, la, dt, dC, lc);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+// DLASCL 'G' (SRC/dlascl.f:233-285): the multipliers are computed on the host exactly as the reference does, each step is one
+// scaling pass on the device
+static void dev_lascl(cudaStream_t s, double cfrom, double cto, int m, int n, double* dA, lb::i64 lda) {
+    if (m == 0 || n == 0) return;
+    const double smlnum = 2.2250738585072014e-308, bignum = 1.0 / smlnum;
+    double cfromc = cfrom, ctoc = cto;
+    for (;;) {
+        double cfrom1 = cfromc * smlnum, mul;
+        bool done;
+        if (cfrom1 == cfromc) { mul = ctoc / cfromc; done = true; }
+        else {
+            double cto1 = ctoc / bignum;
+            if (cto1 == ctoc) { mul = ctoc; done = true; cfromc = 1.0; }
+            else if (fabs(cfrom1) > fabs(ctoc) && ctoc != 0.0) { mul = smlnum; done = false; cfromc = cfrom1; }
+            else if (fabs(cto1) > fabs(cfromc)) { mul = bignum; done = false; ctoc = cto1; }
+            else { mul = ctoc / cfromc; done = true; if (mul == 1.0) return; }
+        }
+        lb::scale_matrix(s, m, n, mul, dA, lda);
+        if (done) break;
+    }
+}
+
+// first exactly-zero diagonal entry of a device triangular matrix (DTRTRS, dtrtrs.f:214-220); 0 if none.  Synchronises.
+static int dev_first_zero_diag(cudaStream_t s, int n, const double* dA, lb::i64 lda) {
+    std::vector<double> d((size_t)n);
+    LB_CUDA_CHECK(cudaMemcpy2DAsync(d.data(), 8, dA, (size_t)(lda + 1) * 8, 8, (size_t)n, cudaMemcpyDeviceToHost, s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) if (d[(size_t)i] == 0.0) return i + 1;
+    return 0;
+}
+
+void dgels_(const char* trans, const int* m, const int* n, const int* nrhs, double* A, const int* lda, double* B, const int* ldb,
+            double* work, const int* lwork, int* info, size_t) {
+    const int mn = imin(*m, *n);
+    const bool lquery = (*lwork == -1);
+    const bool tn = same(trans, 'N');
+    *info = 0;
+    if (!tn && !same(trans, 'T')) *info = -1;
+    else if (*m < 0) *info = -2;
+    else if (*n < 0) *info = -3;
+    else if (*nrhs < 0) *info = -4;
+    else if (*lda < imax(1, *m)) *info = -6;
+    else if (*ldb < imax(1, imax(*m, *n))) *info = -8;
+    else if (*lwork < imax(1, mn + imax(mn, *nrhs)) && !lquery) *info = -10;
+    const int wsize = imax(1, mn + imax(mn, *nrhs) * 32);                               // dgels.f:262-286, NB = 32
+    if ((*info == 0 || *info == -10) && ptr_kind(work) != PK_DEVICE) work[0] = (double)wsize;
+    if (*info != 0) { call_xerbla("DGELS ", -*info); return; }
+    if (lquery) return;
+    const int mx = imax(*m, *n);
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, B});
+    lb::i64 la, lbb;
+    double* dB = c.mat(B, mx, *nrhs, *ldb, true, true, &lbb);
+    if (imin(mn, *nrhs) == 0) {                                                          // dgels.f:297-300
+        if (mx > 0 && *nrhs > 0) lb::laset(c.s, 'A', mx, *nrhs, 0.0, 0.0, dB, lbb);
+        int r = c.finish();
+        if (r) *info = r;
+        return;
+    }
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    const bool tpsd = !tn;
+    const double smlnum = 2.2250738585072014e-308 / 2.220446049250313e-16, bignum = 1.0 / smlnum;   // DLAMCH('S')/DLAMCH('P')
+    const double anrm = lb::amax_abs(c.s, *m, *n, dA, la);
+    int iascl = 0, ibscl = 0, scllen = 0, hinfo = 0;
+    bool solved = true;
+    if (anrm > 0.0 && anrm < smlnum) { dev_lascl(c.s, anrm, smlnum, *m, *n, dA, la); iascl = 1; }
+    else if (anrm > bignum) { dev_lascl(c.s, anrm, bignum, *m, *n, dA, la); iascl = 2; }
+    else if (anrm == 0.0) {                                                              // dgels.f:326-333
+        lb::laset(c.s, 'A', mx, *nrhs, 0.0, 0.0, dB, lbb);
+        int r = c.finish();
+        if (r) *info = r;
+        if (ptr_kind(work) != PK_DEVICE) work[0] = (double)wsize;
+        return;
+    }
+    const int brow = tpsd ? *n : *m;
+    const double bnrm = lb::amax_abs(c.s, brow, *nrhs, dB, lbb);
+    if (bnrm > 0.0 && bnrm < smlnum) { dev_lascl(c.s, bnrm, smlnum, brow, *nrhs, dB, lbb); ibscl = 1; }
+    else if (bnrm > bignum) { dev_lascl(c.s, bnrm, bignum, brow, *nrhs, dB, lbb); ibscl = 2; }
+    double* dtau = (double*)lb::ws_alloc(c.s, sizeof(double) * (size_t)mn);
+    if (*m >= *n) {
+        lb::geqrf(c.s, *m, *n, dA, la, dtau);                                           // dgels.f:359
+        if (!tpsd) {
+            lb::ormqr(c.s, 'L', 'T', *m, *nrhs, *n, dA, la, dtau, dB, lbb);            // dgels.f:371
+            hinfo = dev_first_zero_diag(c.s, *n, dA, la);                               // DTRTRS, dgels.f:379
+            if (hinfo == 0) lb::trsm(c.s, 'L', 'U', 'N', 'N', *n, *nrhs, 1.0, dA, la, dB, lbb); else solved = false;
+            scllen = *n;
+        } else {
+            hinfo = dev_first_zero_diag(c.s, *n, dA, la);                               // dgels.f:395
+            if (hinfo == 0) {
+                lb::trsm(c.s, 'L', 'U', 'T', 'N', *n, *nrhs, 1.0, dA, la, dB, lbb);
+                if (*m > *n) lb::laset(c.s, 'A', *m - *n, *nrhs, 0.0, 0.0, dB + *n, lbb);               // dgels.f:404-408
+                lb::ormqr(c.s, 'L', 'N', *m, *nrhs, *n, dA, la, dtau, dB, lbb);        // dgels.f:412
+            } else solved = false;
+            scllen = *m;
+        }
+    } else {
+        lb::gelqf(c.s, *m, *n, dA, la, dtau);                                           // dgels.f:426
+        if (!tpsd) {
+            hinfo = dev_first_zero_diag(c.s, *m, dA, la);                               // dgels.f:438
+            if (hinfo == 0) {
+                lb::trsm(c.s, 'L', 'L', 'N', 'N', *m, *nrhs, 1.0, dA, la, dB, lbb);
+                lb::laset(c.s, 'A', *n - *m, *nrhs, 0.0, 0.0, dB + *m, lbb);                             // dgels.f:448-452
+                lb::ormlq(c.s, 'L', 'T', *n, *nrhs, *m, dA, la, dtau, dB, lbb);        // dgels.f:456
+            } else solved = false;
+            scllen = *n;
+        } else {
+            lb::ormlq(c.s, 'L', 'N', *n, *nrhs, *m, dA, la, dtau, dB, lbb);            // dgels.f:470
+            hinfo = dev_first_zero_diag(c.s, *m, dA, la);                               // dgels.f:478
+            if (hinfo == 0) lb::trsm(c.s, 'L', 'L', 'T', 'N', *m, *nrhs, 1.0, dA, la, dB, lbb); else solved = false;
+            scllen = *m;
+        }
+    }
+    if (solved) {                                                                        // dgels.f:494-509
+        if (iascl == 1) dev_lascl(c.s, anrm, smlnum, scllen, *nrhs, dB, lbb);
+        else if (iascl == 2) dev_lascl(c.s, anrm, bignum, scllen, *nrhs, dB, lbb);
+        if (ibscl == 1) dev_lascl(c.s, smlnum, bnrm, scllen, *nrhs, dB, lbb);
+        else if (ibscl == 2) dev_lascl(c.s, bignum, bnrm, scllen, *nrhs, dB, lbb);
+    }
+    lb::ws_free(c.s, dtau);
+    int r = c.finish();
+    *info = r ? r : hinfo;
+    if (solved && ptr_kind(work) != PK_DEVICE) work[0] = (double)wsize;
+}
+
 }  // extern "C"

@@ -21,8 +21,11 @@
 #include "lb_internal.h"
 #include <cfloat>
 #include <mutex>
+#include <cstring>
 
 namespace lb {
+
+static inline double __longlong_as_double_host(unsigned long long v) { double d; memcpy(&d, &v, 8); return d; }
 
 void expand_tri(cudaStream_t s, int n, const double* A, i64 lda, bool upper, bool unit, double* T, i64 ldt);
 
@@ -968,6 +971,50 @@ void gemqrt(cudaStream_t s, char side, char trans, int m, int n, int k, int nb, 
         if (left) larfb(s, 'L', trans, m - i, n, ib, Vi, ldv, Ti, ldt, C + i, ldc);
         else larfb(s, 'R', trans, m, n - i, ib, Vi, ldv, Ti, ldt, C + (i64)i * ldc, ldc);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LQ through QR of the transpose (for DGELS): A = L Q  <=>  A^T = Q^T L^T, so DGEQRF of A^T gives
+// R = L^T and the very reflectors DGELQF produces (SRC/dgelq2.f:165-183 runs DLARFG on the rows of A exactly as
+// DGEQR2 does on the columns of A^T); transposing the factored array back yields DGELQF's storage: L on and below the
+// diagonal, reflector i in row i to the right of the diagonal, same TAU.  The two transposes are HBM-bound passes.
+void gelqf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
+    if (m <= 0 || n <= 0) return;
+    const i64 ldt = ((i64)n + 1) & ~1LL;
+    double* At = (double*)ws_alloc(s, sizeof(double) * (size_t)ldt * m);
+    transpose(s, m, n, A, lda, At, ldt);
+    geqrf(s, n, m, At, ldt, tau);
+    transpose(s, n, m, At, ldt, A, lda);
+    ws_free(s, At);
+}
+
+// DORMLQ (SRC/dormlq.f): Q = H(k) ... H(1) with the reflectors in the rows of A (k x nq).  With V = A(1:k,1:nq)^T the
+// same reflectors are the columns of V and Q = (H(1) ... H(k))^T, so Q C = DORMQR('T') and Q^T C = DORMQR('N') on V.
+void ormlq(cudaStream_t s, char side, char trans, int m, int n, int k, const double* A, i64 lda, const double* tau, double* C,
+           i64 ldc) {
+    if (m <= 0 || n <= 0 || k <= 0) return;
+    const bool left = (side == 'L' || side == 'l');
+    const bool notran = (trans == 'N' || trans == 'n');
+    const int nq = left ? m : n;
+    const i64 ldv = ((i64)nq + 1) & ~1LL;
+    double* V = (double*)ws_alloc(s, sizeof(double) * (size_t)ldv * k);
+    transpose(s, k, nq, A, lda, V, ldv);
+    ormqr(s, side, notran ? 'T' : 'N', m, n, k, V, ldv, tau, C, ldc);
+    ws_free(s, V);
+}
+
+// max |a_ij| (DLANGE 'M' for finite data), returned on the host; synchronises the stream
+double amax_abs(cudaStream_t s, int m, int n, const double* A, i64 lda) {
+    if (m <= 0 || n <= 0) return 0.0;
+    unsigned long long* d = (unsigned long long*)ws_alloc(s, 64);
+    LB_CUDA_CHECK(cudaMemsetAsync(d, 0, 8, s));
+    amax_kernel<<<min(n, 4 * num_sms()), 256, 0, s>>>(m, n, A, lda, d);
+    count_launch();
+    unsigned long long h = 0;
+    LB_CUDA_CHECK(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, s));
+    LB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ws_free(s, d);
+    return __longlong_as_double_host(h);
 }
 
 }  // namespace lb

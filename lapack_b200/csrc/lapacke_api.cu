@@ -440,6 +440,54 @@ lapack_int LAPACKE_dgetri(int layout, lapack_int n, double* a, lapack_int lda, c
     return info;
 }
 
+// ------------------------------------------------------------------------------------------------ dgels
+// LAPACKE/src/lapacke_dgels_work.c:41-105, lapacke_dgels.c:36-82
+lapack_int LAPACKE_dgels_work(int layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a, lapack_int lda,
+                              double* b, lapack_int ldb, double* work, lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dgels_(&trans, &m, &n, &nrhs, a, &lda, b, &ldb, work, &lwork, &info, 1);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        const lapack_int mx = imax(m, n);
+        lapack_int lda_t = imax(1, m), ldb_t = imax(1, mx);
+        if (lda < n) { info = -7; lapacke_xerbla("LAPACKE_dgels_work", info); return info; }
+        if (ldb < nrhs) { info = -9; lapacke_xerbla("LAPACKE_dgels_work", info); return info; }
+        if (lwork == -1) {
+            dgels_(&trans, &m, &n, &nrhs, a, &lda_t, b, &ldb_t, work, &lwork, &info, 1);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor ra, rb;
+        if (!ra.in(a, m, n, lda) || !rb.in(b, mx, nrhs, ldb)) {
+            info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dgels_work", info); return info;
+        }
+        lda_t = imax(1, (int)ra.ldc); ldb_t = imax(1, (int)rb.ldc);
+        dgels_(&trans, &m, &n, &nrhs, ra.dev_cm ? ra.dev_cm : a, &lda_t, rb.dev_cm ? rb.dev_cm : b, &ldb_t, work, &lwork, &info, 1);
+        LB_ADJ(info);
+        ra.out();
+        rb.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dgels_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dgels(int layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a, lapack_int lda, double* b,
+                         lapack_int ldb) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dgels", -1); return -1; }
+    if (get_nancheck()) {
+        if (dge_nan(layout, m, n, a, lda)) return -6;
+        if (dge_nan(layout, imax(m, n), nrhs, b, ldb)) return -8;
+    }
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dgels_work(layout, trans, m, n, nrhs, a, lda, b, ldb, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dgels", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dgels_work(layout, trans, m, n, nrhs, a, lda, b, ldb, work, lwork);
+    free(work);
+    return info;
+}
+
 // ------------------------------------------------------------------------------------------------ dgeqrt / dgemqrt
 // LAPACKE/src/lapacke_dgeqrt_work.c:40-98, lapacke_dgeqrt.c:36-68, lapacke_dgemqrt_work.c:40-115, lapacke_dgemqrt.c:36-80.
 // Row-major operands are transposed on the GPU; row-major T is nb x k with ldt >= k (for DGEMQRT the reference checks

@@ -73,6 +73,11 @@ void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const dou
 void geqrt(cudaStream_t s, int m, int n, int nb, double* A, i64 lda, double* T, i64 ldt);
 void gemqrt(cudaStream_t s, char side, char trans, int m, int n, int k, int nb, const double* V, i64 ldv, const double* T,
             i64 ldt, double* C, i64 ldc);
+void gelqf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau);
+void ormlq(cudaStream_t s, char side, char trans, int m, int n, int k, const double* A, i64 lda, const double* tau, double* C,
+           i64 ldc);
+double amax_abs(cudaStream_t s, int m, int n, const double* A, i64 lda);   // host value; synchronises the stream
+void scale_matrix(cudaStream_t s, int m, int n, double alpha, double* B, i64 ldb);
 void ormqr(cudaStream_t s, char side, char trans, int m, int n, int k, const double* A, i64 lda, const double* tau,
            double* C, i64 ldc);
 void orgqr(cudaStream_t s, int m, int n, int k, double* A, i64 lda, const double* tau);

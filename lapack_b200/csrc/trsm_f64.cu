@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(256) trsm_left_lower_small_kernel(int m, int n
     }
 }
 
+void scale_matrix(cudaStream_t s, int m, int n, double alpha, double* B, i64 ldb) { scale_full(s, m, n, alpha, B, ldb); }
+
 static inline bool is(char c, char u) { return c == u || c == (char)(u + 32); }
 
 // split point: largest multiple of TB (power-of-two times TB preferred) not exceeding half, at least TB

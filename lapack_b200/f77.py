@@ -163,6 +163,58 @@ def geqrf(a):
     return tau[:min(m, n)], info, work[0]
 
 
+def dgelqf(m, n, a, lda, tau, work, lwork):
+    info = _i(0)
+    lib().dgelqf_(_r(m), _r(n), _p(a), _r(lda), _p(tau), _p(work), _r(lwork), C.byref(info))
+    return info.value
+
+
+def dormlq(side, trans, m, n, k, a, lda, tau, c, ldc, work, lwork):
+    info = _i(0)
+    lib().dormlq_(_c(side), _c(trans), _r(m), _r(n), _r(k), _p(a), _r(lda), _p(tau), _p(c), _r(ldc), _p(work), _r(lwork),
+                  C.byref(info), C.c_size_t(1), C.c_size_t(1))
+    return info.value
+
+
+def dgels(trans, m, n, nrhs, a, lda, b, ldb, work, lwork):
+    info = _i(0)
+    lib().dgels_(_c(trans), _r(m), _r(n), _r(nrhs), _p(a), _r(lda), _p(b), _r(ldb), _p(work), _r(lwork), C.byref(info),
+                 C.c_size_t(1))
+    return info.value
+
+
+def gelqf(a):
+    m, n = a.shape
+    tau = np.zeros(max(1, min(m, n)))
+    wq = np.zeros(1)
+    info = dgelqf(m, n, a, _ld(a), tau, wq, -1)
+    if info != 0:
+        return tau[:min(m, n)], info
+    work = np.zeros(max(1, int(wq[0])))
+    return tau[:min(m, n)], dgelqf(m, n, a, _ld(a), tau, work, len(work))
+
+
+def ormlq(side, trans, a, tau, c):
+    m, n = c.shape
+    wq = np.zeros(1)
+    info = dormlq(side, trans, m, n, len(tau), a, _ld(a), tau, c, _ld(c), wq, -1)
+    if info != 0:
+        return info
+    work = np.zeros(max(1, int(wq[0])))
+    return dormlq(side, trans, m, n, len(tau), a, _ld(a), tau, c, _ld(c), work, len(work))
+
+
+def gels(trans, a, b):
+    """a (m x n) is overwritten by its QR / LQ factors, b (max(m,n) x nrhs) by the solution; workspace query like the reference"""
+    m, n = a.shape
+    wq = np.zeros(1)
+    info = dgels(trans, m, n, b.shape[1], a, _ld(a), b, _ld(b), wq, -1)
+    if info != 0:
+        return info
+    work = np.zeros(max(1, int(wq[0])))
+    return dgels(trans, m, n, b.shape[1], a, _ld(a), b, _ld(b), work, len(work))
+
+
 def dgeqrt(m, n, nb, a, lda, t, ldt, work):
     info = _i(0)
     lib().dgeqrt_(_r(m), _r(n), _r(nb), _p(a), _r(lda), _p(t), _r(ldt), _p(work), C.byref(info))

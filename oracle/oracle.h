@@ -95,6 +95,12 @@ void ora_dgeqrt3(int m, int n, double *a, int lda, double *t, int ldt, int *info
 void ora_dgeqrt(int m, int n, int nb, double *a, int lda, double *t, int ldt, double *work, int *info);
 void ora_dgemqrt(char side, char trans, int m, int n, int k, int nb, const double *v, int ldv, const double *t, int ldt,
                  double *c, int ldc, double *work, int *info);
+void ora_dlascl_g(double cfrom, double cto, int m, int n, double *a, int lda);
+void ora_dtrtrs(char uplo, char trans, char diag, int n, int nrhs, const double *a, int lda, double *b, int ldb, int *info);
+void ora_dgelq2(int m, int n, double *a, int lda, double *tau, double *work, int *info);
+void ora_dorml2(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
+                double *work, int *info);
+void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b, int ldb, double *work, int lwork, int *info);
 void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
                 double *work, int *info);
 void ora_dormqr(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,

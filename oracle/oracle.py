@@ -265,6 +265,37 @@ def dgemqrt(side, trans, v, t, c, nb, k=None):
     return info.value
 
 
+def dgels(trans, a, b):
+    """least squares / minimum norm solve (SRC/dgels.f); a is overwritten by its QR / LQ factors, b (max(m,n) x nrhs) by the
+    solution"""
+    m, n = a.shape
+    nrhs = b.shape[1]
+    mn = min(m, n)
+    lwork = max(1, mn + max(mn, nrhs, m, n) * 32)
+    work = np.zeros(lwork)
+    info = C.c_int(0)
+    lib().ora_dgels(_c(trans), m, n, nrhs, _d(a), _ld(a), _d(b), _ld(b), _d(work), lwork, C.byref(info))
+    return info.value
+
+
+def dgelq2(a):
+    m, n = a.shape
+    tau = np.zeros(max(1, min(m, n)))
+    work = np.zeros(max(1, m))
+    info = C.c_int(0)
+    lib().ora_dgelq2(m, n, _d(a), _ld(a), _d(tau), _d(work), C.byref(info))
+    return tau[:min(m, n)], info.value
+
+
+def dorml2(side, trans, a, tau, c):
+    m, n = c.shape
+    work = np.zeros(max(1, m, n))
+    info = C.c_int(0)
+    lib().ora_dorml2(_c(side), _c(trans), m, n, len(tau), _d(a), _ld(a), _d(np.ascontiguousarray(tau)), _d(c), _ld(c), _d(work),
+                     C.byref(info))
+    return info.value
+
+
 def dtrtri(uplo, diag, a):
     info = C.c_int(0)
     lib().ora_dtrtri(_c(uplo), _c(diag), a.shape[0], _d(a), _ld(a), C.byref(info))

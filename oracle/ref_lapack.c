@@ -920,3 +920,142 @@ void ora_dgemqrt(char side, char trans, int m, int n, int k, int nb, const doubl
         else ora_dlarfb('R', trans, 'F', 'C', m, n - i, ib, vi, ldv, ti, ldt, &c[(size_t)i * ldc], ldc, work, ldwork);
     }
 }
+
+/* SRC/dlascl.f:233-285, TYPE = 'G' only: A := A * (cto/cfrom) without over/underflow (stepwise by SMLNUM / BIGNUM). */
+void ora_dlascl_g(double cfrom, double cto, int m, int n, double *a, int lda)
+{
+    if (m == 0 || n == 0) return;
+    const double smlnum = 2.2250738585072014e-308, bignum = 1.0 / smlnum;       /* DLAMCH('S') */
+    double cfromc = cfrom, ctoc = cto;
+    for (;;) {
+        double cfrom1 = cfromc * smlnum, mul;
+        int done;
+        if (cfrom1 == cfromc) { mul = ctoc / cfromc; done = 1; }
+        else {
+            double cto1 = ctoc / bignum;
+            if (cto1 == ctoc) { mul = ctoc; done = 1; cfromc = 1.0; }
+            else if (fabs(cfrom1) > fabs(ctoc) && ctoc != 0.0) { mul = smlnum; done = 0; cfromc = cfrom1; }
+            else if (fabs(cto1) > fabs(cfromc)) { mul = bignum; done = 0; ctoc = cto1; }
+            else { mul = ctoc / cfromc; done = 1; if (mul == 1.0) return; }
+        }
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) A_(i, j) = A_(i, j) * mul;
+        if (done) break;
+    }
+}
+
+/* SRC/dtrtrs.f:181-224: INFO = i if A(i,i) is exactly zero (non-unit), otherwise one DTRSM. */
+void ora_dtrtrs(char uplo, char trans, char diag, int n, int nrhs, const double *a, int lda, double *b, int ldb, int *info)
+{
+    *info = 0;
+    if (n == 0) return;
+    if (ora_lsame(diag, 'N'))
+        for (int i = 0; i < n; ++i) if (A_(i, i) == 0.0) { *info = i + 1; return; }
+    ora_dtrsm('L', uplo, trans, diag, n, nrhs, 1.0, a, lda, b, ldb);
+}
+
+/* SRC/dgelq2.f:140-188 -- unblocked LQ.  (SRC/dgelqf.f switches to the blocked DLARFT/DLARFB 'Rowwise' form for
+   k > NX = 128; the factorization is the same up to rounding, so the oracle uses this form at every size.) */
+void ora_dgelq2(int m, int n, double *a, int lda, double *tau, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    if (*info != 0) return;
+    int k = imin(m, n);
+    for (int i = 0; i < k; ++i) {
+        ora_dlarfg(n - i, &A_(i, i), &A_(i, imin(i + 1, n - 1)), lda, &tau[i]);
+        if (i < m - 1) ora_dlarf1f('R', m - i - 1, n - i, &A_(i, i), lda, tau[i], &A_(i + 1, i), lda, work);
+    }
+}
+
+/* SRC/dorml2.f:215-266 -- apply Q or Q^T from DGELQF, Q = H(k) ... H(1), reflectors stored in the rows of A. */
+void ora_dorml2(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
+                double *work, int *info)
+{
+    int left = ora_lsame(side, 'L'), notran = ora_lsame(trans, 'N');
+    int nq = left ? m : n;
+    *info = 0;
+    if (!left && !ora_lsame(side, 'R')) *info = -1; else if (!notran && !ora_lsame(trans, 'T')) *info = -2;
+    else if (m < 0) *info = -3; else if (n < 0) *info = -4; else if (k < 0 || k > nq) *info = -5;
+    else if (lda < imax(1, k)) *info = -7; else if (ldc < imax(1, m)) *info = -10;
+    if (*info != 0) return;
+    if (m == 0 || n == 0 || k == 0) return;
+    int forward = (left && notran) || (!left && !notran);
+    for (int t = 0; t < k; ++t) {
+        int i = forward ? t : k - 1 - t;
+        if (left) ora_dlarf1f('L', m - i, n, &A_(i, i), lda, tau[i], &c[i], ldc, work);
+        else ora_dlarf1f('R', m, n - i, &A_(i, i), lda, tau[i], &c[(size_t)i * ldc], ldc, work);
+    }
+}
+
+/* SRC/dgels.f:238-514 -- least squares / minimum norm solution with QR (m >= n) or LQ (m < n), full rank assumed.
+   work: mn + max(mn, nrhs, n, m) doubles are enough for the unblocked kernels used here. */
+void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b, int ldb, double *work, int lwork, int *info)
+{
+    int mn = imin(m, n), lquery = (lwork == -1);
+    int tn = ora_lsame(trans, 'N');
+    *info = 0;
+    if (!tn && !ora_lsame(trans, 'T')) *info = -1; else if (m < 0) *info = -2; else if (n < 0) *info = -3;
+    else if (nrhs < 0) *info = -4; else if (lda < imax(1, m)) *info = -6; else if (ldb < imax(1, imax(m, n))) *info = -8;
+    else if (lwork < imax(1, mn + imax(mn, nrhs)) && !lquery) *info = -10;
+    int nb = 32;                                                       /* ilaenv.f: DGEQRF/DGELQF/DORMQR/DORMLQ */
+    int wsize = imax(1, mn + imax(mn, nrhs) * nb);
+    if (*info == 0 || *info == -10) work[0] = (double)wsize;
+    if (*info != 0 || lquery) return;
+    int tpsd = !tn;
+#define B_(i, j) b[(size_t)(i) + (size_t)(j) * ldb]
+    if (imin(imin(m, n), nrhs) == 0) {
+        for (int j = 0; j < nrhs; ++j) for (int i = 0; i < imax(m, n); ++i) B_(i, j) = 0.0;
+        return;
+    }
+    const double smlnum = 2.2250738585072014e-308 / 2.220446049250313e-16, bignum = 1.0 / smlnum;   /* 'S' / 'P' */
+    double anrm = ora_dlange('M', m, n, a, lda);
+    int iascl = 0, ibscl = 0, scllen = 0, iinfo;
+    if (anrm > 0.0 && anrm < smlnum) { ora_dlascl_g(anrm, smlnum, m, n, a, lda); iascl = 1; }
+    else if (anrm > bignum) { ora_dlascl_g(anrm, bignum, m, n, a, lda); iascl = 2; }
+    else if (anrm == 0.0) {
+        for (int j = 0; j < nrhs; ++j) for (int i = 0; i < imax(m, n); ++i) B_(i, j) = 0.0;
+        work[0] = (double)wsize;
+        return;
+    }
+    int brow = tpsd ? n : m;
+    double bnrm = ora_dlange('M', brow, nrhs, b, ldb);
+    if (bnrm > 0.0 && bnrm < smlnum) { ora_dlascl_g(bnrm, smlnum, brow, nrhs, b, ldb); ibscl = 1; }
+    else if (bnrm > bignum) { ora_dlascl_g(bnrm, bignum, brow, nrhs, b, ldb); ibscl = 2; }
+    double *tau = work, *w2 = work + mn;
+    int lw2 = lwork - mn;
+    if (m >= n) {
+        ora_dgeqrf(m, n, a, lda, tau, w2, lw2, &iinfo);
+        if (!tpsd) {
+            ora_dormqr('L', 'T', m, nrhs, n, a, lda, tau, b, ldb, w2, lw2, &iinfo);
+            ora_dtrtrs('U', 'N', 'N', n, nrhs, a, lda, b, ldb, info);
+            if (*info > 0) return;
+            scllen = n;
+        } else {
+            ora_dtrtrs('U', 'T', 'N', n, nrhs, a, lda, b, ldb, info);
+            if (*info > 0) return;
+            for (int j = 0; j < nrhs; ++j) for (int i = n; i < m; ++i) B_(i, j) = 0.0;
+            ora_dormqr('L', 'N', m, nrhs, n, a, lda, tau, b, ldb, w2, lw2, &iinfo);
+            scllen = m;
+        }
+    } else {
+        ora_dgelq2(m, n, a, lda, tau, w2, &iinfo);
+        if (!tpsd) {
+            ora_dtrtrs('L', 'N', 'N', m, nrhs, a, lda, b, ldb, info);
+            if (*info > 0) return;
+            for (int j = 0; j < nrhs; ++j) for (int i = m; i < n; ++i) B_(i, j) = 0.0;
+            ora_dorml2('L', 'T', n, nrhs, m, a, lda, tau, b, ldb, w2, &iinfo);
+            scllen = n;
+        } else {
+            ora_dorml2('L', 'N', n, nrhs, m, a, lda, tau, b, ldb, w2, &iinfo);
+            ora_dtrtrs('L', 'T', 'N', m, nrhs, a, lda, b, ldb, info);
+            if (*info > 0) return;
+            scllen = m;
+        }
+    }
+    if (iascl == 1) ora_dlascl_g(anrm, smlnum, scllen, nrhs, b, ldb);
+    else if (iascl == 2) ora_dlascl_g(anrm, bignum, scllen, nrhs, b, ldb);
+    if (ibscl == 1) ora_dlascl_g(smlnum, bnrm, scllen, nrhs, b, ldb);
+    else if (ibscl == 2) ora_dlascl_g(bignum, bnrm, scllen, nrhs, b, ldb);
+#undef B_
+    work[0] = (double)wsize;
+}

@@ -164,6 +164,29 @@ def test_geqrt_gemqrt_error_exits(lb):
         assert expect(lb, lambda a=args: f.dgemqrt(*a), "DGEMQRT", pos) == -pos
 
 
+def test_gels_gelqf_ormlq_error_exits_and_query(lb):
+    """TESTING/LIN/derrls.f:117-139 (DGELS), derrlq.f (DGELQF / DORMLQ positions as in dgelqf.f:172-186, dormlq.f:218-236)."""
+    f = lb.f77
+    for args, pos in ((("/", 0, 0, 0, A, 1, B, 1, W, 1), 1), (("N", -1, 0, 0, A, 1, B, 1, W, 1), 2),
+                      (("N", 0, -1, 0, A, 1, B, 1, W, 1), 3), (("N", 0, 0, -1, A, 1, B, 1, W, 1), 4),
+                      (("N", 2, 0, 0, A, 1, B, 2, W, 2), 6), (("N", 2, 0, 0, A, 2, B, 1, W, 2), 8),
+                      (("N", 0, 2, 0, A, 1, B, 1, W, 2), 8), (("N", 1, 1, 0, A, 1, B, 1, W, 1), 10)):
+        assert expect(lb, lambda a=args: f.dgels(*a), "DGELS", pos) == -pos
+    assert expect(lb, lambda: f.dgelqf(-1, 0, A, 1, TAU, W, 1), "DGELQF", 1) == -1
+    assert expect(lb, lambda: f.dgelqf(0, -1, A, 1, TAU, W, 1), "DGELQF", 2) == -2
+    assert expect(lb, lambda: f.dgelqf(2, 1, A, 1, TAU, W, 2), "DGELQF", 4) == -4
+    assert expect(lb, lambda: f.dgelqf(2, 1, A, 2, TAU, W, 1), "DGELQF", 7) == -7
+    assert expect(lb, lambda: f.dormlq("/", "N", 0, 0, 0, A, 1, TAU, B, 1, W, 1), "DORMLQ", 1) == -1
+    assert expect(lb, lambda: f.dormlq("L", "N", 0, 1, 1, A, 1, TAU, B, 1, W, 1), "DORMLQ", 5) == -5
+    assert expect(lb, lambda: f.dormlq("L", "N", 2, 0, 2, A, 1, TAU, B, 2, W, 1), "DORMLQ", 7) == -7
+    assert expect(lb, lambda: f.dormlq("L", "N", 2, 1, 0, A, 1, TAU, B, 1, W, 1), "DORMLQ", 10) == -10
+    assert expect(lb, lambda: f.dormlq("L", "N", 1, 2, 0, A, 1, TAU, B, 1, W, 1), "DORMLQ", 12) == -12
+    wq = np.zeros(1)
+    assert f.dgels("N", 300, 200, 7, A, 300, B, 300, wq, -1) == 0 and wq[0] == 200 + 200 * 32      # dgels.f:284-285
+    assert f.dgelqf(200, 300, A, 200, TAU, wq, -1) == 0 and wq[0] == 200 * 32
+    assert f.dormlq("L", "T", 300, 7, 200, A, 200, TAU, B, 300, wq, -1) == 0 and wq[0] == 7 * 32 + 65 * 32
+
+
 def test_getri_error_exits_and_query(lb):
     """TESTING/LIN/derrge.f:157-165 (positions 1 and 3) plus the LWORK check and query of dgetri.f:152-170."""
     f = lb.f77

@@ -149,3 +149,21 @@ def test_lapacke_dgetri(libs, layout):
         buf = np.array(lu, order="C" if layout == ROW else "F", copy=True)
         assert L.LAPACKE_dgetri(layout, n, vp(buf), n, vp(ipiv)) == 0, name
         assert np.max(np.abs(buf - ref)) < 1e-10 * np.max(np.abs(ref)), name
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dgels(libs, layout):
+    for (m, n, nrhs, trans) in ((150, 80, 3, b"N"), (80, 150, 2, b"N"), (150, 80, 2, b"T")):
+        a, _ = O.random_matrix(m, n, SEED)
+        b, _ = O.random_matrix(max(m, n), nrhs, (3, 5, 7, 9))
+        a_ref, x_ref = a.copy(order="F"), b.copy(order="F")
+        assert O.dgels(trans.decode(), a_ref, x_ref) == 0
+        rows = n if trans == b"N" else m
+        order = "C" if layout == ROW else "F"
+        for name, L in libs:
+            L.LAPACKE_dgels.argtypes = [C.c_int, C.c_char, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            abuf, bbuf = np.array(a, order=order, copy=True), np.array(b, order=order, copy=True)
+            rc = L.LAPACKE_dgels(layout, trans, m, n, nrhs, vp(abuf), n if layout == ROW else m, vp(bbuf),
+                                 nrhs if layout == ROW else max(m, n))
+            assert rc == 0, name
+            assert np.max(np.abs(bbuf[:rows] - x_ref[:rows])) < 1e-10 * np.max(np.abs(x_ref[:rows])), (name, m, n, trans)

@@ -551,6 +551,69 @@ def test_dlarft_dlarfb_vs_oracle(lb):
             assert rel(got, want) < 1e-11
 
 
+# ------------------------------------------------------------------------------------------- DGELQF / DORMLQ / DGELS
+@pytest.mark.parametrize("shape", [(40, 40), (170, 300), (300, 170), (520, 1500)])
+def test_dgelqf_dormlq_vs_oracle(lb, shape):
+    m, n = shape
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    tau_ref, info = O.dgelq2(ref)
+    got = a.copy(order="F")
+    tau, info = lb.f77.gelqf(got)
+    assert info == 0
+    assert rel(tau, tau_ref) < 1e-11 and rel(got, ref) < 1e-11
+    nc = 7
+    k = min(m, n)
+    for side in "LR":
+        c0, _ = O.random_matrix(n if side == "L" else nc, nc if side == "L" else n, (3, 5, 7, 9))
+        for trans in "NT":
+            c = c0.copy(order="F")
+            assert lb.f77.ormlq(side, trans, got[:k, :], tau, c) == 0
+            c_ref = c0.copy(order="F")
+            assert O.dorml2(side, trans, np.asfortranarray(ref[:k, :]), tau_ref, c_ref) == 0
+            assert rel(c, c_ref) < 1e-11, (side, trans)
+
+
+@pytest.mark.parametrize("m,n,nrhs", [(300, 170, 3), (170, 300, 2), (200, 200, 1), (1500, 520, 4), (520, 1500, 4)])
+@pytest.mark.parametrize("trans", "NT")
+def test_dgels_vs_oracle(lb, m, n, nrhs, trans):
+    a, _ = O.random_matrix(m, n, SEED)
+    b, _ = O.random_matrix(max(m, n), nrhs, (3, 5, 7, 9))
+    a_ref, x_ref = a.copy(order="F"), b.copy(order="F")
+    assert O.dgels(trans, a_ref, x_ref) == 0
+    a_got, x = a.copy(order="F"), b.copy(order="F")
+    assert lb.f77.gels(trans, a_got, x) == 0
+    rows = n if trans == "N" else m
+    assert rel(x[:rows], x_ref[:rows]) < 1e-10
+    assert rel(a_got, a_ref) < 1e-10                                  # the QR / LQ factors are returned in A
+    # least-squares optimality / consistency, independent of the oracle
+    op = a if trans == "N" else a.T
+    rhs = b[:op.shape[0]]
+    r = op @ x[:rows] - rhs
+    if op.shape[0] >= op.shape[1]:
+        assert np.max(np.abs(op.T @ r)) < 1e-9 * np.max(np.abs(op)) * np.max(np.abs(rhs)) * max(m, n)    # normal equations
+    else:
+        assert np.max(np.abs(r)) < 1e-10 * np.max(np.abs(rhs)) * max(m, n)                               # exact solve
+
+
+def test_dgels_scaling_and_rank_deficiency(lb):
+    m, n, nrhs = 200, 90, 2
+    a, _ = O.random_matrix(m, n, SEED)
+    b, _ = O.random_matrix(m, nrhs, (3, 5, 7, 9))
+    for sa, sb in ((1e-300, 1.0), (1e300, 1.0), (1.0, 1e-300), (1.0, 1e300)):       # dgels.f:309-353
+        a_ref, x_ref = (a * sa).copy(order="F"), (b * sb).copy(order="F")
+        assert O.dgels("N", a_ref, x_ref) == 0
+        a_got, x = (a * sa).copy(order="F"), (b * sb).copy(order="F")
+        assert lb.f77.gels("N", a_got, x) == 0
+        assert rel(x[:n], x_ref[:n]) < 1e-10, (sa, sb)
+    a0 = a.copy(order="F")
+    a0[:, 6] = 0.0                                                                  # R(7,7) = 0 exactly: INFO = 7 from DTRTRS
+    assert lb.f77.gels("N", a0, b.copy(order="F")) == 7
+    z = np.zeros((m, n), order="F")                                                 # zero matrix: zero solution (dgels.f:326-333)
+    x = b.copy(order="F")
+    assert lb.f77.gels("N", z, x) == 0 and np.all(x == 0.0)
+
+
 # ------------------------------------------------------------------------------------------- DGEQRT / DGEMQRT
 @pytest.mark.parametrize("m,n,nb", [(40, 40, 40), (300, 170, 32), (700, 700, 100), (1500, 520, 7), (200, 350, 64)])
 def test_dgeqrt_dgemqrt_vs_oracle(lb, m, n, nb):

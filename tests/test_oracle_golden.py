@@ -292,3 +292,29 @@ def test_dgeqrt_dgemqrt_netlib(tag):
     y = a.copy(order="F")
     tau, _, _ = O.dgeqrf(y)
     assert np.max(np.abs(x - y)) < 1e-12
+
+
+def test_dgels_netlib():
+    """ora_dgels (QR and LQ paths, both TRANS, scaling branches, rank deficiency) vs netlib 3.12.0
+    (tests/golden/make_golden_gels.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "netlib_golden_gels.npz"))
+    for tag in ("tall", "wide", "sq"):
+        a, b = np.asfortranarray(g[f"{tag}_a"]), np.asfortranarray(g[f"{tag}_b"])
+        m, n = a.shape
+        for trans in "NT":
+            af, x = a.copy(order="F"), b.copy(order="F")
+            assert O.dgels(trans, af, x) == 0
+            rows = n if trans == "N" else m
+            assert np.max(np.abs(x[:rows] - g[f"{tag}_{trans}_x"][:rows])) < 1e-12
+            assert np.max(np.abs(af - g[f"{tag}_{trans}_af"])) < 1e-12        # QR / LQ factors (DGELQ2 == DGELQF up to rounding)
+    a, b = np.asfortranarray(g["tall_a"]), np.asfortranarray(g["tall_b"])
+    for k in range(4):
+        sa, sb = g[f"scale{k}_s"]
+        af, x = (a * sa).copy(order="F"), (b * sb).copy(order="F")
+        assert O.dgels("N", af, x) == 0
+        ref = g[f"scale{k}_x"][:40]
+        assert np.max(np.abs(x[:40] - ref)) <= 1e-12 * np.max(np.abs(ref))
+    a0 = a.copy(order="F")
+    a0[:, 4] = 0.0
+    assert O.dgels("N", a0, b.copy(order="F")) == int(g["rankdef_info"]) == 5
