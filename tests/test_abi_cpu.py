@@ -21,12 +21,12 @@ def lb():
 
 def declared_symbols():
     names = set()
-    for h in ("lapack_b200.h", "lapack_b200_f77.h", "lapack_b200_lapacke.h", "lapack_b200_cblas.h"):
+    for h in ("lapack_b200.h", "lapack_b200_f77.h", "lapack_b200_f77_64.h", "lapack_b200_lapacke.h", "lapack_b200_cblas.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        for m in re.finditer(r"\b(lb200_\w+|LAPACKE_\w+|cblas_\w+|[a-z0-9]+_)\s*\(", src):
+        for m in re.finditer(r"\b(lb200_\w+|LAPACKE_\w+|cblas_\w+|[a-z0-9]+(?:_64)?_)\s*\(", src):
             n = m.group(1)
-            if n.startswith(("lb200_", "LAPACKE_", "cblas_")) or re.fullmatch(r"(d[a-z0-9]+|xerbla|lsame)_", n):
+            if n.startswith(("lb200_", "LAPACKE_", "cblas_")) or re.fullmatch(r"(d[a-z0-9]+|xerbla|lsame)(_64)?_", n):
                 names.add(n)
     return sorted(names)
 
@@ -275,3 +275,30 @@ def test_cblas_illegal_enums_need_no_gpu(lb, capfd):
     assert "Parameter 2 to routine cblas_dgemm" in err and "Parameter 1 to routine cblas_dgemm" in err
     assert "Parameter 5 to routine cblas_dtrsm" in err
     assert np.all(c == 5.0)
+
+
+def test_ilp64_entry_points_narrow_and_report(lb):
+    """include/lapack_b200_f77_64.h: the _64 symbols forward to the 32-bit-index routines; the reference's own argument
+    errors come back widened, and a dimension that does not fit in 32 bits is reported at its argument position."""
+    L = lb.lib()
+    i64 = C.c_int64
+    a = np.zeros((4, 4), order="F")
+    ip = np.zeros(4, dtype=np.int64)
+    info = i64(7)
+
+    def getrf64(m, n, lda):
+        L.dgetrf_64_(C.byref(i64(m)), C.byref(i64(n)), a.ctypes.data_as(C.c_void_p), C.byref(i64(lda)),
+                     ip.ctypes.data_as(C.c_void_p), C.byref(info))
+        return info.value
+
+    assert expect(lb, lambda: getrf64(-1, 0, 1), "DGETRF", 1) == -1
+    assert expect(lb, lambda: getrf64(2, 1, 1), "DGETRF", 4) == -4
+    assert expect(lb, lambda: getrf64(1 << 40, 1, 1 << 40), "DGETRF", 1) == -1          # does not fit in 32 bits
+    assert getrf64(0, 0, 1) == 0                                                        # quick return, no GPU needed
+    L.lb200_clear_xerbla()
+    one = C.c_double(1.0)
+    L.dgemm_64_(b"N", b"N", C.byref(i64(1 << 33)), C.byref(i64(1)), C.byref(i64(1)), C.byref(one), a.ctypes.data_as(C.c_void_p),
+                C.byref(i64(1 << 33)), a.ctypes.data_as(C.c_void_p), C.byref(i64(1)), C.byref(one), a.ctypes.data_as(C.c_void_p),
+                C.byref(i64(1 << 33)), C.c_size_t(1), C.c_size_t(1))
+    name, pos, cnt = _last(lb)
+    assert (name, pos, cnt) == ("DGEMM", 3, 1)

@@ -845,3 +845,41 @@ def test_fortran_abi_from_several_host_threads(lb):
         else:
             s, f, info = out[t]
             assert info == 0 and O.dpot01("L", s, f) < O.THRESH
+
+
+def test_ilp64_api_matches_32bit(lb):
+    """_64 entry points (64-bit INTEGER, 64-bit IPIV) give exactly the results of the 32-bit ones."""
+    import ctypes as C
+    L = lb.lib()
+    i64 = C.c_int64
+    vp = lambda x: x.ctypes.data_as(C.c_void_p)
+    n, nrhs = 300, 3
+    a, seed = O.random_matrix(n, n, SEED)
+    xt, _ = O.random_matrix(n, nrhs, seed)
+    b = np.asfortranarray(a @ xt)
+    lu32 = a.copy(order="F")
+    piv32, info32 = lb.f77.getrf(lu32)
+    lu64, piv64, info = a.copy(order="F"), np.zeros(n, dtype=np.int64), i64(-9)
+    L.dgetrf_64_(C.byref(i64(n)), C.byref(i64(n)), vp(lu64), C.byref(i64(n)), vp(piv64), C.byref(info))
+    assert info.value == info32 == 0 and np.array_equal(piv64, piv32) and np.array_equal(lu64, lu32)
+    x64 = b.copy(order="F")
+    L.dgetrs_64_(b"N", C.byref(i64(n)), C.byref(i64(nrhs)), vp(lu64), C.byref(i64(n)), vp(piv64), vp(x64), C.byref(i64(n)),
+                 C.byref(info), C.c_size_t(1))
+    assert info.value == 0 and rel(x64, xt) < 1e-10
+    s, _ = O.spd_matrix(n, SEED)
+    f32, f64 = s.copy(order="F"), s.copy(order="F")
+    assert lb.f77.potrf("L", f32) == 0
+    L.dpotrf_64_(b"L", C.byref(i64(n)), vp(f64), C.byref(i64(n)), C.byref(info), C.c_size_t(1))
+    assert info.value == 0 and np.array_equal(f64, f32)
+    c32, c64 = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+    one, zero = C.c_double(1.0), C.c_double(0.0)
+    lb.f77.dgemm("N", "T", n, n, n, 1.0, a, n, s, n, 0.0, c32, n)
+    L.dgemm_64_(b"N", b"T", C.byref(i64(n)), C.byref(i64(n)), C.byref(i64(n)), C.byref(one), vp(a), C.byref(i64(n)), vp(s),
+                C.byref(i64(n)), C.byref(zero), vp(c64), C.byref(i64(n)), C.c_size_t(1), C.c_size_t(1))
+    assert np.array_equal(c64, c32)
+    q32, q64 = a.copy(order="F"), a.copy(order="F")
+    tau32, _, _ = lb.f77.geqrf(q32)
+    tau64, work = np.zeros(n), np.zeros(n * 32)
+    L.dgeqrf_64_(C.byref(i64(n)), C.byref(i64(n)), vp(q64), C.byref(i64(n)), vp(tau64), vp(work), C.byref(i64(len(work))),
+                 C.byref(info))
+    assert info.value == 0 and np.array_equal(q64, q32) and np.array_equal(tau64, tau32)
