@@ -24,6 +24,8 @@ def _p(a):
 def _ld(a):
     if a.ndim == 1:
         return max(1, a.shape[0])
+    if a.size == 0:
+        return max(1, a.shape[0])
     assert a.shape[0] <= 1 or a.strides[0] == a.itemsize, "column-major (order='F') array expected"
     return max(1, a.strides[1] // a.itemsize, a.shape[0]) if a.shape[1] > 1 else max(1, a.shape[0])
 

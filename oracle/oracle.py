@@ -58,6 +58,8 @@ def _ld(a: np.ndarray) -> int:
     """Leading dimension of a Fortran-ordered 2-D array (or a column-major view of one)."""
     if a.ndim == 1:
         return max(1, a.shape[0])
+    if a.size == 0:
+        return max(1, a.shape[0])
     assert a.shape[0] <= 1 or a.strides[0] == 8, "oracle expects column-major (order='F') arrays"
     return max(1, a.strides[1] // 8, a.shape[0]) if a.shape[1] > 1 else max(1, a.shape[0])
 

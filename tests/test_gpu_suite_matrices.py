@@ -128,3 +128,59 @@ def test_qr_types(lb, nb):
                 assert rel(tau, tau_ref) < 1e-10, key
     finally:
         L.lb200_set_geqrf_params(256, 1)
+
+
+@pytest.mark.parametrize("nb", [1, 3, 20])
+def test_tiny_shape_sweep(lb, nb):
+    """The reference test programs sweep M, N in {0, 1, 2, 3, 5, 10, 50} with NB in {1, 3, 20} (TESTING/dtest.in); every
+    combination through LU, QR (+ DORGQR), LQ and, for square sizes, Cholesky, against the oracle."""
+    L = lb.lib()
+    L.lb200_set_getrf_params(nb, 0, 1)
+    L.lb200_set_potrf_params(nb, 1)
+    L.lb200_set_geqrf_params(nb, 1)
+    try:
+        for m in (0, 1, 2, 3, 5, 10, 50):
+            for n in (0, 1, 2, 3, 5, 10, 50):
+                a, _ = O.random_matrix(m, n, (1988, 1989, 1990, 1991))
+                k = min(m, n)
+                # LU
+                ref = a.copy(order="F")
+                ipiv_ref, info_ref = O.dgetrf2(ref)
+                got = a.copy(order="F")
+                ipiv, info = lb.f77.getrf(got)
+                assert info == info_ref, (m, n)
+                if k > 0:
+                    assert np.array_equal(ipiv[:k], ipiv_ref[:k]), (m, n)
+                    assert rel(got, ref) < 1e-11, (m, n)
+                # QR and the first min(m, n) columns of Q
+                ref = a.copy(order="F")
+                tau_ref, _, _ = O.dgeqrf(ref)
+                got = a.copy(order="F")
+                tau, info, _ = lb.f77.geqrf(got)
+                assert info == 0
+                if k > 0:
+                    assert rel(got, ref) < 1e-11 and rel(tau[:k], tau_ref[:k]) < 1e-11, (m, n)
+                    q = np.asfortranarray(got[:, :k])
+                    assert lb.f77.orgqr(q, tau[:k]) == 0
+                    assert np.max(np.abs(q.T @ q - np.eye(k))) < 1e-12 * max(m, 10), (m, n)
+                # LQ
+                if k > 0:
+                    ref = a.copy(order="F")
+                    tau_ref, _ = O.dgelq2(ref)
+                    got = a.copy(order="F")
+                    tau, info = lb.f77.gelqf(got)
+                    assert info == 0 and rel(got, ref) < 1e-11 and rel(tau, tau_ref) < 1e-11, (m, n)
+                # Cholesky
+                if m == n and n > 0:
+                    s, _ = O.spd_matrix(n, (1988, 1989, 1990, 1991))
+                    for uplo in "UL":
+                        ref = s.copy(order="F")
+                        assert O.dpotrf(uplo, ref) == 0
+                        got = s.copy(order="F")
+                        assert lb.f77.potrf(uplo, got) == 0
+                        tri = np.triu if uplo == "U" else np.tril
+                        assert rel(tri(got), tri(ref)) < 1e-12, (n, uplo)
+    finally:
+        L.lb200_set_getrf_params(512, 0, 1)
+        L.lb200_set_potrf_params(512, 1)
+        L.lb200_set_geqrf_params(256, 1)
