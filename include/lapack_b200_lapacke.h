@@ -62,6 +62,15 @@ lapack_int LAPACKE_dgeqrf_work(int matrix_layout, lapack_int m, lapack_int n, do
 lapack_int LAPACKE_dgeqr2(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
 lapack_int LAPACKE_dgeqr2_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
                                double* work);
+/* LAPACKE_dgelqf / LAPACKE_dormlq (+ _work), LAPACKE/src/lapacke_dgelqf*.c, lapacke_dormlq*.c */
+lapack_int LAPACKE_dgelqf(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau);
+lapack_int LAPACKE_dgelqf_work(int matrix_layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau,
+                               double* work, lapack_int lwork);
+lapack_int LAPACKE_dormlq(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k,
+                          const double* a, lapack_int lda, const double* tau, double* c, lapack_int ldc);
+lapack_int LAPACKE_dormlq_work(int matrix_layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k,
+                               const double* a, lapack_int lda, const double* tau, double* c, lapack_int ldc, double* work,
+                               lapack_int lwork);
 /* LAPACKE_dgels / LAPACKE_dgels_work (LAPACKE/src/lapacke_dgels.c, lapacke_dgels_work.c) -- SURVEY 8f rank 4 */
 lapack_int LAPACKE_dgels(int matrix_layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a, lapack_int lda,
                          double* b, lapack_int ldb);

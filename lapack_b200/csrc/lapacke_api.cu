@@ -440,6 +440,92 @@ lapack_int LAPACKE_dgetri(int layout, lapack_int n, double* a, lapack_int lda, c
     return info;
 }
 
+// ------------------------------------------------------------------------------------------------ dgelqf / dormlq
+// LAPACKE/src/lapacke_dgelqf_work.c, lapacke_dgelqf.c, lapacke_dormlq_work.c, lapacke_dormlq.c (same structure as the QR pair)
+lapack_int LAPACKE_dgelqf_work(int layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau, double* work,
+                               lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dgelqf_(&m, &n, a, &lda, tau, work, &lwork, &info);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        if (lda < n) { info = -5; lapacke_xerbla("LAPACKE_dgelqf_work", info); return info; }
+        lapack_int lda_t = imax(1, m);
+        if (lwork == -1) {
+            dgelqf_(&m, &n, a, &lda_t, tau, work, &lwork, &info);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor r;
+        if (!r.in(a, m, n, lda)) { info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dgelqf_work", info); return info; }
+        lda_t = imax(1, (int)r.ldc);
+        dgelqf_(&m, &n, r.dev_cm ? r.dev_cm : a, &lda_t, tau, work, &lwork, &info);
+        LB_ADJ(info);
+        r.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dgelqf_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dgelqf(int layout, lapack_int m, lapack_int n, double* a, lapack_int lda, double* tau) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dgelqf", -1); return -1; }
+    if (get_nancheck() && dge_nan(layout, m, n, a, lda)) return -4;
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dgelqf_work(layout, m, n, a, lda, tau, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dgelqf", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dgelqf_work(layout, m, n, a, lda, tau, work, lwork);
+    free(work);
+    return info;
+}
+lapack_int LAPACKE_dormlq_work(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, const double* a,
+                               lapack_int lda, const double* tau, double* c, lapack_int ldc, double* work, lapack_int lwork) {
+    lapack_int info = 0;
+    if (layout == LAPACK_COL_MAJOR) {
+        dormlq_(&side, &trans, &m, &n, &k, a, &lda, tau, c, &ldc, work, &lwork, &info, 1, 1);
+        LB_ADJ(info);
+    } else if (layout == LAPACK_ROW_MAJOR) {
+        const lapack_int r = lsame(side, 'l') ? m : n;
+        lapack_int lda_t = imax(1, k), ldc_t = imax(1, m);
+        if (lda < r) { info = -8; lapacke_xerbla("LAPACKE_dormlq_work", info); return info; }
+        if (ldc < n) { info = -11; lapacke_xerbla("LAPACKE_dormlq_work", info); return info; }
+        if (lwork == -1) {
+            dormlq_(&side, &trans, &m, &n, &k, a, &lda_t, tau, c, &ldc_t, work, &lwork, &info, 1, 1);
+            LB_ADJ(info);
+            return info;
+        }
+        RowMajor ra, rc;
+        if (!ra.in(a, k, r, lda) || !rc.in(c, m, n, ldc)) {
+            info = LAPACK_TRANSPOSE_MEMORY_ERROR; lapacke_xerbla("LAPACKE_dormlq_work", info); return info;
+        }
+        lda_t = imax(1, (int)ra.ldc); ldc_t = imax(1, (int)rc.ldc);
+        dormlq_(&side, &trans, &m, &n, &k, ra.dev_cm ? ra.dev_cm : a, &lda_t, tau, rc.dev_cm ? rc.dev_cm : c, &ldc_t, work, &lwork,
+                &info, 1, 1);
+        LB_ADJ(info);
+        rc.out();
+    } else { info = -1; lapacke_xerbla("LAPACKE_dormlq_work", info); }
+    return info;
+}
+lapack_int LAPACKE_dormlq(int layout, char side, char trans, lapack_int m, lapack_int n, lapack_int k, const double* a,
+                          lapack_int lda, const double* tau, double* c, lapack_int ldc) {
+    if (!LB_LAYOUT_OK(layout)) { lapacke_xerbla("LAPACKE_dormlq", -1); return -1; }
+    if (get_nancheck()) {
+        const lapack_int r = lsame(side, 'l') ? m : n;
+        if (dge_nan(layout, k, r, a, lda)) return -7;
+        if (dge_nan(layout, m, n, c, ldc)) return -10;
+        if (nan_scan(tau, k, 1, imax(1, k), 0)) return -9;
+    }
+    double wq = 0.0;
+    lapack_int info = LAPACKE_dormlq_work(layout, side, trans, m, n, k, a, lda, tau, c, ldc, &wq, -1);
+    if (info != 0) return info;
+    lapack_int lwork = (lapack_int)wq;
+    double* work = (double*)malloc(sizeof(double) * (size_t)imax(1, lwork));
+    if (!work) { lapacke_xerbla("LAPACKE_dormlq", LAPACK_WORK_MEMORY_ERROR); return LAPACK_WORK_MEMORY_ERROR; }
+    info = LAPACKE_dormlq_work(layout, side, trans, m, n, k, a, lda, tau, c, ldc, work, lwork);
+    free(work);
+    return info;
+}
+
 // ------------------------------------------------------------------------------------------------ dgels
 // LAPACKE/src/lapacke_dgels_work.c:41-105, lapacke_dgels.c:36-82
 lapack_int LAPACKE_dgels_work(int layout, char trans, lapack_int m, lapack_int n, lapack_int nrhs, double* a, lapack_int lda,

@@ -167,3 +167,28 @@ def test_lapacke_dgels(libs, layout):
                                  nrhs if layout == ROW else max(m, n))
             assert rc == 0, name
             assert np.max(np.abs(bbuf[:rows] - x_ref[:rows])) < 1e-10 * np.max(np.abs(x_ref[:rows])), (name, m, n, trans)
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_lapacke_dgelqf_dormlq(libs, layout):
+    dp = C.POINTER(C.c_double)
+    m, n, nc = 70, 130, 9
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    tau_ref, _ = O.dgelq2(ref)
+    c0, _ = O.random_matrix(n, nc, (3, 5, 7, 9))
+    c_ref = c0.copy(order="F")
+    assert O.dorml2("L", "T", ref, tau_ref, c_ref) == 0
+    order = "C" if layout == ROW else "F"
+    for name, L in libs:
+        L.LAPACKE_dgelqf.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_int, dp]
+        L.LAPACKE_dormlq.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, C.c_int, dp, C.c_int, dp, dp, C.c_int]
+        buf = np.array(a, order=order, copy=True)
+        tau = np.zeros(m)
+        assert L.LAPACKE_dgelqf(layout, m, n, buf.ctypes.data_as(dp), n if layout == ROW else m, tau.ctypes.data_as(dp)) == 0, name
+        assert np.max(np.abs(buf - ref)) < 1e-12 and np.max(np.abs(tau - tau_ref)) < 1e-12, name
+        cbuf = np.array(c0, order=order, copy=True)
+        rc = L.LAPACKE_dormlq(layout, b"L", b"T", n, nc, m, buf.ctypes.data_as(dp), n if layout == ROW else m,
+                              tau.ctypes.data_as(dp), cbuf.ctypes.data_as(dp), nc if layout == ROW else n)
+        assert rc == 0, name
+        assert np.max(np.abs(cbuf - c_ref)) < 1e-12, name
