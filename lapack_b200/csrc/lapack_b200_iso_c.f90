@@ -74,5 +74,28 @@ module lapack_b200
        integer(c_int), value :: m, n, k
        integer(c_long_long), value :: lda
      end function
+     ! SRC/dgetri.f:114  inverse from the DGETRF factors; dinfo = i if U(i,i) is exactly zero
+     integer(c_int) function lb200_dgetri(stream, n, dA, lda, dipiv, dinfo) bind(C, name="lb200_dgetri")
+       import :: c_int, c_long_long, c_ptr
+       type(c_ptr), value :: stream, dA, dipiv, dinfo
+       integer(c_int), value :: n
+       integer(c_long_long), value :: lda
+     end function
+     ! SRC/dgeqrt.f:139  blocked QR keeping the compact-WY factors T (nb x min(m,n))
+     integer(c_int) function lb200_dgeqrt(stream, m, n, nb, dA, lda, dT, ldt) bind(C, name="lb200_dgeqrt")
+       import :: c_int, c_long_long, c_ptr
+       type(c_ptr), value :: stream, dA, dT
+       integer(c_int), value :: m, n, nb
+       integer(c_long_long), value :: lda, ldt
+     end function
+     ! SRC/dgemqrt.f:166  apply Q or Q**T from DGEQRT
+     integer(c_int) function lb200_dgemqrt(stream, side, trans, m, n, k, nb, dV, ldv, dT, ldt, dC, ldc) &
+          bind(C, name="lb200_dgemqrt")
+       import :: c_int, c_long_long, c_ptr, c_char
+       type(c_ptr), value :: stream, dV, dT, dC
+       character(kind=c_char), value :: side, trans
+       integer(c_int), value :: m, n, k, nb
+       integer(c_long_long), value :: ldv, ldt, ldc
+     end function
   end interface
 end module lapack_b200
