@@ -63,6 +63,10 @@ void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* ld
              int* info);
 void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, const int* k, const int* nb, const double* V,
               const int* ldv, const double* T, const int* ldt, double* C, const int* ldc, double* work, int* info, size_t, size_t);
+/* SRC/dgerfs.f:183 DGERFS(TRANS,N,NRHS,A,LDA,AF,LDAF,IPIV,B,LDB,X,LDX,FERR,BERR,WORK,IWORK,INFO) */
+void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, const int* lda, const double* AF, const int* ldaf,
+             const int* ipiv, const double* B, const int* ldb, double* X, const int* ldx, double* ferr, double* berr, double* work,
+             int* iwork, int* info, size_t);
 /* SRC/dgetri.f:114 DGETRI(N,A,LDA,IPIV,WORK,LWORK,INFO) (lapack.h LAPACK_dgetri) */
 void dgetri_(const int* n, double* A, const int* lda, const int* ipiv, double* work, const int* lwork, int* info);
 /* SRC/dorgqr.f:126 DORGQR(M,N,K,A,LDA,TAU,WORK,LWORK,INFO); SRC/dormqr.f:165 DORMQR(SIDE,TRANS,M,N,K,A,LDA,TAU,C,LDC,WORK,

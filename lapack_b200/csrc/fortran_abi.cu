@@ -163,6 +163,90 @@ struct Ctx {
 
 }  // namespace
 
+// ---- device helpers of DGERFS ------------------------------------------------------------------------
+namespace {
+// w(i) = |b(i)| + sum_k |A(i,k)| |x(k)|        (dgerfs.f:296-305), one thread per row, coalesced over rows
+__global__ void abs_gemv_n_kernel(int n, const double* __restrict__ A, lb::i64 lda, const double* __restrict__ x,
+                                  const double* __restrict__ b, double* __restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = fabs(b[i]);
+    for (int k = 0; k < n; ++k) acc += fabs(A[i + (lb::i64)k * lda]) * fabs(x[k]);
+    w[i] = acc;
+}
+// w(k) = |b(k)| + sum_i |A(i,k)| |x(i)|        (dgerfs.f:306-314), one warp per column
+__global__ void abs_gemv_t_kernel(int n, const double* __restrict__ A, lb::i64 lda, const double* __restrict__ x,
+                                  const double* __restrict__ b, double* __restrict__ w) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) acc += fabs(A[i + (lb::i64)k * lda]) * fabs(x[i]);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) w[k] = fabs(b[k]) + acc;
+}
+__global__ void vec_add_kernel(int n, const double* __restrict__ d, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += d[i];
+}
+
+// DLACN2 (SRC/dlacn2.f:166-293) on host vectors; same state machine as the reference (isave[3], labels 1..5)
+void host_dlacn2(int n, double* v, double* x, int* isgn, double* est, int* kase, int* isave) {
+    const int itmax = 5;
+    auto iamax = [&](const double* y) { int j = 0; double m = fabs(y[0]); for (int i = 1; i < n; ++i) if (fabs(y[i]) > m) { m = fabs(y[i]); j = i; } return j + 1; };
+    auto asum = [&](const double* y) { double t = 0.0; for (int i = 0; i < n; ++i) t += fabs(y[i]); return t; };
+    if (*kase == 0) {
+        for (int i = 0; i < n; ++i) x[i] = 1.0 / (double)n;
+        *kase = 1; isave[0] = 1;
+        return;
+    }
+    int state = isave[0];
+    if (state == 1) {
+        if (n == 1) { v[0] = x[0]; *est = fabs(v[0]); *kase = 0; return; }
+        *est = asum(x);
+        for (int i = 0; i < n; ++i) { x[i] = (x[i] >= 0.0) ? 1.0 : -1.0; isgn[i] = (int)x[i]; }
+        *kase = 2; isave[0] = 2;
+        return;
+    }
+    bool to50 = false, to120 = false;
+    if (state == 2) { isave[1] = iamax(x); isave[2] = 2; to50 = true; }
+    else if (state == 3) {
+        memcpy(v, x, sizeof(double) * (size_t)n);
+        const double estold = *est;
+        *est = asum(v);
+        bool changed = false;
+        for (int i = 0; i < n; ++i) { const int xs = (x[i] >= 0.0) ? 1 : -1; if (xs != isgn[i]) { changed = true; break; } }
+        if (!changed || *est <= estold) to120 = true;
+        else {
+            for (int i = 0; i < n; ++i) { x[i] = (x[i] >= 0.0) ? 1.0 : -1.0; isgn[i] = (int)x[i]; }
+            *kase = 2; isave[0] = 4;
+            return;
+        }
+    } else if (state == 4) {
+        const int jlast = isave[1];
+        isave[1] = iamax(x);
+        if (x[jlast - 1] != fabs(x[isave[1] - 1]) && isave[2] < itmax) { isave[2] += 1; to50 = true; }
+        else to120 = true;
+    } else if (state == 5) {
+        const double temp = 2.0 * (asum(x) / (double)(3 * n));
+        if (temp > *est) { memcpy(v, x, sizeof(double) * (size_t)n); *est = temp; }
+        *kase = 0;
+        return;
+    }
+    if (to50) {
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+        x[isave[1] - 1] = 1.0;
+        *kase = 1; isave[0] = 3;
+        return;
+    }
+    if (to120) {
+        double altsgn = 1.0;
+        for (int i = 0; i < n; ++i) { x[i] = altsgn * (1.0 + (double)i / (double)(n - 1)); altsgn = -altsgn; }
+        *kase = 1; isave[0] = 5;
+        return;
+    }
+}
+}  // namespace
+
 extern "C" {
 
 // ================================================================================================ BLAS 3
@@ -1070,6 +1154,108 @@ void dgels_(const char* trans, const int* m, const int* n, const int* nrhs, doub
     int r = c.finish();
     *info = r ? r : hinfo;
     if (solved && ptr_kind(work) != PK_DEVICE) work[0] = (double)wsize;
+}
+
+// DGERFS (SRC/dgerfs.f:235-440): iterative refinement with BERR / FERR.  The O(n^2) pieces -- residual, |A||x|, the solves
+// with the factors -- run on the device; the scalar logic and DLACN2's state machine run on the host on length-n vectors.
+void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, const int* lda, const double* AF, const int* ldaf,
+             const int* ipiv, const double* B, const int* ldb, double* X, const int* ldx, double* ferr, double* berr, double* work,
+             int* iwork, int* info, size_t) {
+    (void)work; (void)iwork;
+    *info = 0;
+    const bool notran = same(trans, 'N');
+    if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nrhs < 0) *info = -3;
+    else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldaf < imax(1, *n)) *info = -7;
+    else if (*ldb < imax(1, *n)) *info = -10;
+    else if (*ldx < imax(1, *n)) *info = -12;
+    if (*info != 0) { call_xerbla("DGERFS", -*info); return; }
+    if (*n == 0 || *nrhs == 0) { for (int j = 0; j < *nrhs; ++j) { ferr[j] = 0.0; berr[j] = 0.0; } return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    const int N = *n;
+    Ctx c; c.scan({A, AF, ipiv, B, X});
+    lb::i64 la, laf, lbb, lx;
+    const double* dA = c.mat(const_cast<double*>(A), N, N, *lda, true, false, &la);
+    const double* dAF = c.mat(const_cast<double*>(AF), N, N, *ldaf, true, false, &laf);
+    const int* dp = c.vec<int>(ipiv, (size_t)N, true, false);
+    const double* dB = c.mat(const_cast<double*>(B), N, *nrhs, *ldb, true, false, &lbb);
+    double* dX = c.mat(X, N, *nrhs, *ldx, true, true, &lx);
+    double* dr = (double*)lb::ws_alloc(c.s, sizeof(double) * (size_t)N);
+    double* dw = (double*)lb::ws_alloc(c.s, sizeof(double) * (size_t)N);
+    std::vector<double> r((size_t)N), w((size_t)N), v((size_t)N), xh((size_t)N);
+    std::vector<int> isgn((size_t)N);
+    const char tr = notran ? 'N' : 'T', trt = notran ? 'T' : 'N';
+    const int itmax = 5, nz = N + 1;
+    const double eps = 1.1102230246251565e-16, safmin = 2.2250738585072014e-308;
+    const double safe1 = nz * safmin, safe2 = safe1 / eps;
+    auto solve = [&](char t) { lb::getrs(c.s, t, N, 1, dAF, laf, dp, dr, N); };
+    auto to_host = [&](const double* d, std::vector<double>& h) {
+        LB_CUDA_CHECK(cudaMemcpyAsync(h.data(), d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, c.s));
+        LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    };
+    auto to_dev = [&](const std::vector<double>& h, double* d) {
+        LB_CUDA_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c.s));
+        LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+    };
+    for (int j = 0; j < *nrhs; ++j) {
+        const double* dbj = dB + (lb::i64)j * lbb;
+        double* dxj = dX + (lb::i64)j * lx;
+        int count = 1;
+        double lstres = 3.0;
+        for (;;) {
+            LB_CUDA_CHECK(cudaMemcpyAsync(dr, dbj, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, c.s));
+            lb::gemm(c.s, tr, 'N', N, 1, N, -1.0, dA, la, dxj, N, 1.0, dr, N);                       // dgerfs.f:285-288
+            if (notran) abs_gemv_n_kernel<<<(N + 127) / 128, 128, 0, c.s>>>(N, dA, la, dxj, dbj, dw);
+            else abs_gemv_t_kernel<<<(N + 7) / 8, 256, 0, c.s>>>(N, dA, la, dxj, dbj, dw);
+            to_host(dr, r);
+            to_host(dw, w);
+            double sm = 0.0;
+            for (int i = 0; i < N; ++i) {
+                if (w[(size_t)i] > safe2) sm = fmax(sm, fabs(r[(size_t)i]) / w[(size_t)i]);
+                else sm = fmax(sm, (fabs(r[(size_t)i]) + safe1) / (w[(size_t)i] + safe1));
+            }
+            berr[j] = sm;
+            if (berr[j] > eps && 2.0 * berr[j] <= lstres && count <= itmax) {                            // dgerfs.f:340-352
+                solve(tr);
+                vec_add_kernel<<<(N + 255) / 256, 256, 0, c.s>>>(N, dr, dxj);
+                lstres = berr[j];
+                ++count;
+                continue;
+            }
+            break;
+        }
+        for (int i = 0; i < N; ++i) {                                                                    // dgerfs.f:376-384
+            if (w[(size_t)i] > safe2) w[(size_t)i] = fabs(r[(size_t)i]) + nz * eps * w[(size_t)i];
+            else w[(size_t)i] = fabs(r[(size_t)i]) + nz * eps * w[(size_t)i] + safe1;
+        }
+        int kase = 0, isave[3] = {0, 0, 0};
+        for (;;) {
+            host_dlacn2(N, v.data(), r.data(), isgn.data(), &ferr[j], &kase, isave);
+            if (kase == 0) break;
+            if (kase == 1) {                                                                             // dgerfs.f:392-398
+                to_dev(r, dr);
+                solve(trt);
+                to_host(dr, r);
+                for (int i = 0; i < N; ++i) r[(size_t)i] = w[(size_t)i] * r[(size_t)i];
+            } else {                                                                                     // dgerfs.f:403-409
+                for (int i = 0; i < N; ++i) r[(size_t)i] = w[(size_t)i] * r[(size_t)i];
+                to_dev(r, dr);
+                solve(tr);
+                to_host(dr, r);
+            }
+        }
+        to_host(dxj, xh);
+        lstres = 0.0;
+        for (int i = 0; i < N; ++i) lstres = fmax(lstres, fabs(xh[(size_t)i]));
+        if (lstres != 0.0) ferr[j] = ferr[j] / lstres;
+    }
+    lb::ws_free(c.s, dr);
+    lb::ws_free(c.s, dw);
+    int rr = c.finish();
+    if (rr) *info = rr;
 }
 
 }  // extern "C"

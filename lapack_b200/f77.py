@@ -245,6 +245,23 @@ def gemqrt(side, trans, v, t, c, nb, k=None):
     return dgemqrt(side, trans, m, n, k, nb, v, _ld(v), t, _ld(t), c, _ld(c), work)
 
 
+def dgerfs(trans, n, nrhs, a, lda, af, ldaf, ipiv, b, ldb, x, ldx, ferr, berr, work, iwork):
+    info = _i(0)
+    lib().dgerfs_(_c(trans), _r(n), _r(nrhs), _p(a), _r(lda), _p(af), _r(ldaf), _p(ipiv), _p(b), _r(ldb), _p(x), _r(ldx), _p(ferr),
+                  _p(berr), _p(work), _p(iwork), C.byref(info), C.c_size_t(1))
+    return info.value
+
+
+def gerfs(trans, a, af, ipiv, b, x):
+    """refine x in place; returns (ferr, berr, info)"""
+    n, nrhs = a.shape[0], b.shape[1]
+    ferr, berr = np.zeros(max(1, nrhs)), np.zeros(max(1, nrhs))
+    work, iwork = np.zeros(max(1, 3 * n)), np.zeros(max(1, n), dtype=np.int32)
+    info = dgerfs(trans, n, nrhs, a, _ld(a), af, _ld(af), np.ascontiguousarray(ipiv, dtype=np.int32), b, _ld(b), x, _ld(x), ferr,
+                  berr, work, iwork)
+    return ferr[:nrhs], berr[:nrhs], info
+
+
 def dgetri(n, a, lda, ipiv, work, lwork):
     info = _i(0)
     lib().dgetri_(_r(n), _p(a), _r(lda), _p(ipiv), _p(work), _r(lwork), C.byref(info))

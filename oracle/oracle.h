@@ -101,6 +101,9 @@ void ora_dgelq2(int m, int n, double *a, int lda, double *tau, double *work, int
 void ora_dorml2(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
                 double *work, int *info);
 void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b, int ldb, double *work, int lwork, int *info);
+void ora_dlacn2(int n, double *v, double *x, int *isgn, double *est, int *kase, int *isave);
+void ora_dgerfs(char trans, int n, int nrhs, const double *a, int lda, const double *af, int ldaf, const int *ipiv,
+                const double *b, int ldb, double *x, int ldx, double *ferr, double *berr, double *work, int *iwork, int *info);
 void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,
                 double *work, int *info);
 void ora_dormqr(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,

@@ -267,6 +267,17 @@ def dgemqrt(side, trans, v, t, c, nb, k=None):
     return info.value
 
 
+def dgerfs(trans, a, af, ipiv, b, x):
+    """iterative refinement (SRC/dgerfs.f): x is improved in place; returns (ferr, berr, info)"""
+    n, nrhs = a.shape[0], b.shape[1]
+    ferr, berr = np.zeros(max(1, nrhs)), np.zeros(max(1, nrhs))
+    work, iwork = np.zeros(max(1, 3 * n)), np.zeros(max(1, n), dtype=np.int32)
+    info = C.c_int(0)
+    lib().ora_dgerfs(_c(trans), n, nrhs, _d(a), _ld(a), _d(af), _ld(af), _i(np.ascontiguousarray(ipiv, dtype=np.int32)), _d(b), _ld(b),
+                     _d(x), _ld(x), _d(ferr), _d(berr), _d(work), _i(iwork), C.byref(info))
+    return ferr[:nrhs], berr[:nrhs], info.value
+
+
 def dgels(trans, a, b):
     """least squares / minimum norm solve (SRC/dgels.f); a is overwritten by its QR / LQ factors, b (max(m,n) x nrhs) by the
     solution"""

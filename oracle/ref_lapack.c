@@ -1059,3 +1059,134 @@ void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b
 #undef B_
     work[0] = (double)wsize;
 }
+
+/* SRC/dlacn2.f:166-293 -- Hager/Higham 1-norm estimator, reverse communication (state in isave[3], 1-based labels). */
+void ora_dlacn2(int n, double *v, double *x, int *isgn, double *est, int *kase, int *isave)
+{
+    const int itmax = 5;
+    if (*kase == 0) {
+        for (int i = 0; i < n; ++i) x[i] = 1.0 / (double)n;
+        *kase = 1; isave[0] = 1;
+        return;
+    }
+    int jlast;
+    double estold, temp, altsgn;
+    switch (isave[0]) {
+    case 1:
+        if (n == 1) { v[0] = x[0]; *est = fabs(v[0]); goto L150; }
+        *est = 0.0;
+        for (int i = 0; i < n; ++i) *est += fabs(x[i]);                      /* DASUM */
+        for (int i = 0; i < n; ++i) { x[i] = (x[i] >= 0.0) ? 1.0 : -1.0; isgn[i] = (int)x[i]; }
+        *kase = 2; isave[0] = 2;
+        return;
+    case 2:
+        isave[1] = ora_idamax(n, x, 1);
+        isave[2] = 2;
+    L50:
+        for (int i = 0; i < n; ++i) x[i] = 0.0;
+        x[isave[1] - 1] = 1.0;
+        *kase = 1; isave[0] = 3;
+        return;
+    case 3: {
+        int changed = 0;
+        ora_dcopy(n, x, 1, v, 1);
+        estold = *est;
+        *est = 0.0;
+        for (int i = 0; i < n; ++i) *est += fabs(v[i]);
+        for (int i = 0; i < n; ++i) {
+            int xs = (x[i] >= 0.0) ? 1 : -1;
+            if (xs != isgn[i]) { changed = 1; break; }
+        }
+        if (!changed) goto L120;                                             /* repeated sign vector: converged */
+        if (*est <= estold) goto L120;
+        for (int i = 0; i < n; ++i) { x[i] = (x[i] >= 0.0) ? 1.0 : -1.0; isgn[i] = (int)x[i]; }
+        *kase = 2; isave[0] = 4;
+        return;
+    }
+    case 4:
+        jlast = isave[1];
+        isave[1] = ora_idamax(n, x, 1);
+        if (x[jlast - 1] != fabs(x[isave[1] - 1]) && isave[2] < itmax) { isave[2] += 1; goto L50; }
+    L120:
+        altsgn = 1.0;
+        for (int i = 0; i < n; ++i) { x[i] = altsgn * (1.0 + (double)i / (double)(n - 1)); altsgn = -altsgn; }
+        *kase = 1; isave[0] = 5;
+        return;
+    case 5:
+        temp = 0.0;
+        for (int i = 0; i < n; ++i) temp += fabs(x[i]);
+        temp = 2.0 * (temp / (double)(3 * n));
+        if (temp > *est) { ora_dcopy(n, x, 1, v, 1); *est = temp; }
+        goto L150;
+    }
+L150:
+    *kase = 0;
+}
+
+/* SRC/dgerfs.f:235-440 -- iterative refinement of DGETRS solutions with componentwise backward error BERR and forward
+   error bound FERR.  work: 3n doubles, iwork: n ints. */
+void ora_dgerfs(char trans, int n, int nrhs, const double *a, int lda, const double *af, int ldaf, const int *ipiv,
+                const double *b, int ldb, double *x, int ldx, double *ferr, double *berr, double *work, int *iwork, int *info)
+{
+    const int itmax = 5;
+    int notran = ora_lsame(trans, 'N');
+    *info = 0;
+    if (!notran && !ora_lsame(trans, 'T') && !ora_lsame(trans, 'C')) *info = -1; else if (n < 0) *info = -2;
+    else if (nrhs < 0) *info = -3; else if (lda < imax(1, n)) *info = -5; else if (ldaf < imax(1, n)) *info = -7;
+    else if (ldb < imax(1, n)) *info = -10; else if (ldx < imax(1, n)) *info = -12;
+    if (*info != 0) return;
+    if (n == 0 || nrhs == 0) { for (int j = 0; j < nrhs; ++j) { ferr[j] = 0.0; berr[j] = 0.0; } return; }
+    char transt = notran ? 'T' : 'N';
+    const int nz = n + 1;
+    const double eps = 1.1102230246251565e-16, safmin = 2.2250738585072014e-308;   /* DLAMCH('Epsilon'), ('Safe minimum') */
+    const double safe1 = nz * safmin, safe2 = safe1 / eps;
+    for (int j = 0; j < nrhs; ++j) {
+        const double *bj = b + (size_t)j * ldb;
+        double *xj = x + (size_t)j * ldx;
+        int count = 1, iinfo;
+        double lstres = 3.0;
+        for (;;) {
+            ora_dcopy(n, bj, 1, work + n, 1);
+            ora_dgemv(trans, n, n, -1.0, a, lda, xj, 1, 1.0, work + n, 1);
+            for (int i = 0; i < n; ++i) work[i] = fabs(bj[i]);
+            if (notran) {
+                for (int k = 0; k < n; ++k) { double xk = fabs(xj[k]); for (int i = 0; i < n; ++i) work[i] += fabs(A_(i, k)) * xk; }
+            } else {
+                for (int k = 0; k < n; ++k) { double s = 0.0; for (int i = 0; i < n; ++i) s += fabs(A_(i, k)) * fabs(xj[i]); work[k] += s; }
+            }
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) {
+                if (work[i] > safe2) s = fmax(s, fabs(work[n + i]) / work[i]);
+                else s = fmax(s, (fabs(work[n + i]) + safe1) / (work[i] + safe1));
+            }
+            berr[j] = s;
+            if (berr[j] > eps && 2.0 * berr[j] <= lstres && count <= itmax) {
+                ora_dgetrs(trans, n, 1, af, ldaf, ipiv, work + n, n, &iinfo);
+                ora_daxpy(n, 1.0, work + n, 1, xj, 1);
+                lstres = berr[j];
+                ++count;
+                continue;
+            }
+            break;
+        }
+        for (int i = 0; i < n; ++i) {
+            if (work[i] > safe2) work[i] = fabs(work[n + i]) + nz * eps * work[i];
+            else work[i] = fabs(work[n + i]) + nz * eps * work[i] + safe1;
+        }
+        int kase = 0, isave[3] = {0, 0, 0};
+        for (;;) {
+            ora_dlacn2(n, work + 2 * n, work + n, iwork, &ferr[j], &kase, isave);
+            if (kase == 0) break;
+            if (kase == 1) {
+                ora_dgetrs(transt, n, 1, af, ldaf, ipiv, work + n, n, &iinfo);
+                for (int i = 0; i < n; ++i) work[n + i] = work[i] * work[n + i];
+            } else {
+                for (int i = 0; i < n; ++i) work[n + i] = work[i] * work[n + i];
+                ora_dgetrs(trans, n, 1, af, ldaf, ipiv, work + n, n, &iinfo);
+            }
+        }
+        lstres = 0.0;
+        for (int i = 0; i < n; ++i) lstres = fmax(lstres, fabs(xj[i]));
+        if (lstres != 0.0) ferr[j] = ferr[j] / lstres;
+    }
+}

@@ -187,6 +187,20 @@ def test_gels_gelqf_ormlq_error_exits_and_query(lb):
     assert f.dormlq("L", "T", 300, 7, 200, A, 200, TAU, B, 300, wq, -1) == 0 and wq[0] == 7 * 32 + 65 * 32
 
 
+def test_gerfs_error_exits(lb):
+    """TESTING/LIN/derrge.f:189-216."""
+    f = lb.f77
+    R1, R2, IW = np.zeros(4), np.zeros(4), np.zeros(4, dtype=np.int32)
+    X = np.zeros((4, 4), order="F")
+    for args, pos in ((("/", 0, 0, A, 1, B, 1, IP, B, 1, X, 1), 1), (("N", -1, 0, A, 1, B, 1, IP, B, 1, X, 1), 2),
+                      (("N", 0, -1, A, 1, B, 1, IP, B, 1, X, 1), 3), (("N", 2, 1, A, 1, B, 2, IP, B, 2, X, 2), 5),
+                      (("N", 2, 1, A, 2, B, 1, IP, B, 2, X, 2), 7), (("N", 2, 1, A, 2, B, 2, IP, B, 1, X, 2), 10),
+                      (("N", 2, 1, A, 2, B, 2, IP, B, 2, X, 1), 12)):
+        assert expect(lb, lambda a=args: f.dgerfs(*a, R1, R2, W, IW), "DGERFS", pos) == -pos
+    R1[:] = 5.0
+    assert f.dgerfs("N", 0, 2, A, 1, B, 1, IP, B, 1, X, 1, R1, R2, W, IW) == 0 and np.all(R1[:2] == 0.0)     # quick return
+
+
 def test_getri_error_exits_and_query(lb):
     """TESTING/LIN/derrge.f:157-165 (positions 1 and 3) plus the LWORK check and query of dgetri.f:152-170."""
     f = lb.f77

@@ -644,6 +644,28 @@ def test_dgeqrt_dgemqrt_vs_oracle(lb, m, n, nb):
             assert rel(c, c_ref) < 1e-11, (side, trans)
 
 
+# ------------------------------------------------------------------------------------------- DGERFS
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (40, 2), (300, 3), (1100, 2)])
+@pytest.mark.parametrize("trans", "NT")
+def test_dgerfs_vs_oracle(lb, n, nrhs, trans):
+    a, seed = O.random_matrix(n, n, SEED)
+    xt, _ = O.random_matrix(n, nrhs, seed)
+    b = np.asfortranarray((a if trans == "N" else a.T) @ xt)
+    af = a.copy(order="F")
+    ipiv, info = O.dgetrf(af)
+    x0 = np.asfortranarray(xt * (1.0 + 1e-9))                       # slightly wrong on purpose
+    x_ref = x0.copy(order="F")
+    ferr_ref, berr_ref, info_ref = O.dgerfs(trans, a, af, ipiv, b, x_ref)
+    x = x0.copy(order="F")
+    ferr, berr, info = lb.f77.gerfs(trans, a, af, ipiv, b, x)
+    assert info == info_ref == 0
+    assert rel(x, x_ref) < 1e-11
+    assert np.all(berr < 4e-16 * max(1, n) ** 0.5) and np.all(berr_ref < 4e-16 * max(1, n) ** 0.5)
+    assert np.all(np.abs(ferr - ferr_ref) <= 0.1 * ferr_ref + 1e-16)
+    err = np.max(np.abs(x - xt), axis=0) / np.max(np.abs(x), axis=0)
+    assert np.all(err <= ferr + 1e-16)                               # FERR is a bound on the true forward error (dgerfs.f:96-103)
+
+
 # ------------------------------------------------------------------------------------------- DGETRI
 @pytest.mark.parametrize("n", [1, 33, 300, 1100])
 def test_dgetri_vs_oracle(lb, n):

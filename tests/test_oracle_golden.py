@@ -318,3 +318,19 @@ def test_dgels_netlib():
     a0 = a.copy(order="F")
     a0[:, 4] = 0.0
     assert O.dgels("N", a0, b.copy(order="F")) == int(g["rankdef_info"]) == 5
+
+
+@pytest.mark.parametrize("n", [7, 80])
+def test_dgerfs_netlib(n):
+    """ora_dgerfs / ora_dlacn2 vs netlib 3.12.0 (tests/golden/make_golden_gerfs.py): refined solution to rounding, FERR within
+    a few percent (its value depends on the rounding of the residual), BERR at the rounding level in both."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "netlib_golden_gerfs.npz"))
+    a, af, ipiv = np.asfortranarray(g[f"a{n}"]), np.asfortranarray(g[f"af{n}"]), g[f"ipiv{n}"]
+    for trans in "NT":
+        b, x = np.asfortranarray(g[f"b{n}{trans}"]), np.asfortranarray(g[f"x0_{n}{trans}"].copy())
+        ferr, berr, info = O.dgerfs(trans, a, af, ipiv, b, x)
+        assert info == 0
+        assert np.max(np.abs(x - g[f"x{n}{trans}"])) < 1e-12 * np.max(np.abs(x))
+        assert np.all(np.abs(ferr - g[f"ferr{n}{trans}"]) <= 0.05 * g[f"ferr{n}{trans}"])
+        assert np.all(berr < 1e-15) and np.all(g[f"berr{n}{trans}"] < 1e-15)
