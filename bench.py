@@ -48,6 +48,11 @@ def flops_getrs(n, nrhs):
     return nrhs * (2.0 * n * n - n)
 
 
+def flops_geqrf(m, n):
+    """LAWN-41 count for m >= n: 2mn^2 - 2n^3/3 + mn + n^2 + 14n/3"""
+    return 2.0 * m * n * n - 2.0 * n ** 3 / 3 + m * n + n * n + 14.0 * n / 3
+
+
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md recipe)."""
@@ -98,7 +103,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference leg
-def cpu_reference_sample(n, nrhs=1):
+def cpu_reference_sample(n, nrhs=1, keep=None):
     """One DGESV (DGETRF NB=64 + DGETRS) of the oracle port on an n x n DLARNV matrix; returns (seconds, flops)."""
     import numpy as np
     from oracle import oracle as O
@@ -109,6 +114,8 @@ def cpu_reference_sample(n, nrhs=1):
     ipiv, info = O.dgesv(a, b)
     t = time.perf_counter() - t0
     err = float(np.max(np.abs(b - xact)) / np.max(np.abs(xact)))
+    if keep is not None:
+        keep["ipiv"], keep["x"], keep["n"] = ipiv.copy(), b.copy(), n
     return t, flops_getrf(n) + flops_getrs(n, nrhs), info, err
 
 
@@ -374,19 +381,54 @@ def run_ours(args, rank, world, local_rank):
     ms = t.item()
     value = world * step_flops * args.steps / (ms * 1e-3) * 1e-12
 
-    # separate single-routine timings (informational)
-    def time_one(fn, restore):
-        restore()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        fn()
-        s1.record()
-        torch.cuda.synchronize()
-        return s0.elapsed_time(s1) * 1e-3
+    # ---- per-routine legs (device-resident, CUDA events): every BASELINE config gets its own number
+    def time_one(fn, restore, reps=2):
+        best = 1e30
+        for _ in range(reps):
+            restore()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            fn()
+            s1.record()
+            torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1) * 1e-3)
+        return best
     t_lu = time_one(lambda: lb.dev.getrf(a_lu), lambda: a_lu.copy_(a_lu0))
     t_po = time_one(lambda: lb.dev.potrf("L", a_po), lambda: a_po.copy_(a_po0))
+    t_ps = time_one(lambda: lb.dev.potrs("L", a_po, b_po), lambda: b_po.copy_(b_po0), reps=3)       # a_po holds the factor
+    l0 = L.lb200_launch_count()
+    t_gs = time_one(lambda: lb.dev.getrs("N", a_lu, ipiv, b_po), lambda: b_po.copy_(b_po0), reps=3)  # a_lu holds the LU factors
+    solve_launches = int(L.lb200_launch_count() - l0) // 3
     peak = max(L.lb200_fp64_peak_tflops(None, 0, 8, 2, 20000) for _ in range(2))
+    # independent FP64 denominator: cuBLAS DGEMM 8192^3 through torch.matmul (checker only, never on the product path)
+    ga = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    gb = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    gc = torch.empty_like(ga)
+    torch.matmul(ga, gb, out=gc)
+    t_cublas = time_one(lambda: torch.matmul(ga, gb, out=gc), lambda: None, reps=3)
+    peak_cublas = 2.0 * 8192 ** 3 / t_cublas * 1e-12
+    del ga, gb, gc
+    # BASELINE configs[3]: DGEQRF 32768 x 32768 (SRC/dgeqrf.f:244-267) on the same U(-1,1) matrix, with DQRT01's two ratios
+    tau_box = [None]
+
+    def run_qr():
+        tau_box[0] = lb.dev.geqrf(a_lu)
+    t_qr = time_one(run_qr, lambda: a_lu.copy_(a_lu0))
+    qr_checks = {}
+    if rank == 0 and not args.no_check:
+        q = a_po                                                    # reuse the Cholesky work matrix for Q
+        q.copy_(a_lu)
+        lb.dev.orgqr(q, tau_box[0])                                 # dqrt01.f:191 (DORGQR)
+        r = q.t() @ a_lu0                                           # Q^T A (cuBLAS, checker only)
+        r -= torch.triu(a_lu)
+        anorm = a_lu0.abs().sum(0).max().item()
+        qr_checks["dqrt01_ratio_r"] = r.abs().sum(0).max().item() / (n * anorm * EPS)        # dqrt01.f:203-211
+        torch.matmul(q.t(), q, out=r)
+        r.diagonal().sub_(1.0)
+        qr_checks["dqrt01_ratio_orth"] = r.abs().sum(0).max().item() / (n * EPS)             # dqrt01.f:215-221
+        del r, q
+        torch.cuda.empty_cache()
     batched = bench_batched(lb, torch, dev, (1 << 20) // world)
 
     # ---- e2e: Fortran-77 ABI with pinned host buffers (H2D + compute + D2H per step)
@@ -427,16 +469,80 @@ def run_ours(args, rank, world, local_rank):
                "ipiv_equals_device_run": ipiv_same}
         del h_lu, h_po, h_b
 
+    # ---- e2e with PAGEABLE host buffers (what a Fortran caller's ALLOCATEd array is): same calls, plain numpy memory
+    e2e_pageable = None
+    if not args.no_e2e and world == 1:
+        import numpy as np
+        p_lu = np.empty((n, n), dtype=np.float64)
+        p_po = np.empty((n, n), dtype=np.float64)
+        p_b = np.empty((nrhs, n), dtype=np.float64)
+        p_ipiv = np.zeros(n, dtype=np.int32)
+        tp = []
+        for i in range(2):
+            torch.from_numpy(p_lu).copy_(a_lu0.t())
+            torch.from_numpy(p_po).copy_(a_po0.t())
+            torch.from_numpy(p_b).copy_(b_po0.t())
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            i1 = lb.f77.dposv("L", n, nrhs, p_po.ctypes.data, n, p_b.ctypes.data, n)
+            i3 = lb.f77.dgetrf(n, n, p_lu.ctypes.data, n, p_ipiv)
+            tp.append(time.perf_counter() - t0)
+            assert i1 == 0 and i3 == 0, (i1, i3)
+        e2e_pageable = {"value": step_flops / min(tp) * 1e-12, "unit": "TFLOP/s", "ms_per_step": min(tp) * 1e3,
+                        "ms_first_call": tp[0] * 1e3,
+                        "ipiv_equals_device_run": bool(np.array_equal(p_ipiv, ipiv.cpu().numpy())),
+                        "api": "dposv_ and dgetrf_ on pageable (malloc) host arrays"}
+        del p_lu, p_po, p_b
+
     if rank != 0:
         return
     # ---- CPU baseline (oracle port, bounded sample), rank 0 only, N=1 only
     cpu = None
+    keep = {}
     if world == 1 and not args.no_cpu:
         ncpu = pick_cpu_sample(25.0, 1)
-        tc, fc, _, _ = cpu_reference_sample(ncpu)
+        tc, fc, _, _ = cpu_reference_sample(ncpu, keep=keep)
         cpu = {"value": fc / tc * 1e-12, "unit": "TFLOP/s", "cores": 1, "kind": "port", "seconds": tc,
                "sample": f"DGESV n={ncpu} nrhs=1: reference DGETRF (NB=64) + DGETRS on reference BLAS loops (oracle port), 1 of {os.cpu_count()} host cores"}
+    # ---- BASELINE configs[0] on the GPU: DGESV n=4096, 1 RHS through dgesv_ on the SAME input the CPU leg factored;
+    # IPIV must be bit-identical with the oracle's (SRC/dgesv.f:165-172)
+    c1 = None
+    if world == 1:
+        import numpy as np
+        from oracle import oracle as O
+        n1 = keep.get("n", 4096)
+        a1, seed1 = O.random_matrix(n1, n1, SEED)
+        x1, _ = O.random_matrix(n1, 1, seed1)
+        b1 = np.asfortranarray(a1 @ x1)
+        tg = []
+        for i in range(3):
+            lu1, sol1 = a1.copy(order="F"), b1.copy(order="F")
+            t0 = time.perf_counter()
+            ipiv1, info1 = lb.f77.gesv(lu1, sol1)
+            tg.append(time.perf_counter() - t0)
+        d1 = lb.dev.larnv_matrix(n1, n1, SEED, device=dev)
+        db = lb.dev.colmajor(n1, 1, device=dev)
+        db.copy_(torch.from_numpy(b1))
+        d1w = d1.clone()
+        pv = [None]
+
+        def c1_dev():
+            pv[0], _ = lb.dev.getrf(d1w)
+            lb.dev.getrs("N", d1w, pv[0], db)
+        t_c1 = time_one(c1_dev, lambda: (d1w.copy_(d1), db.copy_(torch.from_numpy(b1))), reps=3)
+        fl1 = flops_getrf(n1) + flops_getrs(n1, 1)
+        c1 = {"n": n1, "info": int(info1), "e2e_ms_pageable_host": min(tg) * 1e3, "e2e_tflops": fl1 / min(tg) * 1e-12,
+              "device_ms": t_c1 * 1e3, "device_tflops": fl1 / t_c1 * 1e-12,
+              "ipiv_equals_oracle": bool(np.array_equal(ipiv1, keep["ipiv"])) if "ipiv" in keep else None,
+              "ipiv_device_equals_host_call": bool(np.array_equal(pv[0].cpu().numpy(), ipiv1)),
+              "x_rel_err_vs_oracle": float(np.max(np.abs(sol1 - keep["x"])) / np.max(np.abs(keep["x"]))) if "x" in keep else None,
+              "x_rel_err_vs_xact": float(np.max(np.abs(sol1 - x1)) / np.max(np.abs(x1)))}
     gemm_tf = (gfl.value / (gms.value * 1e-3) * 1e-12) if gms.value > 0 else None
+    hbm = 6650.0
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", hbm)
+    except Exception:
+        pass
     line = {
         "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,15 +553,30 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "inputs (8 GiB per matrix) are far larger than the 126 MB L2; restored from HBM copies every step"},
         "pct_of_fp64_peak": value / world / peak if peak else None,
         "breakdown": {"dgetrf_tflops": flops_getrf(n) / t_lu * 1e-12, "dgetrf_ms": t_lu * 1e3,
-                      "dpotrf_tflops": flops_potrf(n) / t_po * 1e-12, "dpotrf_ms": t_po * 1e3},
+                      "dgetrf_frac_of_dmma_peak": flops_getrf(n) / t_lu * 1e-12 / peak,
+                      "dgetrf_frac_of_cublas_dgemm": flops_getrf(n) / t_lu * 1e-12 / peak_cublas,
+                      "dpotrf_tflops": flops_potrf(n) / t_po * 1e-12, "dpotrf_ms": t_po * 1e3,
+                      "dpotrf_frac_of_dmma_peak": flops_potrf(n) / t_po * 1e-12 / peak,
+                      "dpotrf_frac_of_cublas_dgemm": flops_potrf(n) / t_po * 1e-12 / peak_cublas,
+                      "dgeqrf_tflops": flops_geqrf(n, n) / t_qr * 1e-12, "dgeqrf_ms": t_qr * 1e3,
+                      "dgeqrf_frac_of_dmma_peak": flops_geqrf(n, n) / t_qr * 1e-12 / peak,
+                      "dgeqrf_frac_of_cublas_dgemm": flops_geqrf(n, n) / t_qr * 1e-12 / peak_cublas,
+                      "dpotrs_1rhs_ms": t_ps * 1e3, "dpotrs_hbm_gbs": 8.0 * n * n / t_ps * 1e-9, "dpotrs_frac_of_hbm": 8.0 * n * n / t_ps * 1e-9 / hbm,
+                      "dgetrs_1rhs_ms": t_gs * 1e3, "dgetrs_hbm_gbs": 8.0 * n * n / t_gs * 1e-9, "dgetrs_frac_of_hbm": 8.0 * n * n / t_gs * 1e-9 / hbm,
+                      "dgetrs_launches": solve_launches},
+        "dgeqrf_32768": {"workload": f"DGEQRF {n}x{n} (BASELINE configs[3]), DLARNV(2) seed 1988-1991", "ms": t_qr * 1e3,
+                         "tflops": flops_geqrf(n, n) / t_qr * 1e-12, "flops": flops_geqrf(n, n), "checks": qr_checks},
+        "dgesv_4096": c1,
         "roofline": {"bound": "tensor", "kernel": "gemm_f64_dmma_kernel<64,64,2,2,...,STAGES=2,BK=16> (trailing updates, DMMA.8x8x4)",
                      "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
+                     "peak_cublas": peak_cublas, "frac_of_cublas": (gemm_tf / peak_cublas) if gemm_tf else None,
+                     "peak_cublas_note": "cuBLAS DGEMM 8192^3 via torch.matmul timed in this run (independent denominator, checker only)",
                      "traffic": 5.41e9, "traffic_note": "dram read+write bytes of ONE representative trailing-update launch "
                      "(m=n=16384, k=512; algorithmic 4.43e9 B) from profiles/r01_gemm_cfg8_ncu_full_16384x16384x512.txt",
                      "launches_timed": int(gcnt.value),
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate peak measured in this run by lb200_fp64_peak_tflops "
                                     "(MEASURED_PEAKS.json carries HBM and bf16 only)"},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "checks": checks,
+        "cpu_baseline": cpu, "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": launches, "clocks": clocks, "checks": checks,
         "batched_dgetrf_32x32": batched,
     }
     OUT.emit(json.dumps(line))

@@ -41,6 +41,10 @@ void lb200_set_getrf_big_leaf(int rows4);
 void lb200_set_geqrf_cluster_max(int ctas);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);
+/* triangular solves with <= 8 right-hand sides: 1 (default) = one persistent streaming kernel, 0 = leaf/GEMV recursion */
+void lb200_set_fewrhs_mode(int mode);
+/* experiment knob: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes) for the LDA-strided row interchanges */
+int lb200_set_l2_fetch_granularity(int bytes);
 
 /* BLAS/SRC/dgemm.f:187 DGEMM(TRANSA,TRANSB,M,N,K,ALPHA,A,LDA,B,LDB,BETA,C,LDC) */
 int lb200_dgemm(void* stream, char transa, char transb, int m, int n, int k, double alpha, const double* dA,

@@ -59,126 +59,251 @@ __global__ void laswp_colsmem_kernel(int rows, double* __restrict__ A, i64 lda, 
     for (int i = threadIdx.x; i < rows; i += blockDim.x) a[i] = scol[i];
 }
 
-// Variant C (default for more than a handful of interchanges): the sequence of transpositions is first
-// composed into a list of independent moves (dst_row <- src_row) by one small CTA, then every column applies
-// that list with all loads in flight at once (gather into shared memory, barrier, scatter).  This removes the
-// dependent load->store->load chain of variant A (about one memory round trip per interchange).
-struct MoveList {
-    int count;
-    int pad;
-    int2 mv[1];   // (dst_row, src_row), 0-based
+// Variant C (default for more than a handful of interchanges).  A sequence of transpositions is first COMPOSED into one
+// permutation by a small CTA (O(np): one thread walks the sequence on an index array in shared memory; rows outside the
+// pivot block K1..K2 live in a small hash table), which yields independent moves in two groups:
+//   group 1: block row K1+t  <- original row srcA[t]      (destinations contiguous: coalesced writes)
+//   group 2: outside row dst <- original row src          (sorted by src, which is a block row for LU pivots: coalesced reads)
+// The apply kernel then gathers every moved element of a few columns into shared memory with all loads in flight at once,
+// and scatters.  DRAM traffic per interchanged pair and column: one 32-B sector read + written back for the row outside
+// the block (the write hits the sector the same CTA has just read), 8 + 8 B for the block row -- 80 B for 32 algorithmic
+// bytes, which is what LDA-strided rows allow.
+struct SwapPlan {
+    int np;       // block rows K1 .. K1+np-1
+    int k1;       // 1-based
+    int nout;     // entries of group 2
+    int nmoved;   // block rows whose content changes (informational)
+    int data[1];  // [np] srcA (0-based row, == K1-1+t when unchanged), then up to 2*np (dst, src) pairs (second half: scratch)
 };
 
-__global__ void laswp_build_kernel(int np, int k1, int k2, const int* __restrict__ ipiv, int incx, MoveList* out) {
+constexpr int LASWP_HASH = 8192;      // slots for rows outside the block (<= LASWP_MAX_PIV of them), power of two
+__device__ __forceinline__ int swp_hash(int row) { return (int)(((unsigned)row * 2654435761u) >> 19) & (LASWP_HASH - 1); }
+
+__global__ void __launch_bounds__(256) laswp_build_kernel(int np, int k1, int k2, const int* __restrict__ ipiv, int incx, SwapPlan* out) {
     extern __shared__ int sm[];
-    int* piv = sm;              // [np]   pivot row (1-based) of the t-th interchange in application order
-    int* slot = sm + np;        // [np]   slot of the pivot row: < np inside the block, >= np outside
-    int* idx = sm + 2 * np;     // [2np]  which original slot currently sits in each slot
-    int* rowof = sm + 4 * np;   // [2np]  global row (1-based) of each slot, 0 = unused
-    __shared__ int s_count;
+    int* piv = sm;                  // [np]   pivot row (1-based) of the t-th interchange in application order
+    int* cur = sm + np;             // [np]   original row (1-based) currently stored in block row K1+q
+    int* inv = sm + 2 * np;         // [np]   final row (1-based) of the original block row K1+q
+    int* hkey = sm + 3 * np;        // [HASH] outside row (1-based), 0 = empty
+    int* hval = hkey + LASWP_HASH;  // [HASH] original row currently stored there
+    __shared__ int s_cnt[256];
+    __shared__ int s_extra;
+    const int tid = threadIdx.x;
     const int ix0 = incx > 0 ? k1 : k1 + (k1 - k2) * incx;
-    for (int t = threadIdx.x; t < np; t += blockDim.x) piv[t] = ipiv[ix0 + t * incx - 1];
-    for (int q = threadIdx.x; q < 2 * np; q += blockDim.x) { idx[q] = q; rowof[q] = (q < np) ? k1 + q : 0; }
-    if (threadIdx.x == 0) s_count = 0;
+    for (int t = tid; t < np; t += 256) { piv[t] = ipiv[ix0 + t * incx - 1]; cur[t] = k1 + t; inv[t] = 0; }
+    for (int q = tid; q < LASWP_HASH; q += 256) hkey[q] = 0;
+    if (tid == 0) s_extra = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < np; t += blockDim.x) {
-        int ip = piv[t];
-        int sl;
-        if (ip >= k1 && ip <= k2) sl = ip - k1;
-        else {
-            int first = t;
-            for (int u = 0; u < t; ++u)
-                if (piv[u] == ip) { first = u; break; }
-            sl = np + first;
-            if (first == t) rowof[sl] = ip;
-        }
-        slot[t] = sl;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         for (int t = 0; t < np; ++t) {
-            int i = incx > 0 ? k1 + t : k2 - t;     // row being interchanged at step t
-            int a = i - k1, b = slot[t];
-            int tmp = idx[a]; idx[a] = idx[b]; idx[b] = tmp;
+            const int i = incx > 0 ? k1 + t : k2 - t;     // row interchanged at step t (dlaswp.f:152-167)
+            const int ip = piv[t];
+            if (ip == i) continue;
+            const int a = cur[i - k1];
+            if (ip >= k1 && ip <= k2) {
+                cur[i - k1] = cur[ip - k1];
+                cur[ip - k1] = a;
+            } else {
+                int h = swp_hash(ip);
+                while (hkey[h] != 0 && hkey[h] != ip) h = (h + 1) & (LASWP_HASH - 1);
+                if (hkey[h] == 0) { hkey[h] = ip; hval[h] = ip; }
+                cur[i - k1] = hval[h];
+                hval[h] = a;
+            }
         }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < 2 * np; q += blockDim.x) {
-        if (rowof[q] != 0 && idx[q] != q) {
-            int pos = atomicAdd(&s_count, 1);
-            out->mv[pos] = make_int2(rowof[q] - 1, rowof[idx[q]] - 1);
+    // group 1 and the inverse map of the block-origin rows
+    int* srcA = out->data;
+    int2* pairs = reinterpret_cast<int2*>(out->data + np + (np & 1));
+    int moved = 0;
+    for (int t = tid; t < np; t += 256) {
+        const int o = cur[t];
+        srcA[t] = o - 1;
+        if (o != k1 + t) ++moved;
+        if (o >= k1 && o <= k2) inv[o - k1] = k1 + t;
+    }
+    for (int q = tid; q < LASWP_HASH; q += 256) {
+        const int r = hkey[q];
+        if (r != 0 && hval[q] != r) {
+            const int o = hval[q];
+            if (o >= k1 && o <= k2) inv[o - k1] = -r;             // block-origin row that ends outside the block
+            else { const int pos = atomicAdd(&s_extra, 1); pairs[np + pos] = make_int2(r - 1, o - 1); }   // outside -> outside (general pivots only)
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) out->count = s_count;
+    // group 2 in the order of the source row: per-thread counts over a contiguous range, exclusive scan, write
+    const int per = (np + 255) / 256;
+    int cnt = 0;
+    for (int q = tid * per; q < min(np, (tid + 1) * per); ++q) cnt += inv[q] < 0;
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int q = 0; q < 256; ++q) { const int c = s_cnt[q]; s_cnt[q] = run; run += c; } out->nout = run + s_extra; }
+    __syncthreads();
+    int pos = s_cnt[tid];
+    for (int q = tid * per; q < min(np, (tid + 1) * per); ++q)
+        if (inv[q] < 0) pairs[pos++] = make_int2(-inv[q] - 1, k1 + q - 1);
+    __syncthreads();
+    // the outside -> outside entries were parked behind the first np slots; move them behind the sorted ones
+    if (tid == 0) {
+        const int base = out->nout - s_extra;
+        for (int e = 0; e < s_extra; ++e) pairs[base + e] = pairs[np + e];
+        out->np = np; out->k1 = k1;
+    }
+    // (counting `moved` is informational only)
+    if (moved) atomicAdd(&out->nmoved, moved);
 }
 
-constexpr int LASWP_CW = 4;   // columns per CTA in the apply kernel
-__global__ void __launch_bounds__(256) laswp_apply_kernel(int n, double* __restrict__ A, i64 lda, const MoveList* __restrict__ ml) {
+// one CTA = CW consecutive columns; shared memory: (np + nout) * CW doubles
+__global__ void __launch_bounds__(256) laswp_apply_kernel(int n, double* __restrict__ A, i64 lda, const SwapPlan* __restrict__ pl, int cw) {
     extern __shared__ double sval[];
-    const int cnt = ml->count;
-    if (cnt == 0) return;
-    const int c0 = blockIdx.x * LASWP_CW;
-    const int nc = min(LASWP_CW, n - c0);
-    const int total = cnt * nc;
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        int c = q / cnt, mvi = q - c * cnt;
-        sval[q] = A[(i64)(c0 + c) * lda + ml->mv[mvi].y];
+    const int np = pl->np, nout = pl->nout, k1 = pl->k1;
+    if (pl->nmoved == 0 && nout == 0) return;
+    const int* __restrict__ srcA = pl->data;
+    const int2* __restrict__ pairs = reinterpret_cast<const int2*>(pl->data + np + (np & 1));
+    const int c0 = blockIdx.x * cw;
+    const int nc = min(cw, n - c0);
+    double* Ac = A + (i64)c0 * lda;
+    const int tot = np + nout;
+    // gather: thread = move, inner loop = columns (all loads of a thread in flight together)
+    for (int q = threadIdx.x; q < tot; q += 256) {
+        int src;
+        bool need;
+        if (q < np) { src = srcA[q]; need = src != k1 - 1 + q; } else { src = pairs[q - np].y; need = true; }
+        if (need) {
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) sval[(size_t)c * tot + q] = Ac[(i64)c * lda + src];
+        }
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        int c = q / cnt, mvi = q - c * cnt;
-        A[(i64)(c0 + c) * lda + ml->mv[mvi].x] = sval[q];
+    for (int q = threadIdx.x; q < tot; q += 256) {
+        int dst;
+        bool need;
+        if (q < np) { dst = k1 - 1 + q; need = srcA[q] != dst; } else { dst = pairs[q - np].x; need = true; }
+        if (need) {
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) Ac[(i64)c * lda + dst] = sval[(size_t)c * tot + q];
+        }
     }
 }
 
-// max row touched must be known for variant B; the caller passes `rows_hint` (0 = unknown)
+static size_t swap_plan_bytes(int np) { return sizeof(SwapPlan) + sizeof(int) * ((size_t)np + 1 + 4 * (size_t)np + 2); }
+static void laswp_attr() {
+    static bool attr = false;
+    if (!attr) {
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (3 * LASWP_MAX_PIV + 2 * LASWP_HASH) * 4));
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAX_PIV * 4 * 8));
+        attr = true;
+    }
+}
+static SwapPlan* swap_plan_build(cudaStream_t s, int k1, int k2, const int* ipiv, int incx) {
+    const int cnt = k2 - k1 + 1;
+    laswp_attr();
+    SwapPlan* pl = (SwapPlan*)ws_alloc(s, swap_plan_bytes(cnt));
+    LB_CUDA_CHECK(cudaMemsetAsync(pl, 0, sizeof(SwapPlan), s));
+    laswp_build_kernel<<<1, 256, (size_t)(3 * cnt + 2 * LASWP_HASH) * sizeof(int), s>>>(cnt, k1, k2, ipiv, incx, pl);
+    count_launch();
+    return pl;
+}
+static void swap_plan_apply(cudaStream_t s, int n, double* A, i64 lda, const SwapPlan* pl, int npiv) {
+    if (n <= 0 || !pl) return;
+    // columns per CTA: as many as fit next to 2*npiv staged rows (<= 128 KB), at most 8, and enough CTAs to fill the GPU
+    int cw = (int)((size_t)(2 * LASWP_MAX_PIV * 4) / (size_t)(2 * npiv));
+    cw = max(1, min(8, cw));
+    while (cw > 1 && ceil_div(n, cw) < 2 * num_sms()) cw >>= 1;
+    laswp_apply_kernel<<<ceil_div(n, cw), 256, (size_t)2 * npiv * cw * sizeof(double), s>>>(n, A, lda, pl, cw);
+    count_launch();
+}
+
+// ---- few columns, many interchanges (DGETRS right-hand sides: all n pivots on nrhs columns; dgetrs.f:187,217).  The whole
+// sequence is composed on an index array in shared memory by ONE thread (rows up to LASWP_LONG_MAX), then every column is
+// permuted by a gather into scratch and a copy back.
+constexpr int LASWP_LONG_MAX = 55 * 1024;
+constexpr int LASWP_LONG_TILE = 1024;
+__global__ void __launch_bounds__(256) laswp_long_build_kernel(int rows, int k1, int k2, const int* __restrict__ ipiv, int incx,
+                                                               int* __restrict__ src_out) {
+    extern __shared__ int cur[];      // cur[r] = original row (0-based) stored in row r; then one tile of pivots
+    int* ptile = cur + rows;
+    for (int r = threadIdx.x; r < rows; r += 256) cur[r] = r;
+    const int np = k2 - k1 + 1;
+    const int ix0 = incx > 0 ? k1 : k1 + (k1 - k2) * incx;
+    for (int t0 = 0; t0 < np; t0 += LASWP_LONG_TILE) {
+        const int tn = min(LASWP_LONG_TILE, np - t0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < tn; q += 256) ptile[q] = ipiv[ix0 + (t0 + q) * incx - 1];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < tn; ++q) {
+                const int t = t0 + q;
+                const int i = incx > 0 ? k1 + t : k2 - t;          // dlaswp.f:152-167
+                const int ip = ptile[q];
+                if (ip != i) { const int a = cur[i - 1]; cur[i - 1] = cur[ip - 1]; cur[ip - 1] = a; }
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < rows; r += 256) src_out[r] = cur[r];
+}
+__global__ void laswp_long_gather_kernel(int rows, int n, const double* __restrict__ A, i64 lda, const int* __restrict__ src,
+                                         double* __restrict__ W) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int sr = src[r];
+    for (int c = blockIdx.y; c < n; c += gridDim.y) W[r + (i64)c * rows] = A[sr + (i64)c * lda];
+}
+__global__ void laswp_long_copy_kernel(int rows, int n, const double* __restrict__ W, const int* __restrict__ src, double* __restrict__ A, i64 lda) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    if (src[r] == r) return;
+    for (int c = blockIdx.y; c < n; c += gridDim.y) A[r + (i64)c * lda] = W[r + (i64)c * rows];
+}
+
 static void laswp_impl(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx,
                        int rows_hint) {
     if (n <= 0 || incx == 0 || k2 < k1) return;
-    (void)rows_hint;
     const int np_all = k2 - k1 + 1;
-    if (np_all >= 4) {
-        // process in chunks of at most 2048 interchanges (shared-memory bound of the build kernel)
-        const int abs_inc = incx > 0 ? incx : -incx;
+    const int abs_inc = incx > 0 ? incx : -incx;
+    if (rows_hint > 0 && rows_hint <= LASWP_LONG_MAX && np_all > LASWP_MAX_PIV / 4 && n <= 64) {
         static bool attr = false;
         if (!attr) {
-            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * LASWP_MAX_PIV * 4));
-            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               2 * LASWP_MAX_PIV * LASWP_CW * 8));
+            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_long_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (LASWP_LONG_MAX + LASWP_LONG_TILE) * 4));
             attr = true;
         }
+        int* src = (int*)ws_alloc(s, sizeof(int) * (size_t)rows_hint);
+        double* W = (double*)ws_alloc(s, sizeof(double) * (size_t)rows_hint * n);
+        laswp_long_build_kernel<<<1, 256, (size_t)(rows_hint + LASWP_LONG_TILE) * sizeof(int), s>>>(rows_hint, k1, k2, ipiv, incx, src);
+        dim3 grid(ceil_div(rows_hint, 256), (unsigned)n);
+        laswp_long_gather_kernel<<<grid, 256, 0, s>>>(rows_hint, n, A, lda, src, W);
+        laswp_long_copy_kernel<<<grid, 256, 0, s>>>(rows_hint, n, W, src, A, lda);
+        count_launch(3);
+        ws_free(s, src);
+        ws_free(s, W);
+        LB_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    if (np_all >= 4) {
+        // process in chunks of at most 2048 interchanges (shared-memory bound of the build kernel)
         for (int done = 0; done < np_all; done += LASWP_MAX_PIV) {
             int cnt = min(LASWP_MAX_PIV, np_all - done);
             int ck1, ck2;
-            const int* cpiv;
-            if (incx > 0) { ck1 = k1 + done; ck2 = ck1 + cnt - 1; cpiv = ipiv + (i64)(ck1 - k1) * (incx - 1); }
-            else { ck2 = k2 - done; ck1 = ck2 - cnt + 1; cpiv = ipiv + (i64)(k1 - ck1) + (i64)(k2 - ck2) * abs_inc; }
-            MoveList* ml = (MoveList*)ws_alloc(s, sizeof(MoveList) + sizeof(int2) * 2 * cnt);
-            laswp_build_kernel<<<1, 256, (size_t)6 * cnt * sizeof(int), s>>>(cnt, ck1, ck2, cpiv, incx, ml);
-            laswp_apply_kernel<<<ceil_div(n, LASWP_CW), 256, (size_t)2 * cnt * LASWP_CW * sizeof(double), s>>>(n, A, lda, ml);
-            count_launch(2);
-            ws_free(s, ml);
+            if (incx > 0) { ck1 = k1 + done; ck2 = ck1 + cnt - 1; }
+            else { ck2 = k2 - done; ck1 = ck2 - cnt + 1; }
+            // the pivot of row i sits at ipiv[(k1 + (i-k1)*|incx|) - 1] in both directions (dlaswp.f:138-150); a sub-call with
+            // k1' = ck1 looks at ipiv'[(ck1 + (i-ck1)*|incx|) - 1], so the base pointer moves by (ck1-k1)*(|incx|-1)
+            const int* cpiv = ipiv + (i64)(ck1 - k1) * (abs_inc - 1);
+            SwapPlan* pl = swap_plan_build(s, ck1, ck2, cpiv, incx);
+            swap_plan_apply(s, n, A, lda, pl, cnt);
+            ws_free(s, pl);
         }
         LB_CUDA_CHECK(cudaGetLastError());
         return;
     }
-    // chunk the pivot list so that it fits in shared memory, preserving the application order
-    int abs_inc = incx > 0 ? incx : -incx;
-    for (int done = 0; done < k2 - k1 + 1; done += LASWP_MAX_PIV) {
-        int cnt = min(LASWP_MAX_PIV, k2 - k1 + 1 - done);
-        int ck1, ck2;
-        const int* cpiv = ipiv;
-        if (incx > 0) { ck1 = k1 + done; ck2 = ck1 + cnt - 1; }
-        else { ck2 = k2 - done; ck1 = ck2 - cnt + 1; }
-        // For chunked calls the pivot of row i must still be found at the same address as in the full call.
-        // Forward: address(i) = ipiv[(k1 + (i-k1)*incx) - 1]; a sub-call with k1'=ck1 uses ipiv'[(ck1 + (i-ck1)*incx) - 1],
-        // so shift the base pointer by (ck1-k1)*(incx-1).  Reverse: address(i) = ipiv[(k1 + (k2-i)*abs) - 1]
-        // (dlaswp.f:143-146); a sub-call uses ipiv'[(ck1 + (ck2-i)*abs) - 1], so shift by (k1-ck1) + (k2-ck2)*abs.
-        if (incx > 0) cpiv = ipiv + (i64)(ck1 - k1) * (incx - 1);
-        else cpiv = ipiv + (i64)(k1 - ck1) + (i64)(k2 - ck2) * abs_inc;
+    // a handful of interchanges: one thread per column walks the list
+    {
         int threads = 128;
-        laswp_cols_kernel<<<ceil_div(n, threads), threads, (size_t)cnt * sizeof(int), s>>>(n, A, lda, ck1, ck2, cpiv, incx);
+        laswp_cols_kernel<<<ceil_div(n, threads), threads, (size_t)np_all * sizeof(int), s>>>(n, A, lda, k1, k2, ipiv, incx);
         count_launch();
     }
     LB_CUDA_CHECK(cudaGetLastError());
@@ -192,25 +317,13 @@ void laswp(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int*
 void* laswp_plan(cudaStream_t s, int k1, int k2, const int* ipiv, int incx) {
     const int cnt = k2 - k1 + 1;
     if (cnt <= 0 || cnt > LASWP_MAX_PIV) return nullptr;
-    static bool attr = false;
-    if (!attr) {
-        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * LASWP_MAX_PIV * 4));
-        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           2 * LASWP_MAX_PIV * LASWP_CW * 8));
-        attr = true;
-    }
-    MoveList* ml = (MoveList*)ws_alloc(s, sizeof(MoveList) + sizeof(int2) * 2 * cnt);
-    laswp_build_kernel<<<1, 256, (size_t)6 * cnt * sizeof(int), s>>>(cnt, k1, k2, ipiv, incx, ml);
-    count_launch();
-    return ml;
+    return swap_plan_build(s, k1, k2, ipiv, incx);
 }
 void laswp_apply_plan(cudaStream_t s, int n, double* A, i64 lda, const void* plan, int npiv) {
-    if (n <= 0 || !plan) return;
-    laswp_apply_kernel<<<ceil_div(n, LASWP_CW), 256, (size_t)2 * npiv * LASWP_CW * sizeof(double), s>>>(n, A, lda, (const MoveList*)plan);
-    count_launch();
+    swap_plan_apply(s, n, A, lda, (const SwapPlan*)plan, npiv);
 }
 void laswp_plan_free(cudaStream_t s, void* plan) { ws_free(s, plan); }
-// variant with a known row extent (all pivots < rows): lets few-column calls use the staged kernel
+// variant with a known row extent (every pivot <= rows): lets few-column calls with long pivot lists use the composed path
 void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx) {
     laswp_impl(s, n, A, lda, k1, k2, ipiv, incx, rows);
 }

@@ -18,6 +18,7 @@ void getrf_set_big_leaf(int v);
 void geqrf_set_cluster_max(int c);
 void potrf_set_params(int nb, int lookahead);
 void geqrf_set_params(int nb, int lookahead);
+void trsm_set_fewrhs_mode(int mode);
 }  // namespace lb
 
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
@@ -50,6 +51,8 @@ void lb200_set_getrf_big_leaf(int rows4) { lb::getrf_set_big_leaf(rows4); }
 void lb200_set_geqrf_cluster_max(int ctas) { lb::geqrf_set_cluster_max(ctas); }
 void lb200_set_potrf_params(int nb, int lookahead) { lb::potrf_set_params(nb, lookahead); }
 void lb200_set_geqrf_params(int nb, int lookahead) { lb::geqrf_set_params(nb, lookahead); }
+void lb200_set_fewrhs_mode(int mode) { lb::trsm_set_fewrhs_mode(mode); }
+int lb200_set_l2_fetch_granularity(int bytes) { return (int)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes); }
 #endif
 
 int lb200_dgemm(void* stream, char transa, char transb, int m, int n, int k, double alpha, const double* dA,

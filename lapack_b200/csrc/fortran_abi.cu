@@ -88,6 +88,23 @@ PtrKind ptr_kind(const void* p) {
 
 std::mutex g_abi_mutex;     // one Fortran-ABI call at a time (the reference is re-entrant; we serialise)
 
+// A large PAGEABLE host matrix (what a Fortran caller's ALLOCATE or malloc gives) is page-locked for the duration of the
+// call, so that the streamed paths below (asynchronous DMA overlapped with the factorization) apply to it too; without
+// this every cudaMemcpyAsync from it degrades to a synchronous staged copy.  LAPACK_B200_HOST_REGISTER=0 disables it.
+struct TempPin {
+    void* base = nullptr;
+    TempPin(const void* p, size_t bytes, size_t min_bytes = (size_t)256 << 20) {
+        static int enabled = -1;
+        if (enabled < 0) { const char* e = getenv("LAPACK_B200_HOST_REGISTER"); enabled = (e && e[0] == '0') ? 0 : 1; }
+        if (!enabled || !p || bytes < min_bytes || ptr_kind(p) != PK_HOST) return;
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) base = const_cast<void*>(p);
+        else (void)cudaGetLastError();
+    }
+    ~TempPin() { if (base && cudaHostUnregister(base) != cudaSuccess) (void)cudaGetLastError(); }
+    TempPin(const TempPin&) = delete;
+    TempPin& operator=(const TempPin&) = delete;
+};
+
 cudaStream_t host_stream() {
     static cudaStream_t s = nullptr;
     if (!s) LB_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -434,6 +451,7 @@ static void getrf_common(bool recursive, const int* m, const int* n, double* A, 
     if (*m == 0 || *n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    TempPin pin(A, ((size_t)*lda * (size_t)(*n - 1) + (size_t)*m) * sizeof(double));
     if (!recursive && *m == *n && *n >= 8192 && ptr_kind(A) == PK_PINNED && ptr_kind(ipiv) != PK_DEVICE) {
         *info = getrf_host_streamed(*n, A, *lda, ipiv);
         return;
@@ -666,6 +684,7 @@ static void potrf_common(bool recursive, const char* uplo, const int* n, double*
     if (*n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    TempPin pin(A, ((size_t)*lda * (size_t)(*n - 1) + (size_t)*n) * sizeof(double));
     if (!recursive && *n >= 2048 && ptr_kind(A) == PK_PINNED && 2048 % lb::potrf_block() == 0) {
         *info = potrf_host_streamed(upper, *n, A, *lda);
         return;
@@ -716,6 +735,7 @@ void dposv_(const char* uplo, const int* n, const int* nrhs, double* A, const in
     if (*n == 0) return;
     if (!device_ok(info)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
+    TempPin pin(A, ((size_t)*lda * (size_t)(*n - 1) + (size_t)*n) * sizeof(double));
     if (*n >= 2048 && ptr_kind(A) == PK_PINNED && (*nrhs == 0 || ptr_kind(B) == PK_PINNED || ptr_kind(B) == PK_HOST) &&
         2048 % lb::potrf_block() == 0) {
         *info = potrf_host_streamed(upper, *n, A, *lda, *nrhs, B, *ldb);

@@ -269,6 +269,10 @@ static void trsm_right_rec(cudaStream_t s, bool upper, bool trans, bool unit, in
 //     the rest of the leaf;
 //   * the off-diagonal updates are streaming GEMV kernels (coalesced, all SMs, fixed summation order).
 constexpr int FR_LEAF = 128, FR_MAXRHS = 8;
+void trsv_stream(cudaStream_t s, bool upper, bool trans, bool unit, int n, int nrhs, const double* A, i64 lda, double* B,
+                 i64 ldb);                      // trsv_stream.cu: one persistent kernel per solve
+static int g_fewrhs_mode = 1;                   // 1 = persistent streaming kernel (default), 0 = leaf/GEMV recursion
+void trsm_set_fewrhs_mode(int mode) { g_fewrhs_mode = mode; }
 
 template <bool eff_lower>     // (L,N) / (U,T): forward substitution; otherwise backward
 __global__ void __launch_bounds__(256) trsm_left_fewrhs_kernel(int m, int nrhs, const double* __restrict__ A, i64 lda,
@@ -511,7 +515,8 @@ void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, in
         trsm_left_lower_small_kernel<<<ceil_div(n, TS_COLS), 256, 0, s>>>(m, n, A, lda, unit, B, ldb);
         count_launch();
     } else if (left && n <= FR_MAXRHS && m > FR_LEAF) {
-        trsm_left_fewrhs_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
+        if (g_fewrhs_mode == 1) trsv_stream(s, upper, tr, unit, m, n, A, lda, B, ldb);
+        else trsm_left_fewrhs_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     } else if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     else trsm_right_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
     LB_CUDA_CHECK(cudaGetLastError());
