@@ -202,12 +202,12 @@ class StdoutToStderr:
 
 # ----------------------------------------------------------------------------------------------- GPU leg
 def run_dist(args, rank, world, local_rank):
-    """N > 1: ONE DGETRF of order n_dist block-column-cyclic over the N GPUs (BASELINE configs[4]); NCCL panel broadcast."""
+    """N > 1: ONE DGETRF of order n_dist, 2D block-cyclic on a P x Q grid over the N GPUs (BASELINE configs[4])."""
+    import numpy as np
     import torch
     import torch.distributed as dist
     import lapack_b200 as lb
-    from lapack_b200.dist import BlockCyclic1D, GpuOps, fill_local_random, pgetrf
-    from lapack_b200.dist_check import randomized_residual
+    from lapack_b200.dist2d import BlockCyclic2D, GpuOps2D, Groups, default_grid, fill_local_random_2d, pgetrf2d, randomized_residual_2d
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
@@ -215,23 +215,44 @@ def run_dist(args, rank, world, local_rank):
     dist.init_process_group("nccl", device_id=dev)
     L = lb.lib()
     n, nb = args.n_dist, args.nb_dist
-    desc = BlockCyclic1D(n, nb, world, rank)
-    ops = GpuOps(dev)
-    a0 = fill_local_random(ops, desc, device=dev)
-    a = lb.dev.colmajor(n, desc.local_cols(), device=dev)
-    fl = flops_getrf(n)
+    if args.grid:
+        P, Q = (int(v) for v in args.grid.lower().split("x"))
+    else:
+        P, Q = 1, world                           # measured faster than default_grid(world) on NVSwitch (profiles/r02_grid_compare.txt)
+    assert P * Q == world, (P, Q, world)
+    desc = BlockCyclic2D(n, nb, P, Q, rank)
+    ops = GpuOps2D(dev)
+    groups = Groups(dist, desc)
 
     def barrier():
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- correctness gate BEFORE timing: the same driver at n=8192 on both grids against the single-GPU factorization
+    # of the same DLARNV matrix -- IPIV must be identical (tests/test_gpu_dist.py needs >= 2 GPUs, so the bench carries it)
+    checks = {}
+    if not args.no_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from _dist2d_gpu_worker import check_against_single_gpu
+        for (cp, cq) in sorted({(P, Q), default_grid(world)}):
+            cdesc = BlockCyclic2D(8192, nb, cp, cq, rank)
+            cgroups = groups if (cp, cq) == (P, Q) else Groups(dist, cdesc)
+            ok, msg = check_against_single_gpu(dev, cdesc, cgroups, ops)
+            checks[f"n8192_grid_{cp}x{cq}_ipiv_equals_single_gpu"] = ok
+            checks[f"n8192_grid_{cp}x{cq}"] = msg
+            assert ok, msg
+        torch.cuda.empty_cache()
+
+    a0 = fill_local_random_2d(desc, device=dev)
+    a = lb.dev.colmajor(desc.mloc, desc.nloc, device=dev)
+    fl = flops_getrf(n)
     ipiv = info = None
     for _ in range(max(args.warmup, 1)):
         a.copy_(a0)
-        ipiv, info = pgetrf(ops, dist, desc, a)
+        ipiv, info = pgetrf2d(ops, dist, desc, a, groups)
     barrier()
-    resid = None if args.no_check else randomized_residual(torch, dist, desc, a0, a, ipiv)
+    resid = None if args.no_check else randomized_residual_2d(torch, dist, desc, a0, a, ipiv)
     sampler = ClockSampler(local_rank)
     launches0 = L.lb200_launch_count()
     barrier()
@@ -240,7 +261,7 @@ def run_dist(args, rank, world, local_rank):
     e0.record()
     for _ in range(args.steps):
         a.copy_(a0)
-        pgetrf(ops, dist, desc, a)
+        pgetrf2d(ops, dist, desc, a, groups)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -259,13 +280,19 @@ def run_dist(args, rank, world, local_rank):
     batched["ms_max_over_ranks"] = bt.item()
     batched["aggregate_matrices_per_s"] = (1 << 20) / (bt.item() * 1e-3)
     if rank == 0:
+        t1 = None
+        try:
+            t1 = json.load(open(os.path.join(ROOT, "profiles", "r02_t1_dgetrf_131072.json")))
+        except Exception:
+            pass
         line = {
             "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"one DGETRF n={n} (BASELINE configs[4]) distributed block-column-cyclic (2D block-cyclic, 1 x {world} grid, NB={nb}) "
-                                   "over the GPUs; panel + pivots broadcast with NCCL, look-ahead; DLARNV(2) seed 1988-1991",
-                       "n": n, "parallelism": f"block-cyclic 1x{world}", "l2": "local matrix far larger than L2; restored from an HBM copy every step"},
+            "config": {"workload": f"one DGETRF n={n} (BASELINE configs[4]) 2D block-cyclic on a {P} x {Q} process grid, NB={nb}; panel "
+                                   "gathered to the diagonal owner + broadcast along process rows with NCCL, row interchanges and U12 "
+                                   "exchanged inside process columns, panel one step ahead on its own stream; DLARNV(2) seed 1988-1991",
+                       "n": n, "parallelism": f"2D block-cyclic {P}x{Q}", "l2": "local matrix far larger than L2; restored from an HBM copy every step"},
             "pct_of_fp64_peak": value / (world * peak), "roofline": {"bound": "tensor", "achieved": value / world, "peak": peak, "unit": "TFLOP/s",
                                                                        "frac": value / (world * peak), "traffic": None,
                                                                        "note": "whole-factorization rate per GPU vs the in-run DMMA peak"},
@@ -273,7 +300,9 @@ def run_dist(args, rank, world, local_rank):
             "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 4,
                     "note": "the distributed matrix is generated on the devices (128 GiB does not pass through one host buffer); only IPIV/INFO return to the host"},
             "gpu_launches": int(lt.item()), "clocks": clocks,
-            "checks": {"randomized_residual_ratio": resid, "info": int(info)},
+            "checks": dict(checks, randomized_residual_ratio=resid, info=int(info)),
+            "t1_single_gpu_same_n": t1,
+            "parallel_efficiency_vs_t1": (t1["ms"] / (world * ms / args.steps)) if (t1 and t1.get("n") == n) else None,
             "batched_dgetrf_32x32": batched,
         }
         OUT.emit(json.dumps(line))
@@ -590,6 +619,7 @@ def main():
     ap.add_argument("--n", type=int, default=32768)
     ap.add_argument("--n-dist", type=int, default=131072, help="order of the single distributed DGETRF when --gpus > 1")
     ap.add_argument("--nb-dist", type=int, default=512)
+    ap.add_argument("--grid", default="", help="process grid PxQ of the distributed DGETRF (default 1xN)")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent n=32768 replicas instead of one distributed matrix")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")

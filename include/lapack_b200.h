@@ -98,6 +98,16 @@ int lb200_dpotrf_batched32(void* stream, char uplo, long long batch, double* dA,
  * starting `stream_offset` draws after `iseed` (O(log n) jump-ahead, bit-identical to DLARNV(2)). */
 int lb200_dlarnv_matrix(void* stream, const int iseed[4], long long stream_offset, int m, int n, double* dA,
                         long long lda);
+/* window of a global DLARNV matrix with stream_ld rows: A(i,j) = draw (stream_offset + j*stream_ld + i) */
+int lb200_dlarnv_submatrix(void* stream, const int iseed[4], long long stream_offset, long long stream_ld, int m, int n,
+                           double* dA, long long lda);
+/* building blocks of the P x Q distributed DGETRF (lapack_b200/dist2d.py): one panel's interchanges (SRC/dlaswp.f:152-167 with
+ * DGETRF's pivots, relative to the panel's first row, 1-based, np <= 2048) composed into src_top[t] = relative row whose
+ * content ends in panel row t and inv_top[t] = relative row where the original panel row t ends; row gather / scatter
+ * between a column-major matrix and a packed np x ncols buffer (idx[t] < 0 skips the row) */
+int lb200_laswp_compose(void* stream, int np, const int* dipiv_rel, int* dsrc_top, int* dinv_top);
+int lb200_gather_rows(void* stream, int nidx, const int* didx, const double* dA, long long lda, int ncols, double* dW, long long ldw);
+int lb200_scatter_rows(void* stream, int nidx, const int* didx, const double* dW, long long ldw, int ncols, double* dA, long long lda);
 int lb200_make_spd(void* stream, int n, double* dA, long long lda, double shift); /* A := (A+A')/2 + shift*I */
 int lb200_dlacpy(void* stream, char uplo, int m, int n, const double* dA, long long lda, double* dB, long long ldb);
 int lb200_transpose(void* stream, int m, int n, const double* dA, long long lda, double* dB, long long ldb);

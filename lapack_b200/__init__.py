@@ -77,6 +77,12 @@ def _declare(L):
     L.lb200_dpotrf_batched32.argtypes = [VP, ch, LL, VP, VP]
     L.lb200_dlarnv_matrix.argtypes = [VP, C.POINTER(C.c_int * 4), LL, i, i, VP, LL]
     L.lb200_make_spd.argtypes = [VP, i, VP, LL, d]
+    L.lb200_dlarnv_submatrix.argtypes = [VP, C.POINTER(C.c_int * 4), LL, LL, i, i, VP, LL]
+    L.lb200_laswp_compose.argtypes = [VP, i, VP, VP, VP]
+    L.lb200_gather_rows.argtypes = [VP, i, VP, VP, LL, i, VP, LL]
+    L.lb200_scatter_rows.argtypes = [VP, i, VP, VP, LL, i, VP, LL]
+    L.lb200_set_fewrhs_mode.argtypes = [i]
+    L.lb200_set_l2_fetch_granularity.argtypes = [i]
     L.lb200_dlacpy.argtypes = [VP, ch, i, i, VP, LL, VP, LL]
     L.lb200_transpose.argtypes = [VP, i, i, VP, LL, VP, LL]
     L.lb200_set_xerbla_mode.argtypes = [i]

@@ -328,6 +328,99 @@ void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int
     laswp_impl(s, n, A, lda, k1, k2, ipiv, incx, rows);
 }
 
+// ---- pieces of the row interchanges for the P x Q distributed LU (lapack_b200/dist2d.py), where the rows of one panel's
+// interchanges live on different GPUs.  compose: the np transpositions (pivots relative to the block, 1-based, ip >= i as
+// DGETRF produces them) as two maps over the np block rows: src_top[t] = original relative row whose content ends in block
+// row t;  inv_top[t] = relative row where the original block row t ends (0-based, relative to the first block row).
+__global__ void __launch_bounds__(256) laswp_compose_kernel(int np, const int* __restrict__ ipiv, int* __restrict__ src_top,
+                                                            int* __restrict__ inv_top) {
+    extern __shared__ int sm[];
+    int* cur = sm;                    // [np]
+    int* hkey = sm + np;              // [HASH] relative row + 1, 0 = empty
+    int* hval = hkey + LASWP_HASH;
+    const int tid = threadIdx.x;
+    for (int t = tid; t < np; t += 256) { cur[t] = t; inv_top[t] = -1; }
+    for (int q = tid; q < LASWP_HASH; q += 256) hkey[q] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < np; ++t) {
+            const int ip = ipiv[t] - 1;          // relative, 0-based
+            if (ip == t) continue;
+            const int a = cur[t];
+            if (ip < np) { cur[t] = cur[ip]; cur[ip] = a; }
+            else {
+                int h = swp_hash(ip);
+                while (hkey[h] != 0 && hkey[h] != ip + 1) h = (h + 1) & (LASWP_HASH - 1);
+                if (hkey[h] == 0) { hkey[h] = ip + 1; hval[h] = ip; }
+                cur[t] = hval[h];
+                hval[h] = a;
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < np; t += 256) {
+        const int o = cur[t];
+        src_top[t] = o;
+        if (o < np) inv_top[o] = t;
+    }
+    __syncthreads();
+    for (int q = tid; q < LASWP_HASH; q += 256)
+        if (hkey[q] != 0 && hval[q] < np) inv_top[hval[q]] = hkey[q] - 1;
+}
+void laswp_compose(cudaStream_t s, int np, const int* ipiv, int* src_top, int* inv_top) {
+    if (np <= 0) return;
+    laswp_attr();
+    static bool attr = false;
+    if (!attr) {
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LASWP_MAX_PIV + 2 * LASWP_HASH) * 4));
+        attr = true;
+    }
+    laswp_compose_kernel<<<1, 256, (size_t)(np + 2 * LASWP_HASH) * sizeof(int), s>>>(np, ipiv, src_top, inv_top);
+    count_launch();
+    LB_CUDA_CHECK(cudaGetLastError());
+}
+// W(t, c) = A(idx[t], c) for idx[t] >= 0 (W column-major nidx x ncols, ldw); rows with idx < 0 are left untouched
+__global__ void gather_rows_kernel(int nidx, const int* __restrict__ idx, const double* __restrict__ A, i64 lda, int ncols,
+                                   double* __restrict__ W, i64 ldw) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nidx) return;
+    const int r = idx[t];
+    if (r < 0) return;
+    for (int c = blockIdx.y * 8; c < ncols; c += gridDim.y * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c + u < ncols) ? A[r + (i64)(c + u) * lda] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (c + u < ncols) W[t + (i64)(c + u) * ldw] = v[u];
+    }
+}
+__global__ void scatter_rows_kernel(int nidx, const int* __restrict__ idx, const double* __restrict__ W, i64 ldw, int ncols,
+                                    double* __restrict__ A, i64 lda) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nidx) return;
+    const int r = idx[t];
+    if (r < 0) return;
+    for (int c = blockIdx.y * 8; c < ncols; c += gridDim.y * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c + u < ncols) ? W[t + (i64)(c + u) * ldw] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (c + u < ncols) A[r + (i64)(c + u) * lda] = v[u];
+    }
+}
+void gather_rows(cudaStream_t s, int nidx, const int* idx, const double* A, i64 lda, int ncols, double* W, i64 ldw) {
+    if (nidx <= 0 || ncols <= 0) return;
+    dim3 grid(ceil_div(nidx, 128), (unsigned)min(ceil_div(ncols, 8), 16384));
+    gather_rows_kernel<<<grid, 128, 0, s>>>(nidx, idx, A, lda, ncols, W, ldw);
+    count_launch();
+}
+void scatter_rows(cudaStream_t s, int nidx, const int* idx, const double* W, i64 ldw, int ncols, double* A, i64 lda) {
+    if (nidx <= 0 || ncols <= 0) return;
+    dim3 grid(ceil_div(nidx, 128), (unsigned)min(ceil_div(ncols, 8), 16384));
+    scatter_rows_kernel<<<grid, 128, 0, s>>>(nidx, idx, W, ldw, ncols, A, lda);
+    count_launch();
+}
+
 // ----------------------------------------------------------------------------------------------
 __global__ void lacpy_kernel(int uplo, int m, int n, const double* __restrict__ A, i64 lda, double* __restrict__ B,
                              i64 ldb) {
@@ -423,6 +516,30 @@ void larnv_matrix(cudaStream_t s, const int iseed[4], i64 stream_offset, int m, 
     i64 total = (i64)m * n;
     i64 threads = (total + LARNV_CHUNK - 1) / LARNV_CHUNK;
     larnv_matrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(seed, stream_offset, m, n, A, lda);
+    count_launch();
+}
+// A(i,j) = draw number (offset + j*stream_ld + i) of the stream: an m x n window of a global column-major DLARNV matrix with
+// stream_ld rows (2D block-cyclic pieces of ONE global matrix)
+__global__ void larnv_submatrix_kernel(unsigned long long seed, i64 offset, i64 stream_ld, int m, int n, double* __restrict__ A, i64 lda) {
+    const unsigned long long MASK = (1ULL << 48) - 1, AMUL = 33952834046453ULL;
+    const int chunks = (m + LARNV_CHUNK - 1) / LARNV_CHUNK;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (i64)chunks * n) return;
+    const int j = (int)(t / chunks), i0 = (int)(t - (i64)j * chunks) * LARNV_CHUNK;
+    unsigned long long st = (seed * lcg_pow((unsigned long long)(offset + (i64)j * stream_ld + i0))) & MASK;
+#pragma unroll
+    for (int q = 0; q < LARNV_CHUNK; ++q) {
+        if (i0 + q >= m) break;
+        st = (st * AMUL) & MASK;
+        A[i0 + q + (i64)j * lda] = 2.0 * ((double)st * (1.0 / 281474976710656.0)) - 1.0;
+    }
+}
+void larnv_submatrix(cudaStream_t s, const int iseed[4], i64 stream_offset, i64 stream_ld, int m, int n, double* A, i64 lda) {
+    if (m <= 0 || n <= 0) return;
+    unsigned long long seed = ((unsigned long long)iseed[0] << 36) | ((unsigned long long)iseed[1] << 24) |
+                              ((unsigned long long)iseed[2] << 12) | (unsigned long long)iseed[3];
+    const i64 threads = (i64)((m + LARNV_CHUNK - 1) / LARNV_CHUNK) * n;
+    larnv_submatrix_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(seed, stream_offset, stream_ld, m, n, A, lda);
     count_launch();
 }
 void larnv_fill(cudaStream_t s, int idist, const int iseed[4], i64 offset, i64 count, double* x) {

@@ -159,6 +159,24 @@ int lb200_dlarnv_matrix(void* stream, const int iseed[4], long long stream_offse
     lb::larnv_matrix(S(stream), iseed, stream_offset, m, n, dA, lda);
     return rc();
 }
+int lb200_dlarnv_submatrix(void* stream, const int iseed[4], long long stream_offset, long long stream_ld, int m, int n,
+                           double* dA, long long lda) {
+    lb::larnv_submatrix(S(stream), iseed, stream_offset, stream_ld, m, n, dA, lda);
+    return rc();
+}
+int lb200_laswp_compose(void* stream, int np, const int* dipiv_rel, int* dsrc_top, int* dinv_top) {
+    if (np > 2048) return -1;
+    lb::laswp_compose(S(stream), np, dipiv_rel, dsrc_top, dinv_top);
+    return rc();
+}
+int lb200_gather_rows(void* stream, int nidx, const int* didx, const double* dA, long long lda, int ncols, double* dW, long long ldw) {
+    lb::gather_rows(S(stream), nidx, didx, dA, lda, ncols, dW, ldw);
+    return rc();
+}
+int lb200_scatter_rows(void* stream, int nidx, const int* didx, const double* dW, long long ldw, int ncols, double* dA, long long lda) {
+    lb::scatter_rows(S(stream), nidx, didx, dW, ldw, ncols, dA, lda);
+    return rc();
+}
 int lb200_make_spd(void* stream, int n, double* dA, long long lda, double shift) {
     lb::make_spd(S(stream), n, dA, lda, shift);
     return rc();

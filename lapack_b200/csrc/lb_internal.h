@@ -52,6 +52,10 @@ void transpose(cudaStream_t s, int m, int n, const double* A, i64 lda, double* B
 void larnv_fill(cudaStream_t s, int idist, const int iseed[4], i64 offset, i64 count, double* x);
 void larnv_matrix(cudaStream_t s, const int iseed[4], i64 stream_offset, int m, int n, double* A, i64 lda);
 void make_spd(cudaStream_t s, int n, double* A, i64 lda, double shift);  // A := (A+A^T)/2 + shift*I
+void larnv_submatrix(cudaStream_t s, const int iseed[4], i64 stream_offset, i64 stream_ld, int m, int n, double* A, i64 lda);
+void laswp_compose(cudaStream_t s, int np, const int* ipiv_rel, int* src_top, int* inv_top);
+void gather_rows(cudaStream_t s, int nidx, const int* idx, const double* A, i64 lda, int ncols, double* W, i64 ldw);
+void scatter_rows(cudaStream_t s, int nidx, const int* idx, const double* W, i64 ldw, int ncols, double* A, i64 lda);
 void iadd(cudaStream_t s, int n, int* x, int v);
 void info_max_offset(cudaStream_t s, int* info, const int* iinfo, int offset);  // LU: first nonzero wins
 

@@ -172,6 +172,33 @@ def larnv_matrix(m, n, iseed=(1988, 1989, 1990, 1991), offset=0, ld_=None, devic
     return a
 
 
+def larnv_submatrix(a, stream_offset, stream_ld, iseed=(1988, 1989, 1990, 1991)):
+    """fill the column-major view `a` with the window of the global DLARNV(2) matrix: a(i,j) = draw (offset + j*stream_ld + i)"""
+    seed = (C.c_int * 4)(*iseed)
+    _chk(lib().lb200_dlarnv_submatrix(stream(), C.byref(seed), stream_offset, stream_ld, a.shape[0], a.shape[1], a.data_ptr(), ld(a)))
+    return a
+
+
+def laswp_compose(ipiv_rel):
+    """(src_top, inv_top) int32 device tensors for one panel's interchanges (see include/lapack_b200.h)"""
+    torch = _torch()
+    np_ = ipiv_rel.shape[0]
+    src = torch.empty(np_, dtype=torch.int32, device=ipiv_rel.device)
+    inv = torch.empty(np_, dtype=torch.int32, device=ipiv_rel.device)
+    _chk(lib().lb200_laswp_compose(stream(), np_, ipiv_rel.data_ptr(), src.data_ptr(), inv.data_ptr()))
+    return src, inv
+
+
+def gather_rows(a, idx, w):
+    """w(t, :) = a(idx[t], :) for idx[t] >= 0; a, w column-major views, idx int32"""
+    _chk(lib().lb200_gather_rows(stream(), idx.shape[0], idx.data_ptr(), a.data_ptr(), ld(a), a.shape[1], w.data_ptr(), ld(w)))
+
+
+def scatter_rows(w, idx, a):
+    """a(idx[t], :) = w(t, :) for idx[t] >= 0"""
+    _chk(lib().lb200_scatter_rows(stream(), idx.shape[0], idx.data_ptr(), w.data_ptr(), ld(w), a.shape[1], a.data_ptr(), ld(a)))
+
+
 def make_spd(a, shift):
     _chk(lib().lb200_make_spd(stream(), a.shape[0], a.data_ptr(), ld(a), float(shift)))
     return a
