@@ -38,6 +38,8 @@ void lb200_set_getrf_params(int nb, int leaf, int lookahead);
 void lb200_set_getrf_cluster_max(int ctas);
 /* panels too tall for one cluster: 1 (default) = 256-thread x 4-row leaf kernel, 0 = 1024-thread x 1-row kernel */
 void lb200_set_getrf_big_leaf(int rows4);
+/* rows per CTA (1024 default / 2048 / 4096) of the leaf kernel for panels too tall for one cluster: fewer, fatter CTAs hold fewer SMs */
+void lb200_set_getrf_tall_rows(int rows_per_cta);
 void lb200_set_geqrf_cluster_max(int ctas);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);

@@ -36,6 +36,8 @@ int getrf_block() { return min(g_nb, 2048); }
 void getrf_set_cluster_max(int c) { g_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
 static int g_big_leaf_rows4 = 1;    // panels too tall for a cluster: 1 = 256 threads x 4 rows kernel, 0 = 1024 x 1 row kernel
 void getrf_set_big_leaf(int v) { g_big_leaf_rows4 = v ? 1 : 0; }
+static int g_tall_rows = 1024;      // rows per CTA of the global-packet leaf for panels too tall for one cluster: 1024 / 2048 / 4096
+void getrf_set_tall_rows(int r) { g_tall_rows = (r == 2048 || r == 4096) ? r : 1024; }
 void getrf_set_params(int nb, int leaf, int lookahead) {
     (void)leaf;
     if (nb > 0) g_nb = nb;
@@ -663,8 +665,9 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     {
         const int S4 = (pc.width > n) ? ceil_div(pc.width, CL_THREADS) : 0;
         const int cap = min(w.maxG, num_sms() - S4 - 2);
-        if (p.G > cap) {
-            int rows_per_cta = 2048;
+        const bool beyond_cluster = !(p.G <= g_cluster_max && p.G <= cluster_hw_max());
+        if (p.G > cap || (beyond_cluster && g_tall_rows > 1024)) {
+            int rows_per_cta = (p.G > cap) ? 2048 : g_tall_rows;
             if (ceil_div(m, rows_per_cta) > cap) rows_per_cta = 4096;
             p.G = ceil_div(m, rows_per_cta);
             if (p.G > cap) {

@@ -45,6 +45,14 @@ void* ws_alloc(cudaStream_t s, size_t bytes) {
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long thr = ~0ULL;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            // The panel, update and side streams all take scratch from this pool.  With the default policy the allocator
+            // may hand a block freed on one stream to another stream by INSERTING a dependency between the two streams
+            // (cudaMemPoolReuseAllowInternalDependencies), which silently serialises the high-priority panel behind a
+            // long low-priority update.  LAPACK_B200_POOL_INTERNAL_DEPS=0 restricts reuse across streams to frees that have
+            // already completed (A/B knob).
+            const char* e = getenv("LAPACK_B200_POOL_INTERNAL_DEPS");
+            int off = (e && e[0] == '0') ? 0 : 1;      // default: CUDA's default (allowed); =0 was measured neutral on one GPU
+            cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
         }
         pool_cfg = true;
     }

@@ -133,14 +133,21 @@ class Groups:
 class GpuOps2D:
     """Local compute through the lapack_b200 C ABI on torch CUDA tensors (column-major views) + the two streams."""
 
-    def __init__(self, device):
+    def __init__(self, device, panel_stream: bool = True, panel_priority: int = -1, concurrent_panel_max_rows: int = 16384):
         import torch
         from . import dev
         self.torch = torch
         self.dev = dev
         self.device = device
         self.main = torch.cuda.current_stream(device)
-        self.panel = torch.cuda.Stream(device=device, priority=-1)
+        # panel_stream=False keeps the panel on the update stream (serial schedule, for A/B measurements)
+        self.panel = torch.cuda.Stream(device=device, priority=panel_priority) if panel_stream else None
+        # Panels taller than this run on the UPDATE stream instead (between the update of their own columns and the rest of
+        # the update).  Measured (profiles/r02_dist_panel_stream_ab.txt): a tall panel's leaf kernels hold one whole SM per
+        # 1024 rows and are ~100 separate high-priority launches, each of which drains and refills the update GEMM's CTAs --
+        # overlapping them costs the GEMM 3x the panel's own duration (29.5 vs 33.4 TFLOP/s in situ); panels that fit one
+        # thread-block cluster (<= 16 SMs) overlap profitably.
+        self.concurrent_panel_max_rows = concurrent_panel_max_rows
 
     def empty_vec(self, n):
         return self.torch.empty(n, dtype=self.torch.float64, device=self.device)
@@ -174,23 +181,27 @@ class GpuOps2D:
         if a.shape[1] > 0 and idx.shape[0] > 0:
             self.dev.scatter_rows(w, idx, a)
 
-    def panel_stream(self):
+    def panel_stream(self, rows=0):
+        if self.panel is None or rows > self.concurrent_panel_max_rows:
+            return contextlib.nullcontext()
         return self.torch.cuda.stream(self.panel)
 
     def fork_panel(self):
         """panel stream waits for everything queued on the main stream so far"""
-        self.panel.wait_stream(self.main)
+        if self.panel is not None:
+            self.panel.wait_stream(self.main)
 
     def join_panel(self):
         """main stream waits for everything queued on the panel stream so far"""
-        self.main.wait_stream(self.panel)
+        if self.panel is not None:
+            self.main.wait_stream(self.panel)
 
 
 def _colmajor_view(buf, rows, cols, off=0):
     return buf[off: off + rows * cols].view(cols, rows).t()
 
 
-def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookahead: bool = True):
+def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookahead: bool = True, trace: list = None):
     """In-place LU with partial pivoting of the 2D block-cyclic matrix `aloc` (mloc x nloc column-major view).
     Returns (ipiv, info): global 1-based pivot rows (length n, replicated), INFO as DGETRF defines it."""
     torch = ops.torch
@@ -212,6 +223,12 @@ def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookah
     srecv = {}
     ipiv_all = []
     arange_nb = torch.arange(nb, device=dev, dtype=i32)
+
+    def mark():
+        """CUDA event on the current stream (tracing only)"""
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
 
     def p2p(ops_list, group):
         """issue a batch of sends / receives [(is_send, tensor, peer_rank)], return the work handles"""
@@ -337,7 +354,9 @@ def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookah
             return
         j, jb = k * nb, desc.width(k)
         pk = k % P
+        e_a = mark() if trace is not None else None
         swap_rows(k, piv, plan, c0, c1)
+        e_b = mark() if trace is not None else None
         ncols = c1 - c0
         r0 = desc.lrow0(k)
         lr1 = desc.lrow0(k + 1)
@@ -352,20 +371,33 @@ def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookah
         else:
             dist.broadcast(ubuf[: jb * ncols], src=desc.rank_of(pk, q), group=groups.col_upd)
             u = _colmajor_view(ubuf, jb, ncols)
+        e_c = mark() if trace is not None else None
         if lr1 < mloc:
             ops.gemm_update(lp[lr1 - r0:, :], u, aloc[lr1:, c0:c1])    # dgetrf.f:212
+        if trace is not None:
+            trace.append(("upd", k, e_a, e_b, e_c, mark(), 2.0 * max(0, mloc - lr1) * jb * ncols))
 
     # ------------------------------------------------------------------------------------------ driver
-    with ops.panel_stream():
+    def traced_panel(k):
+        if trace is None:
+            return panel_phase(k)
+        e0 = mark()
+        w = panel_phase(k)
+        trace.append(("panel", k, e0, mark()))
+        return w
+
+    with ops.panel_stream(n):
         ops.fork_panel()
-        works = panel_phase(0)
+        works = traced_panel(0)
     for k in range(nblk):
         j, jb = k * nb, desc.width(k)
         buf = pbuf[k % 2]
         r0 = desc.lrow0(k)
         rows = mloc - r0
+        t_begin = mark() if trace is not None else None
         wait_all(works)
         ops.join_panel()
+        t_ready = mark() if trace is not None else None
         tail = buf[rows * jb: rows * jb + tail_len]
         piv = tail[:jb].to(i32)                                        # relative to row j, 1-based
         ipiv_all.append((j, piv, tail[nb:nb + 1] * 1.0))
@@ -379,18 +411,20 @@ def pgetrf2d(ops, dist, desc: BlockCyclic2D, aloc, groups: Groups = None, lookah
             if lookahead:
                 cn0, cn1 = (desc.lcol0(nk), desc.lcol0(nk) + desc.width(nk)) if q == nk % Q else (c_after, c_after)
                 update_cols(k, piv, plan, lp, cn0, cn1)                # the next panel's columns first ...
-                with ops.panel_stream():
+                with ops.panel_stream(n - nk * nb):
                     ops.fork_panel()
-                    works = panel_phase(nk)                            # ... factor + ship it while update k continues
+                    works = traced_panel(nk)                           # ... factor + ship it while update k continues
                 update_cols(k, piv, plan, lp, cn1, nloc)
             else:
                 update_cols(k, piv, plan, lp, c_after, nloc)
-                with ops.panel_stream():
+                with ops.panel_stream(n - nk * nb):
                     ops.fork_panel()
-                    works = panel_phase(nk)
+                    works = traced_panel(nk)
         else:
             update_cols(k, piv, plan, lp, c_after, nloc)
         swap_rows(k, piv, plan, 0, c_before)                           # interchanges left of the panel (dgetrf.f:193)
+        if trace is not None:
+            trace.append(("step", k, t_begin, t_ready, mark()))
 
     import numpy as np
     ipiv = np.zeros(n, dtype=np.int32)

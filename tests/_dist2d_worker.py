@@ -77,7 +77,7 @@ class MockOps2D:
         for t in np.nonzero(ix >= 0)[0]:
             a[int(ix[t]), :] = w[t, :]
 
-    def panel_stream(self):
+    def panel_stream(self, rows=0):
         return contextlib.nullcontext()
 
     def fork_panel(self):
