@@ -99,10 +99,133 @@ __global__ void __launch_bounds__(BWARPS * 32, 5) getrf_batched32_kernel(i64 bat
     if (lane == 0) info[id] = minfo;
 }
 
+// Persistent, software-pipelined form of the same algorithm (lb200_set_batched_mode(1); NOT the default).  Idea: every warp
+// loops over matrices, the NEXT matrix is already in flight into a shared-memory stage (cp.async) while the current one is
+// factored from registers.  Measured SLOWER than the one-shot kernel (9.12 vs 7.18 ms per 1M matrices, tools/bench_batched2.py):
+// the one-shot kernel is not phase-locked on HBM vs LSU as assumed -- it is issue/latency-bound (3286 warp instructions per
+// matrix at IPC 1.77: 651 DFMA, 320 LDS, 304 predicated STS of the pivot-row publication, ~1000 instructions of pivot search
+// and interchange bookkeeping, 12% of the stall samples are instruction-cache misses of the 52 KB unrolled body;
+// profiles/r02_batched_getrf32_ncu_source.txt), and the pipelined form has fewer resident warps (158 registers, 12 warps
+// per SM instead of 20) to hide the same dependent chain.
+constexpr int PWARPS = 4;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(PWARPS * 32, 3) getrf_batched32_pipe_kernel(i64 batch, double* __restrict__ A, int* __restrict__ ipiv,
+                                                                            int* __restrict__ info) {
+    extern __shared__ __align__(16) double pstage[];          // [PWARPS][2][1024] staged matrices
+    __shared__ __align__(16) double rowbuf[PWARPS][2][BW];
+    __shared__ int posbuf[PWARPS][2];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const i64 nw = (i64)gridDim.x * PWARPS;
+    i64 id = (i64)blockIdx.x * PWARPS + w;
+    double* st = pstage + (size_t)w * 2 * (BW * BW);
+    if (id < batch) {
+        const double* src = A + id * (BW * BW);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cp_async16(st + (q * 32 + lane) * 2, src + (q * 32 + lane) * 2);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int it = 0; id < batch; id += nw, ++it) {
+        double* cur = st + (it & 1) * (BW * BW);
+        double* nxt = st + ((it + 1) & 1) * (BW * BW);
+        const i64 idn = id + nw;
+        if (idn < batch) {
+            const double* src = A + idn * (BW * BW);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) cp_async16(nxt + (q * 32 + lane) * 2, src + (q * 32 + lane) * 2);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        __syncwarp();
+        double* M = A + id * (BW * BW);
+        double a[BW];
+#pragma unroll
+        for (int q = 0; q < BW; ++q) a[q] = cur[lane + BW * q];
+        __syncwarp();                                          // the stage may be refilled two iterations from now
+        int mypos = lane;
+        bool done = false;
+        int myipiv = 0, minfo = 0;
+#pragma unroll
+        for (int c = 0; c < BW; ++c) {
+            unsigned long long kb = (unsigned long long)__double_as_longlong(fabs(a[c]));
+            bool cand = !done;
+            if (a[c] != a[c]) {                                   // NaN only wins from the first place (idamax.f:103)
+                if (mypos == c) kb = 0x7ff0000000000000ULL; else cand = false;
+            }
+            const unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+            const unsigned mh = __reduce_max_sync(full, cand ? hi : 0u);
+            const bool c1 = cand && hi == mh;
+            unsigned tie = __ballot_sync(full, c1);
+            if (__popc(tie) != 1) {
+                const unsigned ml = __reduce_max_sync(full, c1 ? lo : 0u);
+                const bool c2 = c1 && lo == ml;
+                tie = __ballot_sync(full, c2);
+                if (__popc(tie) != 1) {
+                    const unsigned mp = __reduce_min_sync(full, c2 ? (unsigned)mypos : 0xffffffffu);
+                    tie = __ballot_sync(full, c2 && (unsigned)mypos == mp);
+                }
+            }
+            const int who = __ffs(tie) - 1;
+            double* rb = rowbuf[w][c & 1];
+            if (lane == who) {
+                posbuf[w][c & 1] = mypos;
+#pragma unroll
+                for (int q = c & ~1; q < BW; q += 2) *reinterpret_cast<double2*>(rb + q) = make_double2(a[q], a[q + 1]);
+            }
+            __syncwarp();
+            const int pos = posbuf[w][c & 1];
+            if (lane == c) myipiv = pos + 1;
+            if (!done && mypos == c && lane != who) mypos = pos;
+            if (lane == who) { mypos = c; done = true; }
+            const double pivot = rb[c];
+            if (pivot == 0.0) {
+                if (minfo == 0) minfo = c + 1;                              // dgetrf2.f:212-214
+            } else if (!done) {
+                double l;
+                if (fabs(pivot) >= DBL_MIN) l = a[c] * (1.0 / pivot);       // dgetrf2.f:204-205
+                else l = a[c] / pivot;                                      // dgetrf2.f:207-209
+                a[c] = l;
+                if (c + 1 < BW) {
+                    if ((c & 1) == 0) a[c + 1] = fma(-l, rb[c + 1], a[c + 1]);
+#pragma unroll
+                    for (int q = (c + 2) & ~1; q < BW; q += 2) {
+                        const double2 pr = *reinterpret_cast<const double2*>(rb + q);
+                        a[q] = fma(-l, pr.x, a[q]);
+                        a[q + 1] = fma(-l, pr.y, a[q + 1]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < BW; ++q) __stcs(M + mypos + BW * q, a[q]);
+        ipiv[id * BW + lane] = myipiv;
+        if (lane == 0) info[id] = minfo;
+        __syncwarp();                                          // rowbuf / posbuf are reused by the next matrix
+    }
+}
+
+static int g_batched_mode = 0;     // 0 = one-shot kernel (default, faster), 1 = persistent pipelined kernel
+void batched_set_mode(int m) { g_batched_mode = m; }
+
 void getrf_batched_32(cudaStream_t s, i64 batch, double* A, int* ipiv, int* info) {
     if (batch <= 0) return;
-    const int wpb = BWARPS;
-    getrf_batched32_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, s>>>(batch, A, ipiv, info);
+    if (g_batched_mode == 1) {
+        const size_t smem = sizeof(double) * PWARPS * 2 * BW * BW;     // 64 KB
+        static bool attr = false;
+        if (!attr) {
+            LB_CUDA_CHECK(cudaFuncSetAttribute(getrf_batched32_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = true;
+        }
+        const i64 want = (batch + PWARPS - 1) / PWARPS;
+        const int grid = (int)(want < (i64)num_sms() * 3 ? want : (i64)num_sms() * 3);
+        getrf_batched32_pipe_kernel<<<grid, PWARPS * 32, smem, s>>>(batch, A, ipiv, info);
+    } else {
+        const int wpb = BWARPS;
+        getrf_batched32_kernel<<<(unsigned)((batch + wpb - 1) / wpb), wpb * 32, 0, s>>>(batch, A, ipiv, info);
+    }
     count_launch();
     LB_CUDA_CHECK(cudaGetLastError());
 }

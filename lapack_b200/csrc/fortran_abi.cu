@@ -807,47 +807,41 @@ void dgeqr2_(const int* m, const int* n, double* A, const int* lda, double* tau,
     if (r) *info = r;
 }
 
-// SRC/dlarft.f:160 -- DIRECT='F', STOREV='C' (the QR case) is implemented; no argument checking, no INFO
+// SRC/dlarft.f:160 -- all four DIRECT x STOREV schemes (the reference's own DORGLQ / DGERQF / DGEQLF / DORMxx call the others
+// through this symbol when the library is preloaded); no argument checking, no INFO, like the reference
 void dlarft_(const char* direct, const char* storev, const int* n, const int* k, const double* V, const int* ldv,
              const double* tau, double* T, const int* ldt, size_t, size_t) {
     if (*n == 0 || *k == 0) return;
-    if (!same(direct, 'F') || !same(storev, 'C')) {
-        fprintf(stderr, "lapack_b200: DLARFT supports DIRECT='F', STOREV='C' only (QR path)\n");
-        call_xerbla("DLARFT", same(direct, 'F') ? 2 : 1);
-        return;
-    }
+    const bool backward = !same(direct, 'F'), rowwise = !same(storev, 'C');
     if (!device_ok(nullptr)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
     Ctx c; c.scan({V, tau, T});
     lb::i64 lv, lt;
-    const double* dV = c.mat(V, *n, *k, *ldv, true, false, &lv);
+    const double* dV = rowwise ? c.mat(V, *k, *n, *ldv, true, false, &lv) : c.mat(V, *n, *k, *ldv, true, false, &lv);
     const double* dtau = c.vec<double>(tau, (size_t)*k, true, false);
-    double* dT = c.mat(T, *k, *k, *ldt, true, true, &lt);   // strictly lower part travels unchanged
-    lb::larft(c.s, *n, *k, dV, lv, dtau, dT, lt);
+    double* dT = c.mat(T, *k, *k, *ldt, true, true, &lt);   // the other triangle travels unchanged
+    lb::larft_general(c.s, backward, rowwise, *n, *k, dV, lv, dtau, dT, lt);
     c.finish();
 }
 
-// SRC/dlarfb.f:192 -- DIRECT='F', STOREV='C'; WORK is not used (device scratch)
+// SRC/dlarfb.f:192 -- all SIDE / TRANS / DIRECT / STOREV combinations; WORK is not used (device scratch)
 void dlarfb_(const char* side, const char* trans, const char* direct, const char* storev, const int* m, const int* n,
              const int* k, const double* V, const int* ldv, const double* T, const int* ldt, double* C, const int* ldc,
              double* work, const int* ldwork, size_t, size_t, size_t, size_t) {
     (void)work; (void)ldwork;
     if (*m <= 0 || *n <= 0) return;
-    if (!same(direct, 'F') || !same(storev, 'C')) {
-        fprintf(stderr, "lapack_b200: DLARFB supports DIRECT='F', STOREV='C' only (QR path)\n");
-        call_xerbla("DLARFB", same(direct, 'F') ? 4 : 3);
-        return;
-    }
     if (*k <= 0) return;
+    const bool backward = !same(direct, 'F'), rowwise = !same(storev, 'C');
     if (!device_ok(nullptr)) return;
     std::lock_guard<std::mutex> lock(g_abi_mutex);
     Ctx c; c.scan({V, T, C});
     lb::i64 lv, lt, lc;
     const bool left = same(side, 'L');
-    const double* dV = c.mat(V, left ? *m : *n, *k, *ldv, true, false, &lv);
+    const int nv = left ? *m : *n;
+    const double* dV = rowwise ? c.mat(V, *k, nv, *ldv, true, false, &lv) : c.mat(V, nv, *k, *ldv, true, false, &lv);
     const double* dT = c.mat(T, *k, *k, *ldt, true, false, &lt);
     double* dC = c.mat(C, *m, *n, *ldc, true, true, &lc);
-    lb::larfb(c.s, left ? 'L' : 'R', same(trans, 'N') ? 'N' : 'T', *m, *n, *k, dV, lv, dT, lt, dC, lc);
+    lb::larfb_general(c.s, left ? 'L' : 'R', same(trans, 'N') ? 'N' : 'T', backward, rowwise, *m, *n, *k, dV, lv, dT, lt, dC, lc);
     c.finish();
 }
 
@@ -960,6 +954,28 @@ void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* ld
     double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
     double* dT = c.mat(T, *nb, k, *ldt, true, true, &lt);          // in + out: the strictly lower parts of the T blocks stay
     lb::geqrt(c.s, *m, *n, *nb, dA, la, dT, lt);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+// SRC/dgeqrt3.f:129 DGEQRT3(M,N,A,LDA,T,LDT,INFO): recursive QR with the full N x N compact-WY factor T (M >= N).  The panel
+// recursion of csrc/geqrf.cu IS this algorithm (dgeqrt3.f:157-250: split N1 = N/2, factor left, apply to the right, factor
+// the right, T12 = -T1 (V1^T V2) T2), so the routine is DGEQRT with one block of width N.
+void dgeqrt3_(const int* m, const int* n, double* A, const int* lda, double* T, const int* ldt, int* info) {
+    *info = 0;
+    if (*n < 0) *info = -2;
+    else if (*m < *n) *info = -1;
+    else if (*lda < imax(1, *m)) *info = -4;
+    else if (*ldt < imax(1, *n)) *info = -6;
+    if (*info != 0) { call_xerbla("DGEQRT3", -*info); return; }
+    if (*n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, T});
+    lb::i64 la, lt;
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    double* dT = c.mat(T, *n, *n, *ldt, true, true, &lt);           // the part below the diagonal is not used and stays
+    lb::geqrt(c.s, *m, *n, *n, dA, la, dT, lt);
     int r = c.finish();
     if (r) *info = r;
 }

@@ -773,19 +773,39 @@ void geqr2(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// clean copy of reflectors stored below the diagonal of V (n x k): zeros above, ones on the diagonal
-__global__ void clean_v_kernel(int n, int k, const double* __restrict__ V, i64 ldv, double* __restrict__ Vc, i64 ldvc) {
+// clean dense copy Vc (n x k, one reflector per column, explicit unit entry and explicit zeros) of the reflectors stored in V
+// for every DIRECT / STOREV combination of dlarft.f:100-150 / dlarfb.f:150-190:
+//   forward : v_j has its unit entry in row j and zeros above;      backward: unit entry in row n-k+j, zeros below
+//   columnwise: v_j = V(:, j) (V is n x k);                          rowwise : v_j = V(j, :) (V is k x n)
+__global__ void clean_v_kernel(int n, int k, const double* __restrict__ V, i64 ldv, double* __restrict__ Vc, i64 ldvc, bool backward,
+                               bool rowwise) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     for (int j = blockIdx.y; j < k; j += gridDim.y) {
-        double v = (i > j) ? V[i + (i64)j * ldv] : (i == j ? 1.0 : 0.0);
+        const int u = backward ? n - k + j : j;                 // row of the unit entry
+        double v;
+        if (i == u) v = 1.0;
+        else if (backward ? i > u : i < u) v = 0.0;
+        else v = rowwise ? V[j + (i64)i * ldv] : V[i + (i64)j * ldv];
         Vc[i + (i64)j * ldvc] = v;
     }
 }
-static void clean_v(cudaStream_t s, int n, int k, const double* V, i64 ldv, double* Vc, i64 ldvc) {
+static void clean_v(cudaStream_t s, int n, int k, const double* V, i64 ldv, double* Vc, i64 ldvc, bool backward = false,
+                    bool rowwise = false) {
     dim3 grid(ceil_div(n, 256), (unsigned)min(k, 4096));
-    clean_v_kernel<<<grid, 256, 0, s>>>(n, k, V, ldv, Vc, ldvc);
+    clean_v_kernel<<<grid, 256, 0, s>>>(n, k, V, ldv, Vc, ldvc, backward, rowwise);
     count_launch();
+}
+// index reversal of a k x k matrix / a k-vector (backward DLARFT is forward DLARFT on the reflectors in reverse order)
+__global__ void flip_square_kernel(int k, const double* __restrict__ A, i64 lda, double* __restrict__ B, i64 ldb, int tri) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= k) return;
+    if (tri == 2 && i < j) return;                              // write the lower triangle only
+    B[i + (i64)j * ldb] = A[(k - 1 - i) + (i64)(k - 1 - j) * lda];
+}
+__global__ void flip_vec_kernel(int k, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) y[i] = x[k - 1 - i];
 }
 
 // T block (len <= 32) from G = V^T V and tau: dlarft_lvl2.f:199-258
@@ -832,23 +852,44 @@ static void larft_rec(cudaStream_t s, int k, const double* G, i64 ldg, const dou
     gemm(s, 'N', 'N', k1, k2, k2, 1.0, Tm, ldw, E2, ldw, 0.0, T + (i64)k1 * ldt, ldt);
 }
 
-// DLARFT('Forward','Columnwise', n, k, V, ldv, tau, T, ldt): only the upper triangle of T is written
-void larft(cudaStream_t s, int n, int k, const double* V, i64 ldv, const double* tau, double* T, i64 ldt) {
+// DLARFT(DIRECT, STOREV, n, k, V, ldv, tau, T, ldt) (SRC/dlarft.f:160; H = H(1)...H(k) forward, H(k)...H(1) backward; H = I - V T V^T
+// columnwise, I - V^T T V rowwise): only the upper (forward) / lower (backward) triangle of T is written.
+void larft_general(cudaStream_t s, bool backward, bool rowwise, int n, int k, const double* V, i64 ldv, const double* tau, double* T,
+                   i64 ldt) {
     if (n <= 0 || k <= 0) return;
     const i64 ldvc = (n + 1) & ~1, ldg = (k + 1) & ~1, ldw = (k + 1) & ~1;
     double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * k);
     double* G = (double*)ws_alloc(s, sizeof(double) * ldg * k);
     double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * (k + 2));
     double* W2 = (double*)ws_alloc(s, sizeof(double) * ldw * (k + 2));
-    clean_v(s, n, k, V, ldv, Vc, ldvc);
+    clean_v(s, n, k, V, ldv, Vc, ldvc, backward, rowwise);
     gemm(s, 'T', 'N', k, k, n, 1.0, Vc, ldvc, Vc, ldvc, 0.0, G, ldg);
-    larft_rec(s, k, G, ldg, tau, T, ldt, W1, W2, ldw);
+    if (!backward) larft_rec(s, k, G, ldg, tau, T, ldt, W1, W2, ldw);
+    else {
+        // reflectors in reverse order: G' = J G J, tau' = J tau, T' upper from the forward recurrence, T = J T' J (lower)
+        double* Gf = (double*)ws_alloc(s, sizeof(double) * ldg * k);
+        double* Tf = (double*)ws_alloc(s, sizeof(double) * ldg * k);
+        double* tf = (double*)ws_alloc(s, sizeof(double) * (size_t)k);
+        dim3 grid(ceil_div(k, 128), (unsigned)k);
+        flip_square_kernel<<<grid, 128, 0, s>>>(k, G, ldg, Gf, ldg, 0);
+        flip_vec_kernel<<<ceil_div(k, 128), 128, 0, s>>>(k, tau, tf);
+        LB_CUDA_CHECK(cudaMemsetAsync(Tf, 0, sizeof(double) * ldg * k, s));
+        larft_rec(s, k, Gf, ldg, tf, Tf, ldg, W1, W2, ldw);
+        flip_square_kernel<<<grid, 128, 0, s>>>(k, Tf, ldg, T, ldt, 2);
+        count_launch(3);
+        ws_free(s, Gf); ws_free(s, Tf); ws_free(s, tf);
+    }
     ws_free(s, Vc); ws_free(s, G); ws_free(s, W1); ws_free(s, W2);
 }
+void larft(cudaStream_t s, int n, int k, const double* V, i64 ldv, const double* tau, double* T, i64 ldt) {
+    larft_general(s, false, false, n, k, V, ldv, tau, T, ldt);
+}
 
-// DLARFB(SIDE, TRANS, 'Forward', 'Columnwise', m, n, k, V, T, C): C := H C, H^T C, C H or C H^T, H = I - V T V^T
-void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const double* V, i64 ldv, const double* T, i64 ldt,
-           double* C, i64 ldc) {
+// DLARFB(SIDE, TRANS, DIRECT, STOREV, m, n, k, V, T, C) (SRC/dlarfb.f:192): C := H C, H^T C, C H or C H^T with the block
+// reflector H = I - Vc T Vc^T, Vc the dense n x k reflector matrix of any storage scheme, T upper (forward) or lower
+// (backward) triangular.  Two GEMMs with the long dimension and a k x k one in between (dlarfb.f:248-304 and the other 7 cases).
+void larfb_general(cudaStream_t s, char side, char trans, bool backward, bool rowwise, int m, int n, int k, const double* V, i64 ldv,
+                   const double* T, i64 ldt, double* C, i64 ldc) {
     if (m <= 0 || n <= 0 || k <= 0) return;
     const bool left = (side == 'L' || side == 'l');
     const bool tr = !(trans == 'N' || trans == 'n');
@@ -856,8 +897,8 @@ void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const dou
     const i64 ldvc = (nv + 1) & ~1, lde = (k + 1) & ~1;
     double* Vc = (double*)ws_alloc(s, sizeof(double) * ldvc * k);
     double* E = (double*)ws_alloc(s, sizeof(double) * lde * k);
-    clean_v(s, nv, k, V, ldv, Vc, ldvc);
-    expand_tri(s, k, T, ldt, true, false, E, lde);
+    clean_v(s, nv, k, V, ldv, Vc, ldvc, backward, rowwise);
+    expand_tri(s, k, T, ldt, !backward, false, E, lde);
     if (left) {
         const i64 ldw = (k + 1) & ~1;
         double* W1 = (double*)ws_alloc(s, sizeof(double) * ldw * n);
@@ -876,6 +917,10 @@ void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const dou
         ws_free(s, W1); ws_free(s, W2);
     }
     ws_free(s, Vc); ws_free(s, E);
+}
+void larfb(cudaStream_t s, char side, char trans, int m, int n, int k, const double* V, i64 ldv, const double* T, i64 ldt,
+           double* C, i64 ldc) {
+    larfb_general(s, side, trans, false, false, m, n, k, V, ldv, T, ldt, C, ldc);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -223,6 +223,12 @@ def dgeqrt(m, n, nb, a, lda, t, ldt, work):
     return info.value
 
 
+def dgeqrt3(m, n, a, lda, t, ldt):
+    info = _i(0)
+    lib().dgeqrt3_(_r(m), _r(n), _p(a), _r(lda), _p(t), _r(ldt), C.byref(info))
+    return info.value
+
+
 def dgemqrt(side, trans, m, n, k, nb, v, ldv, t, ldt, c, ldc, work):
     info = _i(0)
     lib().dgemqrt_(_c(side), _c(trans), _r(m), _r(n), _r(k), _r(nb), _p(v), _r(ldv), _p(t), _r(ldt), _p(c), _r(ldc), _p(work),
