@@ -83,6 +83,23 @@ void dlarfb_(const char* side, const char* trans, const char* direct, const char
              const int* k, const double* V, const int* ldv, const double* T, const int* ldt, double* C, const int* ldc,
              double* work, const int* ldwork, size_t, size_t, size_t, size_t);
 
+/* ---- condition estimation and the expert driver ---- */
+/* SRC/dlatrs.f:238 DLATRS(UPLO,TRANS,DIAG,NORMIN,N,A,LDA,X,SCALE,CNORM,INFO) (lapack.h dlatrs_) */
+void dlatrs_(const char* uplo, const char* trans, const char* diag, const char* normin, const int* n, const double* A, const int* lda,
+             double* x, double* scale, double* cnorm, int* info, size_t, size_t, size_t, size_t);
+/* SRC/dgecon.f:128 DGECON(NORM,N,A,LDA,ANORM,RCOND,WORK,IWORK,INFO) (lapack.h dgecon_) */
+void dgecon_(const char* norm, const int* n, const double* A, const int* lda, const double* anorm, double* rcond, double* work,
+             int* iwork, int* info, size_t);
+/* SRC/dgeequ.f:139 DGEEQU(M,N,A,LDA,R,C,ROWCND,COLCND,AMAX,INFO); SRC/dlaqge.f:140 DLAQGE(M,N,A,LDA,R,C,ROWCND,COLCND,AMAX,EQUED) */
+void dgeequ_(const int* m, const int* n, const double* A, const int* lda, double* r, double* c, double* rowcnd, double* colcnd,
+             double* amax, int* info);
+void dlaqge_(const int* m, const int* n, double* A, const int* lda, const double* r, const double* c, const double* rowcnd,
+             const double* colcnd, const double* amax, char* equed, size_t);
+/* SRC/dgesvx.f:344 DGESVX(FACT,TRANS,N,NRHS,A,LDA,AF,LDAF,IPIV,EQUED,R,C,B,LDB,X,LDX,RCOND,FERR,BERR,WORK,IWORK,INFO) (lapack.h dgesvx_) */
+void dgesvx_(const char* fact, const char* trans, const int* n, const int* nrhs, double* A, const int* lda, double* AF, const int* ldaf,
+             int* ipiv, char* equed, double* R, double* C, double* B, const int* ldb, double* X, const int* ldx, double* rcond,
+             double* ferr, double* berr, double* work, int* iwork, int* info, size_t, size_t, size_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,12 +16,23 @@
 // routines report INFO = -1001 - cudaError and return.
 #include "lb_internal.h"
 #include "../../include/lapack_b200_f77.h"
+#include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <vector>
 
 namespace lb {
 void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx);
+// gecon.cu
+double latrs(cudaStream_t s, bool upper, bool notran, bool nounit, bool normin_y, int n, const double* A, i64 lda, double* x,
+             double* cnorm, std::vector<double>& hdiag);
+int gecon(cudaStream_t s, bool onenrm, int n, const double* A, i64 lda, double anorm, double* rcond);
+double lange(cudaStream_t s, char norm, int m, int n, const double* A, i64 lda);
+double lantr_max_upper(cudaStream_t s, int m, int n, const double* A, i64 lda);
+int geequ(cudaStream_t s, int m, int n, const double* A, i64 lda, double* r, double* c, double* rowcnd, double* colcnd, double* amax);
+char laqge(cudaStream_t s, int m, int n, double* A, i64 lda, const double* r, const double* c, double rowcnd, double colcnd, double amax);
+void scale_rows(cudaStream_t s, int m, int n, double* B, i64 ldb, const double* d);
 }
 
 // ------------------------------------------------------------------------------------------------ XERBLA
@@ -1194,58 +1205,37 @@ void dgels_(const char* trans, const int* m, const int* n, const int* nrhs, doub
 
 // DGERFS (SRC/dgerfs.f:235-440): iterative refinement with BERR / FERR.  The O(n^2) pieces -- residual, |A||x|, the solves
 // with the factors -- run on the device; the scalar logic and DLACN2's state machine run on the host on length-n vectors.
-void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, const int* lda, const double* AF, const int* ldaf,
-             const int* ipiv, const double* B, const int* ldb, double* X, const int* ldx, double* ferr, double* berr, double* work,
-             int* iwork, int* info, size_t) {
-    (void)work; (void)iwork;
-    *info = 0;
-    const bool notran = same(trans, 'N');
-    if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -1;
-    else if (*n < 0) *info = -2;
-    else if (*nrhs < 0) *info = -3;
-    else if (*lda < imax(1, *n)) *info = -5;
-    else if (*ldaf < imax(1, *n)) *info = -7;
-    else if (*ldb < imax(1, *n)) *info = -10;
-    else if (*ldx < imax(1, *n)) *info = -12;
-    if (*info != 0) { call_xerbla("DGERFS", -*info); return; }
-    if (*n == 0 || *nrhs == 0) { for (int j = 0; j < *nrhs; ++j) { ferr[j] = 0.0; berr[j] = 0.0; } return; }
-    if (!device_ok(info)) return;
-    std::lock_guard<std::mutex> lock(g_abi_mutex);
-    const int N = *n;
-    Ctx c; c.scan({A, AF, ipiv, B, X});
-    lb::i64 la, laf, lbb, lx;
-    const double* dA = c.mat(const_cast<double*>(A), N, N, *lda, true, false, &la);
-    const double* dAF = c.mat(const_cast<double*>(AF), N, N, *ldaf, true, false, &laf);
-    const int* dp = c.vec<int>(ipiv, (size_t)N, true, false);
-    const double* dB = c.mat(const_cast<double*>(B), N, *nrhs, *ldb, true, false, &lbb);
-    double* dX = c.mat(X, N, *nrhs, *ldx, true, true, &lx);
-    double* dr = (double*)lb::ws_alloc(c.s, sizeof(double) * (size_t)N);
-    double* dw = (double*)lb::ws_alloc(c.s, sizeof(double) * (size_t)N);
+// DGERFS on device operands (dgerfs.f:270-420): residual, |A||x| and the solves on the device, BERR / FERR logic and DLACN2 on
+// the host.  ferr / berr are host arrays.
+static void gerfs_device(cudaStream_t st, bool notran, int N, int nrhs, const double* dA, lb::i64 la, const double* dAF, lb::i64 laf,
+                         const int* dp, const double* dB, lb::i64 lbb, double* dX, lb::i64 lx, double* ferr, double* berr) {
+    double* dr = (double*)lb::ws_alloc(st, sizeof(double) * (size_t)N);
+    double* dw = (double*)lb::ws_alloc(st, sizeof(double) * (size_t)N);
     std::vector<double> r((size_t)N), w((size_t)N), v((size_t)N), xh((size_t)N);
     std::vector<int> isgn((size_t)N);
     const char tr = notran ? 'N' : 'T', trt = notran ? 'T' : 'N';
     const int itmax = 5, nz = N + 1;
     const double eps = 1.1102230246251565e-16, safmin = 2.2250738585072014e-308;
     const double safe1 = nz * safmin, safe2 = safe1 / eps;
-    auto solve = [&](char t) { lb::getrs(c.s, t, N, 1, dAF, laf, dp, dr, N); };
+    auto solve = [&](char t) { lb::getrs(st, t, N, 1, dAF, laf, dp, dr, N); };
     auto to_host = [&](const double* d, std::vector<double>& h) {
-        LB_CUDA_CHECK(cudaMemcpyAsync(h.data(), d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, c.s));
-        LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+        LB_CUDA_CHECK(cudaMemcpyAsync(h.data(), d, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, st));
+        LB_CUDA_CHECK(cudaStreamSynchronize(st));
     };
     auto to_dev = [&](const std::vector<double>& h, double* d) {
-        LB_CUDA_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c.s));
-        LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+        LB_CUDA_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+        LB_CUDA_CHECK(cudaStreamSynchronize(st));
     };
-    for (int j = 0; j < *nrhs; ++j) {
+    for (int j = 0; j < nrhs; ++j) {
         const double* dbj = dB + (lb::i64)j * lbb;
         double* dxj = dX + (lb::i64)j * lx;
         int count = 1;
         double lstres = 3.0;
         for (;;) {
-            LB_CUDA_CHECK(cudaMemcpyAsync(dr, dbj, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, c.s));
-            lb::gemm(c.s, tr, 'N', N, 1, N, -1.0, dA, la, dxj, N, 1.0, dr, N);                       // dgerfs.f:285-288
-            if (notran) abs_gemv_n_kernel<<<(N + 127) / 128, 128, 0, c.s>>>(N, dA, la, dxj, dbj, dw);
-            else abs_gemv_t_kernel<<<(N + 7) / 8, 256, 0, c.s>>>(N, dA, la, dxj, dbj, dw);
+            LB_CUDA_CHECK(cudaMemcpyAsync(dr, dbj, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, st));
+            lb::gemm(st, tr, 'N', N, 1, N, -1.0, dA, la, dxj, N, 1.0, dr, N);                       // dgerfs.f:285-288
+            if (notran) abs_gemv_n_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, dA, la, dxj, dbj, dw);
+            else abs_gemv_t_kernel<<<(N + 7) / 8, 256, 0, st>>>(N, dA, la, dxj, dbj, dw);
             to_host(dr, r);
             to_host(dw, w);
             double sm = 0.0;
@@ -1256,7 +1246,7 @@ void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, 
             berr[j] = sm;
             if (berr[j] > eps && 2.0 * berr[j] <= lstres && count <= itmax) {                            // dgerfs.f:340-352
                 solve(tr);
-                vec_add_kernel<<<(N + 255) / 256, 256, 0, c.s>>>(N, dr, dxj);
+                vec_add_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, dr, dxj);
                 lstres = berr[j];
                 ++count;
                 continue;
@@ -1288,10 +1278,235 @@ void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, 
         for (int i = 0; i < N; ++i) lstres = fmax(lstres, fabs(xh[(size_t)i]));
         if (lstres != 0.0) ferr[j] = ferr[j] / lstres;
     }
-    lb::ws_free(c.s, dr);
-    lb::ws_free(c.s, dw);
+    lb::ws_free(st, dr);
+    lb::ws_free(st, dw);
+}
+
+void dgerfs_(const char* trans, const int* n, const int* nrhs, const double* A, const int* lda, const double* AF, const int* ldaf,
+             const int* ipiv, const double* B, const int* ldb, double* X, const int* ldx, double* ferr, double* berr, double* work,
+             int* iwork, int* info, size_t) {
+    (void)work; (void)iwork;
+    *info = 0;
+    const bool notran = same(trans, 'N');
+    if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*nrhs < 0) *info = -3;
+    else if (*lda < imax(1, *n)) *info = -5;
+    else if (*ldaf < imax(1, *n)) *info = -7;
+    else if (*ldb < imax(1, *n)) *info = -10;
+    else if (*ldx < imax(1, *n)) *info = -12;
+    if (*info != 0) { call_xerbla("DGERFS", -*info); return; }
+    if (*n == 0 || *nrhs == 0) { for (int j = 0; j < *nrhs; ++j) { ferr[j] = 0.0; berr[j] = 0.0; } return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    const int N = *n;
+    Ctx c; c.scan({A, AF, ipiv, B, X});
+    lb::i64 la, laf, lbb, lx;
+    const double* dA = c.mat(const_cast<double*>(A), N, N, *lda, true, false, &la);
+    const double* dAF = c.mat(const_cast<double*>(AF), N, N, *ldaf, true, false, &laf);
+    const int* dp = c.vec<int>(ipiv, (size_t)N, true, false);
+    const double* dB = c.mat(const_cast<double*>(B), N, *nrhs, *ldb, true, false, &lbb);
+    double* dX = c.mat(X, N, *nrhs, *ldx, true, true, &lx);
+    gerfs_device(c.s, notran, N, *nrhs, dA, la, dAF, laf, dp, dB, lbb, dX, lx, ferr, berr);
     int rr = c.finish();
     if (rr) *info = rr;
+}
+
+// ================================================================================================ condition number / expert driver
+// SRC/dlatrs.f:238 DLATRS(UPLO,TRANS,DIAG,NORMIN,N,A,LDA,X,SCALE,CNORM,INFO)
+void dlatrs_(const char* uplo, const char* trans, const char* diag, const char* normin, const int* n, const double* A, const int* lda,
+             double* x, double* scale, double* cnorm, int* info, size_t, size_t, size_t, size_t) {
+    *info = 0;
+    const bool upper = same(uplo, 'U'), notran = same(trans, 'N'), nounit = same(diag, 'N');
+    if (!upper && !same(uplo, 'L')) *info = -1;
+    else if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -2;
+    else if (!nounit && !same(diag, 'U')) *info = -3;
+    else if (!same(normin, 'Y') && !same(normin, 'N')) *info = -4;
+    else if (*n < 0) *info = -5;
+    else if (*lda < imax(1, *n)) *info = -7;
+    if (*info != 0) { call_xerbla("DLATRS", -*info); return; }
+    *scale = 1.0;
+    if (*n == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, x, cnorm});
+    lb::i64 la;
+    const double* dA = c.mat(A, *n, *n, *lda, true, false, &la);
+    double* dx = c.vec<double>(x, (size_t)*n, true, true);
+    double* dc = c.vec<double>(cnorm, (size_t)*n, same(normin, 'Y'), true);
+    std::vector<double> hdiag;
+    *scale = lb::latrs(c.s, upper, notran, nounit, same(normin, 'Y'), *n, dA, la, dx, dc, hdiag);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
+// SRC/dgecon.f:128 DGECON(NORM,N,A,LDA,ANORM,RCOND,WORK,IWORK,INFO); WORK / IWORK are not used (device scratch)
+void dgecon_(const char* norm, const int* n, const double* A, const int* lda, const double* anorm, double* rcond, double* work,
+             int* iwork, int* info, size_t) {
+    (void)work; (void)iwork;
+    *info = 0;
+    const bool onenrm = same(norm, '1') || same(norm, 'O');
+    if (!onenrm && !same(norm, 'I')) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *n)) *info = -4;
+    else if (*anorm < 0.0) *info = -5;
+    if (*info != 0) { call_xerbla("DGECON", -*info); return; }
+    *rcond = 0.0;                                                       // dgecon.f:195-209
+    if (*n == 0) { *rcond = 1.0; return; }
+    else if (*anorm == 0.0) return;
+    else if (*anorm != *anorm) { *rcond = *anorm; *info = -5; return; }
+    else if (*anorm > DBL_MAX) { *info = -5; return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A});
+    lb::i64 la;
+    const double* dA = c.mat(A, *n, *n, *lda, true, false, &la);
+    const int ci = lb::gecon(c.s, onenrm, *n, dA, la, *anorm, rcond);
+    int r = c.finish();
+    *info = r ? r : ci;
+}
+
+// SRC/dgeequ.f:139 DGEEQU(M,N,A,LDA,R,C,ROWCND,COLCND,AMAX,INFO); R, C are host vectors
+void dgeequ_(const int* m, const int* n, const double* A, const int* lda, double* r, double* c, double* rowcnd, double* colcnd,
+             double* amax, int* info) {
+    *info = 0;
+    if (*m < 0) *info = -1;
+    else if (*n < 0) *info = -2;
+    else if (*lda < imax(1, *m)) *info = -4;
+    if (*info != 0) { call_xerbla("DGEEQU", -*info); return; }
+    if (*m == 0 || *n == 0) { *rowcnd = 1.0; *colcnd = 1.0; *amax = 0.0; return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx cx; cx.scan({A});
+    lb::i64 la;
+    const double* dA = cx.mat(A, *m, *n, *lda, true, false, &la);
+    const int gi = lb::geequ(cx.s, *m, *n, dA, la, r, c, rowcnd, colcnd, amax);
+    int rr = cx.finish();
+    *info = rr ? rr : gi;
+}
+
+// SRC/dlaqge.f:140 DLAQGE(M,N,A,LDA,R,C,ROWCND,COLCND,AMAX,EQUED); no INFO
+void dlaqge_(const int* m, const int* n, double* A, const int* lda, const double* r, const double* c, const double* rowcnd,
+             const double* colcnd, const double* amax, char* equed, size_t) {
+    if (*m <= 0 || *n <= 0) { *equed = 'N'; return; }
+    if (!device_ok(nullptr)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx cx; cx.scan({A});
+    lb::i64 la;
+    double* dA = cx.mat(A, *m, *n, *lda, true, true, &la);
+    *equed = lb::laqge(cx.s, *m, *n, dA, la, r, c, *rowcnd, *colcnd, *amax);
+    if (*equed == 'N') { for (auto& it : cx.items) it.out = false; }      // nothing was scaled: leave A alone
+    cx.finish();
+}
+
+// SRC/dgesvx.f:344 DGESVX: equilibrate (FACT='E'), factor, estimate the condition number, solve, refine, bound the errors.
+// R, C, FERR, BERR are host vectors; WORK(1) returns the reciprocal pivot growth when WORK is host memory; IWORK is not used.
+void dgesvx_(const char* fact, const char* trans, const int* n, const int* nrhs, double* A, const int* lda, double* AF, const int* ldaf,
+             int* ipiv, char* equed, double* R, double* Cs, double* B, const int* ldb, double* X, const int* ldx, double* rcond,
+             double* ferr, double* berr, double* work, int* iwork, int* info, size_t, size_t, size_t) {
+    (void)iwork;
+    *info = 0;
+    const bool nofact = same(fact, 'N'), equil = same(fact, 'E'), notran = same(trans, 'N');
+    const int N = *n;
+    bool rowequ, colequ;
+    const double smlnum = DBL_MIN, bignum = 1.0 / smlnum;
+    double rowcnd = 1.0, colcnd = 1.0, amax = 0.0;
+    if (nofact || equil) { *equed = 'N'; rowequ = false; colequ = false; }
+    else { rowequ = same(equed, 'R') || same(equed, 'B'); colequ = same(equed, 'C') || same(equed, 'B'); }
+    if (!nofact && !equil && !same(fact, 'F')) *info = -1;                 // dgesvx.f:390-447
+    else if (!notran && !same(trans, 'T') && !same(trans, 'C')) *info = -2;
+    else if (N < 0) *info = -3;
+    else if (*nrhs < 0) *info = -4;
+    else if (*lda < imax(1, N)) *info = -6;
+    else if (*ldaf < imax(1, N)) *info = -8;
+    else if (same(fact, 'F') && !(rowequ || colequ || same(equed, 'N'))) *info = -10;
+    else {
+        if (rowequ) {
+            double rcmin = bignum, rcmax = 0.0;
+            for (int j = 0; j < N; ++j) { rcmin = fmin(rcmin, R[j]); rcmax = fmax(rcmax, R[j]); }
+            if (rcmin <= 0.0) *info = -11;
+            else if (N > 0) rowcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+        }
+        if (colequ && *info == 0) {
+            double rcmin = bignum, rcmax = 0.0;
+            for (int j = 0; j < N; ++j) { rcmin = fmin(rcmin, Cs[j]); rcmax = fmax(rcmax, Cs[j]); }
+            if (rcmin <= 0.0) *info = -12;
+            else if (N > 0) colcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+        }
+        if (*info == 0) {
+            if (*ldb < imax(1, N)) *info = -14;
+            else if (*ldx < imax(1, N)) *info = -16;
+        }
+    }
+    if (*info != 0) { call_xerbla("DGESVX", -*info); return; }
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    Ctx c; c.scan({A, AF, ipiv, B, X});
+    lb::i64 la, laf, lbb, lx;
+    double* dA = c.mat(A, N, N, *lda, true, equil, &la);
+    double* dAF = c.mat(AF, N, N, *ldaf, !(nofact || equil), nofact || equil, &laf);
+    int* dp = c.vec<int>(ipiv, (size_t)N, !(nofact || equil), nofact || equil);
+    double* dB = c.mat(B, N, *nrhs, *ldb, true, true, &lbb);
+    double* dX = c.mat(X, N, *nrhs, *ldx, false, true, &lx);
+    auto set_out = [&](void* dev, bool out) { for (auto& it : c.items) if (it.dev == dev) it.out = out; };
+    if (equil && N > 0) {                                                   // dgesvx.f:453-467
+        const int infequ = lb::geequ(c.s, N, N, dA, la, R, Cs, &rowcnd, &colcnd, &amax);
+        if (infequ == 0) {
+            *equed = lb::laqge(c.s, N, N, dA, la, R, Cs, rowcnd, colcnd, amax);
+            rowequ = (*equed == 'R' || *equed == 'B');
+            colequ = (*equed == 'C' || *equed == 'B');
+        }
+    }
+    if (!rowequ && !colequ) set_out(dA, false);                             // A was not scaled
+    bool b_changed = false;
+    if (notran) { if (rowequ) { lb::scale_rows(c.s, N, *nrhs, dB, lbb, R); b_changed = true; } }        // dgesvx.f:471-487
+    else if (colequ) { lb::scale_rows(c.s, N, *nrhs, dB, lbb, Cs); b_changed = true; }
+    if (!b_changed) set_out(dB, false);
+    double rpvgrw;
+    if (nofact || equil) {                                                  // dgesvx.f:489-513
+        if (N > 0) lb::lacpy(c.s, 'A', N, N, dA, la, dAF, laf);
+        int* dinfo = c.dev_info();
+        if (N > 0) lb::getrf(c.s, N, N, dAF, laf, dp, dinfo);
+        int hinfo = 0;
+        LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c.s));
+        LB_CUDA_CHECK(cudaStreamSynchronize(c.s));
+        lb::ws_free(c.s, dinfo);
+        if (hinfo > 0) {
+            rpvgrw = lb::lantr_max_upper(c.s, hinfo, hinfo, dAF, laf);
+            if (rpvgrw == 0.0) rpvgrw = 1.0;
+            else rpvgrw = lb::lange(c.s, 'M', N, hinfo, dA, la) / rpvgrw;
+            if (ptr_kind(work) != PK_DEVICE) work[0] = rpvgrw;
+            *rcond = 0.0;
+            set_out(dX, false);
+            int r = c.finish();
+            *info = r ? r : hinfo;
+            return;
+        }
+    }
+    const char norm = notran ? '1' : 'I';
+    const double anorm = lb::lange(c.s, norm, N, N, dA, la);
+    rpvgrw = lb::lantr_max_upper(c.s, N, N, dAF, laf);
+    if (rpvgrw == 0.0) rpvgrw = 1.0;
+    else rpvgrw = lb::lange(c.s, 'M', N, N, dA, la) / rpvgrw;
+    // DGECON (its own quick returns, dgecon.f:195-209)
+    *rcond = 0.0;
+    if (N == 0) *rcond = 1.0;
+    else if (anorm == 0.0) {}
+    else if (anorm != anorm) { *rcond = anorm; *info = -5; }
+    else if (anorm > DBL_MAX) *info = -5;
+    else *info = lb::gecon(c.s, notran, N, dAF, laf, anorm, rcond);
+    if (N > 0 && *nrhs > 0) {
+        lb::lacpy(c.s, 'A', N, *nrhs, dB, lbb, dX, lx);
+        lb::getrs(c.s, notran ? 'N' : 'T', N, *nrhs, dAF, laf, dp, dX, lx);
+        gerfs_device(c.s, notran, N, *nrhs, dA, la, dAF, laf, dp, dB, lbb, dX, lx, ferr, berr);
+    } else for (int j = 0; j < *nrhs; ++j) { ferr[j] = 0.0; berr[j] = 0.0; }
+    if (notran) {                                                           // dgesvx.f:556-581
+        if (colequ) { lb::scale_rows(c.s, N, *nrhs, dX, lx, Cs); for (int j = 0; j < *nrhs; ++j) ferr[j] /= colcnd; }
+    } else if (rowequ) { lb::scale_rows(c.s, N, *nrhs, dX, lx, R); for (int j = 0; j < *nrhs; ++j) ferr[j] /= rowcnd; }
+    if (ptr_kind(work) != PK_DEVICE) work[0] = rpvgrw;
+    int r = c.finish();
+    *info = r;
+    if (r == 0 && *rcond < 1.1102230246251565e-16) *info = N + 1;           // dgesvx.f:587-588
 }
 
 }  // extern "C"

@@ -341,3 +341,46 @@ def larfb(side, trans, v, t, c):
     ldw = n if side.upper() == "L" else m
     work = np.zeros((max(1, ldw), max(1, k)), order="F")
     dlarfb(side, trans, "F", "C", m, n, k, v, _ld(v), t, _ld(t), c, _ld(c), work, _ld(work))
+
+
+# ---- condition estimation / expert driver ------------------------------------
+def dlatrs(uplo, trans, diag, normin, a, x, cnorm):
+    """x (1-D) := solution of op(A) x = scale*b; cnorm in/out; returns (scale, info)"""
+    n = a.shape[0]
+    scale, info = _d(0.0), _i(0)
+    lib().dlatrs_(_c(uplo), _c(trans), _c(diag), _c(normin), _r(n), _p(a), _r(_ld(a)), _p(x), C.byref(scale), _p(cnorm), C.byref(info),
+                  C.c_size_t(1), C.c_size_t(1), C.c_size_t(1), C.c_size_t(1))
+    return scale.value, info.value
+
+
+def dgecon(norm, a, anorm, n=None, lda=None):
+    n = a.shape[0] if n is None else n
+    lda = _ld(a) if lda is None else lda
+    work, iwork = np.zeros(max(1, 4 * n)), np.zeros(max(1, n), dtype=np.int32)
+    rcond, info = _d(0.0), _i(0)
+    lib().dgecon_(_c(norm), _r(n), _p(a), _r(lda), C.byref(_d(anorm)), C.byref(rcond), _p(work), _p(iwork), C.byref(info), C.c_size_t(1))
+    return rcond.value, info.value
+
+
+def dgeequ(a):
+    m, n = a.shape
+    r, c = np.zeros(max(1, m)), np.zeros(max(1, n))
+    rowcnd, colcnd, amax, info = _d(0.0), _d(0.0), _d(0.0), _i(0)
+    lib().dgeequ_(_r(m), _r(n), _p(a), _r(_ld(a)), _p(r), _p(c), C.byref(rowcnd), C.byref(colcnd), C.byref(amax), C.byref(info))
+    return r[:m], c[:n], rowcnd.value, colcnd.value, amax.value, info.value
+
+
+def dgesvx(fact, trans, a, af, ipiv, equed, r, c, b, n=None, nrhs=None, lda=None, ldaf=None, ldb=None):
+    """SRC/dgesvx.f; a, af, ipiv, r, c, b in/out like the reference.  Returns dict(x, rcond, ferr, berr, rpvgrw, equed, info)."""
+    n = a.shape[0] if n is None else n
+    nrhs = b.shape[1] if nrhs is None else nrhs
+    x = np.zeros((max(1, n), max(1, nrhs)), order="F")
+    ferr, berr = np.zeros(max(1, nrhs)), np.zeros(max(1, nrhs))
+    work, iwork = np.zeros(max(1, 4 * n)), np.zeros(max(1, n), dtype=np.int32)
+    rcond, info = _d(0.0), _i(0)
+    eq = C.create_string_buffer(equed.encode(), 2)
+    lib().dgesvx_(_c(fact), _c(trans), _r(n), _r(nrhs), _p(a), _r(_ld(a) if lda is None else lda), _p(af), _r(_ld(af) if ldaf is None else ldaf),
+                  _p(ipiv), eq, _p(r), _p(c), _p(b), _r(_ld(b) if ldb is None else ldb), _p(x), _r(max(1, n)), C.byref(rcond), _p(ferr),
+                  _p(berr), _p(work), _p(iwork), C.byref(info), C.c_size_t(1), C.c_size_t(1), C.c_size_t(1))
+    return dict(x=x[:n, :nrhs], rcond=rcond.value, ferr=ferr[:nrhs], berr=berr[:nrhs], rpvgrw=work[0], equed=eq.value.decode()[:1],
+                info=info.value)

@@ -102,6 +102,18 @@ void ora_dorml2(char side, char trans, int m, int n, int k, const double *a, int
                 double *work, int *info);
 void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b, int ldb, double *work, int lwork, int *info);
 void ora_dlacn2(int n, double *v, double *x, int *isgn, double *est, int *kase, int *isave);
+/* ---- condition estimation / expert driver ---- */
+void ora_dtrsv(char uplo, char trans, char diag, int n, const double *a, int lda, double *x);
+void ora_drscl(int n, double sa, double *x);
+void ora_dlatrs(char uplo, char trans, char diag, char normin, int n, const double *a, int lda, double *x, double *scale,
+                double *cnorm, int *info);
+void ora_dgecon(char norm, int n, const double *a, int lda, double anorm, double *rcond, double *work, int *iwork, int *info);
+void ora_dgeequ(int m, int n, const double *a, int lda, double *r, double *c, double *rowcnd, double *colcnd, double *amax,
+                int *info);
+char ora_dlaqge(int m, int n, double *a, int lda, const double *r, const double *c, double rowcnd, double colcnd, double amax);
+void ora_dgesvx(char fact, char trans, int n, int nrhs, double *a, int lda, double *af, int ldaf, int *ipiv, char *equed,
+                double *r, double *c, double *b, int ldb, double *x, int ldx, double *rcond, double *ferr, double *berr,
+                double *work, int *iwork, int *info);
 void ora_dgerfs(char trans, int n, int nrhs, const double *a, int lda, const double *af, int ldaf, const int *ipiv,
                 const double *b, int ldb, double *x, int ldx, double *ferr, double *berr, double *work, int *iwork, int *info);
 void ora_dorm2r(char side, char trans, int m, int n, int k, const double *a, int lda, const double *tau, double *c, int ldc,

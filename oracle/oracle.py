@@ -278,6 +278,45 @@ def dgerfs(trans, a, af, ipiv, b, x):
     return ferr[:nrhs], berr[:nrhs], info.value
 
 
+def dlatrs(uplo, trans, diag, normin, a, x, cnorm):
+    """SRC/dlatrs.f: x (1-D) := solution of op(A) x = scale*b; returns (scale, info); cnorm is in/out"""
+    n = a.shape[0]
+    scale, info = C.c_double(0.0), C.c_int(0)
+    lib().ora_dlatrs(_c(uplo), _c(trans), _c(diag), _c(normin), n, _d(a), _ld(a), _d(x), C.byref(scale), _d(cnorm), C.byref(info))
+    return scale.value, info.value
+
+
+def dgecon(norm, a, anorm):
+    """SRC/dgecon.f on DGETRF factors; returns (rcond, info)"""
+    n = a.shape[0]
+    work, iwork = np.zeros(max(1, 4 * n)), np.zeros(max(1, n), dtype=np.int32)
+    rcond, info = C.c_double(0.0), C.c_int(0)
+    lib().ora_dgecon(_c(norm), n, _d(a), _ld(a), C.c_double(anorm), C.byref(rcond), _d(work), _i(iwork), C.byref(info))
+    return rcond.value, info.value
+
+
+def dgeequ(a):
+    m, n = a.shape
+    r, c = np.zeros(max(1, m)), np.zeros(max(1, n))
+    rowcnd, colcnd, amax, info = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0), C.c_int(0)
+    lib().ora_dgeequ(m, n, _d(a), _ld(a), _d(r), _d(c), C.byref(rowcnd), C.byref(colcnd), C.byref(amax), C.byref(info))
+    return r[:m], c[:n], rowcnd.value, colcnd.value, amax.value, info.value
+
+
+def dgesvx(fact, trans, a, af, ipiv, equed, r, c, b):
+    """SRC/dgesvx.f; a, af, ipiv, r, c, b are in/out as in the reference.  Returns dict(x, rcond, ferr, berr, rpvgrw, equed, info)"""
+    n, nrhs = a.shape[0], b.shape[1]
+    x = np.zeros((max(1, n), max(1, nrhs)), order="F")
+    ferr, berr = np.zeros(max(1, nrhs)), np.zeros(max(1, nrhs))
+    work, iwork = np.zeros(max(1, 4 * n)), np.zeros(max(1, n), dtype=np.int32)
+    rcond, info = C.c_double(0.0), C.c_int(0)
+    eq = C.c_char(equed.encode())
+    lib().ora_dgesvx(_c(fact), _c(trans), n, nrhs, _d(a), _ld(a), _d(af), _ld(af), _i(ipiv), C.byref(eq), _d(r), _d(c), _d(b), _ld(b),
+                     _d(x), max(1, n), C.byref(rcond), _d(ferr), _d(berr), _d(work), _i(iwork), C.byref(info))
+    return dict(x=x[:n, :nrhs], rcond=rcond.value, ferr=ferr[:nrhs], berr=berr[:nrhs], rpvgrw=work[0], equed=eq.value.decode(),
+                info=info.value)
+
+
 def dgels(trans, a, b):
     """least squares / minimum norm solve (SRC/dgels.f); a is overwritten by its QR / LQ factors, b (max(m,n) x nrhs) by the
     solution"""

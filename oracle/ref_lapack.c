@@ -1190,3 +1190,424 @@ void ora_dgerfs(char trans, int n, int nrhs, const double *a, int lda, const dou
         if (lstres != 0.0) ferr[j] = ferr[j] / lstres;
     }
 }
+
+/* ======================================================================================================================
+ * Condition estimation and the expert driver: DLATRS, DRSCL, DGECON, DGEEQU, DLAQGE, DGESVX.
+ * ====================================================================================================================== */
+
+/* BLAS/SRC/dtrsv.f:180-330 (INCX = 1) */
+void ora_dtrsv(char uplo, char trans, char diag, int n, const double *a, int lda, double *x)
+{
+    const int upper = ora_lsame(uplo, 'U'), notran = ora_lsame(trans, 'N'), nounit = ora_lsame(diag, 'N');
+    if (n == 0) return;
+    if (notran) {
+        if (upper) {
+            for (int j = n - 1; j >= 0; --j)
+                if (x[j] != 0.0) {
+                    if (nounit) x[j] = x[j] / A_(j, j);
+                    double temp = x[j];
+                    for (int i = j - 1; i >= 0; --i) x[i] = x[i] - temp * A_(i, j);
+                }
+        } else {
+            for (int j = 0; j < n; ++j)
+                if (x[j] != 0.0) {
+                    if (nounit) x[j] = x[j] / A_(j, j);
+                    double temp = x[j];
+                    for (int i = j + 1; i < n; ++i) x[i] = x[i] - temp * A_(i, j);
+                }
+        }
+    } else {
+        if (upper) {
+            for (int j = 0; j < n; ++j) {
+                double temp = x[j];
+                for (int i = 0; i < j; ++i) temp = temp - A_(i, j) * x[i];
+                if (nounit) temp = temp / A_(j, j);
+                x[j] = temp;
+            }
+        } else {
+            for (int j = n - 1; j >= 0; --j) {
+                double temp = x[j];
+                for (int i = n - 1; i > j; --i) temp = temp - A_(i, j) * x[i];
+                if (nounit) temp = temp / A_(j, j);
+                x[j] = temp;
+            }
+        }
+    }
+}
+
+/* SRC/drscl.f:120-170: x := x / sa without overflow / underflow of the reciprocal */
+void ora_drscl(int n, double sa, double *x)
+{
+    if (n <= 0) return;
+    const double smlnum = ora_dlamch('S'), bignum = 1.0 / smlnum;
+    double cden = sa, cnum = 1.0, mul;
+    int done;
+    do {
+        double cden1 = cden * smlnum, cnum1 = cnum / bignum;
+        if (fabs(cden1) > fabs(cnum) && cnum != 0.0) { mul = smlnum; done = 0; cden = cden1; }
+        else if (fabs(cnum1) > fabs(cden)) { mul = bignum; done = 0; cnum = cnum1; }
+        else { mul = cnum / cden; done = 1; }
+        ora_dscal(n, mul, x, 1);
+    } while (!done);
+}
+
+static double asum_(int n, const double *x) { double s = 0.0; for (int i = 0; i < n; ++i) s += fabs(x[i]); return s; }
+
+/* SRC/dlatrs.f:250-850 -- triangular solve with scaling to prevent overflow: A x = scale b or A^T x = scale b. */
+void ora_dlatrs(char uplo, char trans, char diag, char normin, int n, const double *a, int lda, double *x, double *scale,
+                double *cnorm, int *info)
+{
+    const int upper = ora_lsame(uplo, 'U'), notran = ora_lsame(trans, 'N'), nounit = ora_lsame(diag, 'N');
+    *info = 0;
+    if (!upper && !ora_lsame(uplo, 'L')) *info = -1;
+    else if (!notran && !ora_lsame(trans, 'T') && !ora_lsame(trans, 'C')) *info = -2;
+    else if (!nounit && !ora_lsame(diag, 'U')) *info = -3;
+    else if (!ora_lsame(normin, 'Y') && !ora_lsame(normin, 'N')) *info = -4;
+    else if (n < 0) *info = -5;
+    else if (lda < imax(1, n)) *info = -7;
+    if (*info != 0) return;
+    *scale = 1.0;
+    if (n == 0) return;
+    const double ovfl = ora_dlamch('O');
+    const double smlnum = ora_dlamch('S') / ora_dlamch('P'), bignum = 1.0 / smlnum;
+    if (ora_lsame(normin, 'N')) {                                            /* dlatrs.f:300-317 */
+        if (upper) for (int j = 0; j < n; ++j) cnorm[j] = asum_(j, &A_(0, j));
+        else { for (int j = 0; j < n - 1; ++j) cnorm[j] = asum_(n - j - 1, &A_(j + 1, j)); cnorm[n - 1] = 0.0; }
+    }
+    int imaxi = ora_idamax(n, cnorm, 1);
+    double tmax = cnorm[imaxi - 1], tscal;
+    if (tmax <= bignum) tscal = 1.0;
+    else if (tmax <= ovfl) { tscal = 1.0 / (smlnum * tmax); ora_dscal(n, tscal, cnorm, 1); }
+    else {                                                                   /* dlatrs.f:338-392 */
+        tmax = 0.0;
+        if (upper) { for (int j = 1; j < n; ++j) for (int i = 0; i < j; ++i) tmax = fmax(fabs(A_(i, j)), tmax); }
+        else { for (int j = 0; j < n - 1; ++j) for (int i = j + 1; i < n; ++i) tmax = fmax(fabs(A_(i, j)), tmax); }
+        if (tmax <= ovfl) {
+            tscal = 1.0 / (smlnum * tmax);
+            for (int j = 0; j < n; ++j) {
+                if (cnorm[j] <= ovfl) cnorm[j] = cnorm[j] * tscal;
+                else {
+                    cnorm[j] = 0.0;
+                    if (upper) for (int i = 0; i < j; ++i) cnorm[j] += tscal * fabs(A_(i, j));
+                    else for (int i = j + 1; i < n; ++i) cnorm[j] += tscal * fabs(A_(i, j));
+                }
+            }
+        } else { ora_dtrsv(uplo, trans, diag, n, a, lda, x); return; }
+    }
+    int j = ora_idamax(n, x, 1);
+    double xmax = fabs(x[j - 1]), xbnd = xmax, grow;
+    int jfirst, jlast, jinc;
+    if (notran) {
+        if (upper) { jfirst = n - 1; jlast = 0; jinc = -1; } else { jfirst = 0; jlast = n - 1; jinc = 1; }
+        if (tscal != 1.0) grow = 0.0;
+        else if (nounit) {
+            grow = 1.0 / fmax(xbnd, smlnum);
+            xbnd = grow;
+            int broke = 0;
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                if (grow <= smlnum) { broke = 1; break; }
+                double tjj = fabs(A_(j, j));
+                xbnd = fmin(xbnd, fmin(1.0, tjj) * grow);
+                if (tjj + cnorm[j] >= smlnum) grow = grow * (tjj / (tjj + cnorm[j]));
+                else grow = 0.0;
+            }
+            if (!broke) grow = xbnd;
+        } else {
+            grow = fmin(1.0, 1.0 / fmax(xbnd, smlnum));
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                if (grow <= smlnum) break;
+                grow = grow * (1.0 / (1.0 + cnorm[j]));
+            }
+        }
+    } else {
+        if (upper) { jfirst = 0; jlast = n - 1; jinc = 1; } else { jfirst = n - 1; jlast = 0; jinc = -1; }
+        if (tscal != 1.0) grow = 0.0;
+        else if (nounit) {
+            grow = 1.0 / fmax(xbnd, smlnum);
+            xbnd = grow;
+            int broke = 0;
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                if (grow <= smlnum) { broke = 1; break; }
+                double xj = 1.0 + cnorm[j];
+                grow = fmin(grow, xbnd / xj);
+                double tjj = fabs(A_(j, j));
+                if (xj > tjj) xbnd = xbnd * (tjj / xj);
+            }
+            if (!broke) grow = fmin(grow, xbnd);
+        } else {
+            grow = fmin(1.0, 1.0 / fmax(xbnd, smlnum));
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                if (grow <= smlnum) break;
+                double xj = 1.0 + cnorm[j];
+                grow = grow / xj;
+            }
+        }
+    }
+    if (grow * tscal > smlnum) {
+        ora_dtrsv(uplo, trans, diag, n, a, lda, x);                          /* dlatrs.f:562-567 */
+    } else {
+        double rec, tjjs = 0.0, tjj, xj;
+        if (xmax > bignum) { *scale = bignum / xmax; ora_dscal(n, *scale, x, 1); xmax = bignum; }
+        if (notran) {
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                xj = fabs(x[j]);
+                int skip = 0;
+                if (nounit) tjjs = A_(j, j) * tscal;
+                else { tjjs = tscal; if (tscal == 1.0) skip = 1; }
+                if (!skip) {
+                    tjj = fabs(tjjs);
+                    if (tjj > smlnum) {
+                        if (tjj < 1.0 && xj > tjj * bignum) { rec = 1.0 / xj; ora_dscal(n, rec, x, 1); *scale *= rec; xmax *= rec; }
+                        x[j] = x[j] / tjjs;
+                        xj = fabs(x[j]);
+                    } else if (tjj > 0.0) {
+                        if (xj > tjj * bignum) {
+                            rec = (tjj * bignum) / xj;
+                            if (cnorm[j] > 1.0) rec = rec / cnorm[j];
+                            ora_dscal(n, rec, x, 1); *scale *= rec; xmax *= rec;
+                        }
+                        x[j] = x[j] / tjjs;
+                        xj = fabs(x[j]);
+                    } else {
+                        for (int i = 0; i < n; ++i) x[i] = 0.0;
+                        x[j] = 1.0; xj = 1.0; *scale = 0.0; xmax = 0.0;
+                    }
+                }
+                if (xj > 1.0) {
+                    rec = 1.0 / xj;
+                    if (cnorm[j] > (bignum - xmax) * rec) { rec *= 0.5; ora_dscal(n, rec, x, 1); *scale *= rec; }
+                } else if (xj * cnorm[j] > bignum - xmax) { ora_dscal(n, 0.5, x, 1); *scale *= 0.5; }
+                if (upper) {
+                    if (j > 0) {
+                        ora_daxpy(j, -x[j] * tscal, &A_(0, j), 1, x, 1);
+                        int i = ora_idamax(j, x, 1);
+                        xmax = fabs(x[i - 1]);
+                    }
+                } else if (j < n - 1) {
+                    ora_daxpy(n - j - 1, -x[j] * tscal, &A_(j + 1, j), 1, x + j + 1, 1);
+                    int i = j + ora_idamax(n - j - 1, x + j + 1, 1);
+                    xmax = fabs(x[i]);
+                }
+            }
+        } else {
+            for (j = jfirst; jinc > 0 ? j <= jlast : j >= jlast; j += jinc) {
+                xj = fabs(x[j]);
+                double uscal = tscal, sumj;
+                rec = 1.0 / fmax(xmax, 1.0);
+                if (cnorm[j] > (bignum - xj) * rec) {
+                    rec *= 0.5;
+                    if (nounit) tjjs = A_(j, j) * tscal; else tjjs = tscal;
+                    tjj = fabs(tjjs);
+                    if (tjj > 1.0) { rec = fmin(1.0, rec * tjj); uscal = uscal / tjjs; }
+                    if (rec < 1.0) { ora_dscal(n, rec, x, 1); *scale *= rec; xmax *= rec; }
+                }
+                sumj = 0.0;
+                if (uscal == 1.0) {
+                    if (upper) sumj = ora_ddot(j, &A_(0, j), 1, x, 1);
+                    else if (j < n - 1) sumj = ora_ddot(n - j - 1, &A_(j + 1, j), 1, x + j + 1, 1);
+                } else {
+                    if (upper) for (int i = 0; i < j; ++i) sumj = sumj + (A_(i, j) * uscal) * x[i];
+                    else for (int i = j + 1; i < n; ++i) sumj = sumj + (A_(i, j) * uscal) * x[i];
+                }
+                if (uscal == tscal) {
+                    x[j] = x[j] - sumj;
+                    xj = fabs(x[j]);
+                    int skip = 0;
+                    if (nounit) tjjs = A_(j, j) * tscal;
+                    else { tjjs = tscal; if (tscal == 1.0) skip = 1; }
+                    if (!skip) {
+                        tjj = fabs(tjjs);
+                        if (tjj > smlnum) {
+                            if (tjj < 1.0 && xj > tjj * bignum) { rec = 1.0 / xj; ora_dscal(n, rec, x, 1); *scale *= rec; xmax *= rec; }
+                            x[j] = x[j] / tjjs;
+                        } else if (tjj > 0.0) {
+                            if (xj > tjj * bignum) { rec = (tjj * bignum) / xj; ora_dscal(n, rec, x, 1); *scale *= rec; xmax *= rec; }
+                            x[j] = x[j] / tjjs;
+                        } else {
+                            for (int i = 0; i < n; ++i) x[i] = 0.0;
+                            x[j] = 1.0; *scale = 0.0; xmax = 0.0;
+                        }
+                    }
+                } else x[j] = x[j] / tjjs - sumj;
+                xmax = fmax(xmax, fabs(x[j]));
+            }
+        }
+        *scale = *scale / tscal;
+    }
+    if (tscal != 1.0) ora_dscal(n, 1.0 / tscal, cnorm, 1);
+}
+
+/* SRC/dgecon.f:128-285.  work: 4n doubles, iwork: n ints. */
+void ora_dgecon(char norm, int n, const double *a, int lda, double anorm, double *rcond, double *work, int *iwork, int *info)
+{
+    const double hugeval = ora_dlamch('O');
+    *info = 0;
+    const int onenrm = ora_lsame(norm, '1') || ora_lsame(norm, 'O');
+    if (!onenrm && !ora_lsame(norm, 'I')) *info = -1;
+    else if (n < 0) *info = -2;
+    else if (lda < imax(1, n)) *info = -4;
+    else if (anorm < 0.0) *info = -5;
+    if (*info != 0) return;
+    *rcond = 0.0;
+    if (n == 0) { *rcond = 1.0; return; }
+    else if (anorm == 0.0) return;
+    else if (anorm != anorm) { *rcond = anorm; *info = -5; return; }
+    else if (anorm > hugeval) { *info = -5; return; }
+    const double smlnum = ora_dlamch('S');
+    double ainvnm = 0.0, sl, su, scale;
+    char normin = 'N';
+    const int kase1 = onenrm ? 1 : 2;
+    int kase = 0, isave[3] = {0, 0, 0}, iinfo;
+    for (;;) {
+        ora_dlacn2(n, work + n, work, iwork, &ainvnm, &kase, isave);
+        if (kase == 0) break;
+        if (kase == kase1) {
+            ora_dlatrs('L', 'N', 'U', normin, n, a, lda, work, &sl, work + 2 * n, &iinfo);
+            ora_dlatrs('U', 'N', 'N', normin, n, a, lda, work, &su, work + 3 * n, &iinfo);
+        } else {
+            ora_dlatrs('U', 'T', 'N', normin, n, a, lda, work, &su, work + 3 * n, &iinfo);
+            ora_dlatrs('L', 'T', 'U', normin, n, a, lda, work, &sl, work + 2 * n, &iinfo);
+        }
+        scale = sl * su;
+        normin = 'Y';
+        if (scale != 1.0) {
+            int ix = ora_idamax(n, work, 1);
+            if (scale < fabs(work[ix - 1]) * smlnum || scale == 0.0) return;
+            ora_drscl(n, scale, work);
+        }
+    }
+    if (ainvnm != 0.0) *rcond = (1.0 / ainvnm) / anorm;
+    else { *info = 1; return; }
+    if (*rcond != *rcond || *rcond > hugeval) *info = 1;
+}
+
+/* SRC/dgeequ.f:160-310 */
+void ora_dgeequ(int m, int n, const double *a, int lda, double *r, double *c, double *rowcnd, double *colcnd, double *amax,
+                int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (lda < imax(1, m)) *info = -4;
+    if (*info != 0) return;
+    if (m == 0 || n == 0) { *rowcnd = 1.0; *colcnd = 1.0; *amax = 0.0; return; }
+    const double smlnum = ora_dlamch('S'), bignum = 1.0 / smlnum;
+    for (int i = 0; i < m; ++i) r[i] = 0.0;
+    for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) r[i] = fmax(r[i], fabs(A_(i, j)));
+    double rcmin = bignum, rcmax = 0.0;
+    for (int i = 0; i < m; ++i) { rcmax = fmax(rcmax, r[i]); rcmin = fmin(rcmin, r[i]); }
+    *amax = rcmax;
+    if (rcmin == 0.0) { for (int i = 0; i < m; ++i) if (r[i] == 0.0) { *info = i + 1; return; } }
+    else {
+        for (int i = 0; i < m; ++i) r[i] = 1.0 / fmin(fmax(r[i], smlnum), bignum);
+        *rowcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+    }
+    for (int j = 0; j < n; ++j) c[j] = 0.0;
+    for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) c[j] = fmax(c[j], fabs(A_(i, j)) * r[i]);
+    rcmin = bignum; rcmax = 0.0;
+    for (int j = 0; j < n; ++j) { rcmin = fmin(rcmin, c[j]); rcmax = fmax(rcmax, c[j]); }
+    if (rcmin == 0.0) { for (int j = 0; j < n; ++j) if (c[j] == 0.0) { *info = m + j + 1; return; } }
+    else {
+        for (int j = 0; j < n; ++j) c[j] = 1.0 / fmin(fmax(c[j], smlnum), bignum);
+        *colcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum);
+    }
+}
+
+/* SRC/dlaqge.f:160-230; returns EQUED */
+char ora_dlaqge(int m, int n, double *a, int lda, const double *r, const double *c, double rowcnd, double colcnd, double amax)
+{
+    const double thresh = 0.1;
+    if (m <= 0 || n <= 0) return 'N';
+    const double small = ora_dlamch('S') / ora_dlamch('P'), large = 1.0 / small;
+    if (rowcnd >= thresh && amax >= small && amax <= large) {
+        if (colcnd >= thresh) return 'N';
+        for (int j = 0; j < n; ++j) { double cj = c[j]; for (int i = 0; i < m; ++i) A_(i, j) = cj * A_(i, j); }
+        return 'C';
+    } else if (colcnd >= thresh) {
+        for (int j = 0; j < n; ++j) for (int i = 0; i < m; ++i) A_(i, j) = r[i] * A_(i, j);
+        return 'R';
+    }
+    for (int j = 0; j < n; ++j) { double cj = c[j]; for (int i = 0; i < m; ++i) A_(i, j) = cj * r[i] * A_(i, j); }
+    return 'B';
+}
+
+static double lantr_max_upper_(int m, int n, const double *a, int lda)        /* DLANTR('M','U','N', m, n) (dlantr.f:190-200) */
+{
+    double v = 0.0;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < imin(m, j + 1); ++i) { double t = fabs(A_(i, j)); if (v < t || t != t) v = t; }
+    return v;
+}
+
+/* SRC/dgesvx.f:344-600.  work: 4n doubles (work[0] returns RPVGRW), iwork: n ints.  equed is in/out. */
+void ora_dgesvx(char fact, char trans, int n, int nrhs, double *a, int lda, double *af, int ldaf, int *ipiv, char *equed,
+                double *r, double *c, double *b, int ldb, double *x, int ldx, double *rcond, double *ferr, double *berr,
+                double *work, int *iwork, int *info)
+{
+    *info = 0;
+    const int nofact = ora_lsame(fact, 'N'), equil = ora_lsame(fact, 'E'), notran = ora_lsame(trans, 'N');
+    int rowequ, colequ;
+    double smlnum = ora_dlamch('S'), bignum = 1.0 / smlnum, rowcnd = 1.0, colcnd = 1.0, amax, rcmin, rcmax, rpvgrw;
+    if (nofact || equil) { *equed = 'N'; rowequ = 0; colequ = 0; }
+    else { rowequ = ora_lsame(*equed, 'R') || ora_lsame(*equed, 'B'); colequ = ora_lsame(*equed, 'C') || ora_lsame(*equed, 'B'); }
+    if (!nofact && !equil && !ora_lsame(fact, 'F')) *info = -1;
+    else if (!notran && !ora_lsame(trans, 'T') && !ora_lsame(trans, 'C')) *info = -2;
+    else if (n < 0) *info = -3;
+    else if (nrhs < 0) *info = -4;
+    else if (lda < imax(1, n)) *info = -6;
+    else if (ldaf < imax(1, n)) *info = -8;
+    else if (ora_lsame(fact, 'F') && !(rowequ || colequ || ora_lsame(*equed, 'N'))) *info = -10;
+    else {
+        if (rowequ) {
+            rcmin = bignum; rcmax = 0.0;
+            for (int j = 0; j < n; ++j) { rcmin = fmin(rcmin, r[j]); rcmax = fmax(rcmax, r[j]); }
+            if (rcmin <= 0.0) *info = -11; else if (n > 0) rowcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum); else rowcnd = 1.0;
+        }
+        if (colequ && *info == 0) {
+            rcmin = bignum; rcmax = 0.0;
+            for (int j = 0; j < n; ++j) { rcmin = fmin(rcmin, c[j]); rcmax = fmax(rcmax, c[j]); }
+            if (rcmin <= 0.0) *info = -12; else if (n > 0) colcnd = fmax(rcmin, smlnum) / fmin(rcmax, bignum); else colcnd = 1.0;
+        }
+        if (*info == 0) { if (ldb < imax(1, n)) *info = -14; else if (ldx < imax(1, n)) *info = -16; }
+    }
+    if (*info != 0) return;
+    if (equil) {
+        int infequ;
+        ora_dgeequ(n, n, a, lda, r, c, &rowcnd, &colcnd, &amax, &infequ);
+        if (infequ == 0) {
+            *equed = ora_dlaqge(n, n, a, lda, r, c, rowcnd, colcnd, amax);
+            rowequ = ora_lsame(*equed, 'R') || ora_lsame(*equed, 'B');
+            colequ = ora_lsame(*equed, 'C') || ora_lsame(*equed, 'B');
+        }
+    }
+    if (notran) { if (rowequ) for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) b[i + (size_t)j * ldb] *= r[i]; }
+    else if (colequ) for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) b[i + (size_t)j * ldb] *= c[i];
+    if (nofact || equil) {
+        ora_dlacpy('F', n, n, a, lda, af, ldaf);
+        ora_dgetrf(n, n, af, ldaf, ipiv, info);
+        if (*info > 0) {
+            rpvgrw = lantr_max_upper_(*info, *info, af, ldaf);
+            if (rpvgrw == 0.0) rpvgrw = 1.0; else rpvgrw = ora_dlange('M', n, *info, a, lda) / rpvgrw;
+            work[0] = rpvgrw;
+            *rcond = 0.0;
+            return;
+        }
+    }
+    char norm = notran ? '1' : 'I';
+    double anorm = ora_dlange(norm, n, n, a, lda);
+    rpvgrw = lantr_max_upper_(n, n, af, ldaf);
+    if (rpvgrw == 0.0) rpvgrw = 1.0; else rpvgrw = ora_dlange('M', n, n, a, lda) / rpvgrw;
+    ora_dgecon(norm, n, af, ldaf, anorm, rcond, work, iwork, info);
+    ora_dlacpy('F', n, nrhs, b, ldb, x, ldx);
+    ora_dgetrs(trans, n, nrhs, af, ldaf, ipiv, x, ldx, info);
+    ora_dgerfs(trans, n, nrhs, a, lda, af, ldaf, ipiv, b, ldb, x, ldx, ferr, berr, work, iwork, info);
+    if (notran) {
+        if (colequ) {
+            for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) x[i + (size_t)j * ldx] *= c[i];
+            for (int j = 0; j < nrhs; ++j) ferr[j] /= colcnd;
+        }
+    } else if (rowequ) {
+        for (int j = 0; j < nrhs; ++j) for (int i = 0; i < n; ++i) x[i + (size_t)j * ldx] *= r[i];
+        for (int j = 0; j < nrhs; ++j) ferr[j] /= rowcnd;
+    }
+    work[0] = rpvgrw;
+    if (*rcond < ora_dlamch('E')) *info = n + 1;
+}
