@@ -419,3 +419,62 @@ def test_dgesvx_matches_netlib(golden_gecon):
             assert _close(res["x"][:, j], g[f"svx{k}_x"][:, j], tol), (k, j, tol)
         assert np.all(res["berr"] <= 4 * 2.0 ** -53 * (n + 1)) and np.all(g[f"svx{k}_berr"] <= 4 * 2.0 ** -53 * (n + 1))
         assert np.all(res["ferr"] <= 10 * g[f"svx{k}_ferr"]) and np.all(g[f"svx{k}_ferr"] <= 10 * res["ferr"])
+
+
+# ------------------------------------------------------------------------------------------- blocked drivers at >= 1000^2
+@pytest.fixture(scope="module")
+def golden_large():
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "netlib_golden_large.npz"))
+
+
+def _sample(a):
+    return np.ascontiguousarray(a[::7, ::7]), a.sum(axis=1)
+
+
+@pytest.mark.parametrize("tag", ["sq", "tall", "wide"])
+def test_blocked_dgetrf_large_matches_netlib(golden_large, tag):
+    """ora_dgetrf (SRC/dgetrf.f:164-219, NB = 64, with its DLASWP / DTRSM / DGEMM) at >= 1000^2 against netlib's recursive DGETRF2 on
+    the same DLARNV input: IPIV identical, factors to rounding."""
+    g = golden_large
+    m, n = (int(v) for v in g[f"lu_{tag}_shape"])
+    a, seed = O.random_matrix(m, n, (1988, 1989, 1990, 1991))
+    lu = a.copy(order="F")
+    ipiv, info = O.dgetrf(lu)
+    assert info == int(g[f"lu_{tag}_info"][0]) == 0
+    assert np.array_equal(ipiv, g[f"lu_{tag}_ipiv"])
+    smp, rs = _sample(lu)
+    assert np.max(np.abs(smp - g[f"lu_{tag}_sample"])) < 1e-11 * np.max(np.abs(smp))
+    assert np.max(np.abs(rs - g[f"lu_{tag}_rowsum"])) < 1e-10 * np.max(np.abs(rs))
+    if tag == "sq":
+        x, _ = O.random_matrix(n, 3, seed)
+        for tr in "NT":
+            sol = np.asfortranarray((a if tr == "N" else a.T) @ x)
+            O.dgetrs(tr, lu, ipiv, sol)                                 # SRC/dgetrs.f:187-217
+            ref = g[f"getrs_{tr}"]
+            assert np.max(np.abs(sol - ref)) / np.max(np.abs(ref)) < 1e-9
+            assert np.max(np.abs(sol - x)) / np.max(np.abs(x)) < 1e-8
+
+
+@pytest.mark.parametrize("uplo", "LU")
+def test_blocked_dpotrf_large_matches_netlib(golden_large, uplo):
+    g = golden_large
+    n = 1200
+    s, _ = O.spd_matrix(n, (1988, 1989, 1990, 1991))
+    f = s.copy(order="F")
+    assert O.dpotrf(uplo, f) == int(g[f"po_{uplo}_info"][0]) == 0       # SRC/dpotrf.f:166-240, NB = 64
+    tri = np.tril(f) if uplo == "L" else np.triu(f)
+    smp, rs = _sample(tri)
+    assert np.max(np.abs(smp - g[f"po_{uplo}_sample"])) < 1e-12 * np.max(np.abs(smp))
+    assert np.max(np.abs(rs - g[f"po_{uplo}_rowsum"])) < 1e-11 * np.max(np.abs(rs))
+
+
+def test_dlaswp_long_lists_match_netlib(golden_large):
+    g = golden_large
+    m, ncol = 1100, 40
+    enc = np.asfortranarray(np.arange(m)[:, None] * 1000.0 + np.arange(ncol)[None, :])
+    for k in range(int(g["n_swp"][0])):
+        k1, k2, incx = (int(v) for v in g[f"swp{k}_args"])
+        a = enc.copy(order="F")
+        O.dlaswp(a, k1, k2, g[f"swp{k}_ipiv"], incx)                    # SRC/dlaswp.f:138-183 (32-column strips + remainder)
+        assert np.array_equal(a[:, 0], g[f"swp{k}_col0"])
+        assert np.array_equal(a, a[:, :1] + np.arange(ncol)[None, :])
