@@ -31,6 +31,7 @@ struct GemmParams {
     int tiles_m, tiles_n;
     int kchunk;           // split-K: blockIdx.y owns k in [y*kchunk, (y+1)*kchunk); C advances by c_zstride
     i64 c_zstride;
+    const int* guard;     // device word: when non-null and non-zero the launch does nothing (Cholesky after INFO > 0)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
     int pid_m = first_m + (pid % width) % gsz;
     int pid_n = (pid % width) / gsz;
     const int m0 = pid_m * BM, n0 = pid_n * BN;
+    if (p.guard && *p.guard != 0) return;
     if (p.tri == 1 && m0 + BM - 1 < n0) return;       // tile strictly above the diagonal
     if (p.tri == 2 && n0 + BN - 1 < m0) return;       // tile strictly below the diagonal
 
@@ -415,6 +417,7 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
     p.tiles_m = p.tiles_n = 0;
     p.kchunk = k;
     p.c_zstride = 0;
+    p.guard = kernel_guard();
     int cfg = g_gemm_cfg;
     // Reduce-shaped products (few output tiles, long K: V^T*C in the QR panel, V^T*V) are split along K;
     // the slices go to scratch and are summed in a fixed order (deterministic).

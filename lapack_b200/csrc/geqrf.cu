@@ -629,7 +629,7 @@ static void geqrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, double
     }
 }
 
-// max |A| -> power-of-two scale factor (1.0 when no scaling is needed), kept on the device
+// max |A| of a device matrix (finite entries only), as the bit pattern of a non-negative double
 __global__ void amax_kernel(int m, int n, const double* __restrict__ A, i64 lda, unsigned long long* amax_bits) {
     double v = 0.0;
     for (i64 j = blockIdx.x; j < n; j += gridDim.x)
@@ -640,27 +640,43 @@ __global__ void amax_kernel(int m, int n, const double* __restrict__ A, i64 lda,
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
     if ((threadIdx.x & 31) == 0) atomicMax(amax_bits, (unsigned long long)__double_as_longlong(v));
 }
-__global__ void decide_scale_kernel(const unsigned long long* amax_bits, double* scale) {
-    double amax = __longlong_as_double((long long)*amax_bits);
-    double sc = 1.0;
-    if (amax > 0.0) {
-        int e;
-        frexp(amax, &e);
-        if (e > 400 || e < -400) { sc = ldexp(1.0, 1 - e); scale[1] = ldexp(1.0, e - 1); }
+
+// Exact power-of-two scaling PER COLUMN against over/underflow in the fused sum-of-squares reduction of the leaves (the reference
+// gets the same protection from DNRM2's scaled accumulation and DLARFG's rescaling loop, dlarfg.f:159-176).  QR commutes with
+// positive column scalings: A D = Q (R D) with the same reflectors and the same tau, so a column whose largest entry lies outside
+// 2^+-300 is multiplied by 2^(1-e) before the factorization and its part of R (rows <= column) by the inverse afterwards.  Powers of
+// two: every other column's result is bit-identical to the unscaled computation.
+__global__ void col_scale_decide_kernel(int m, int n, const double* __restrict__ A, i64 lda, double* __restrict__ dcol, int* __restrict__ any) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= n) return;
+    const double* col = A + (i64)j * lda;
+    double v = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const double x = fabs(col[i]);
+        if (x == x && x <= DBL_MAX) v = fmax(v, x);       // ignore NaN/Inf: they propagate on their own
     }
-    scale[0] = sc;
-    if (sc == 1.0) scale[1] = 1.0;
+    for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+    if (lane == 0) {
+        double d = 1.0;
+        if (v > 0.0) {
+            int e;
+            frexp(v, &e);
+            if (e > 300 || e < -300) { d = ldexp(1.0, 1 - e); atomicOr(any, 1); }
+        }
+        dcol[j] = d;
+    }
 }
-// A := A * scale[which]; tri: 0 all, 1 = upper triangle incl. diagonal only (R)
-__global__ void scale_by_dev_kernel(int m, int n, double* __restrict__ A, i64 lda, const double* scale, int which,
-                                    int upper_only) {
-    const double sc = scale[which];
-    if (sc == 1.0) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// A(:,j) *= d(j) (inverse = 0) or A(0:j, j) /= d(j) (inverse = 1: un-scale R), flagged columns only
+__global__ void col_scale_apply_kernel(int m, int n, double* __restrict__ A, i64 lda, const double* __restrict__ dcol, const int* __restrict__ any,
+                                       int inverse) {
+    if (*any == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     for (int j = blockIdx.y; j < n; j += gridDim.y) {
-        if (upper_only && i > j) continue;
-        A[i + (i64)j * lda] *= sc;
+        const double d = dcol[j];
+        if (d == 1.0) continue;
+        if (inverse) { if (i <= j) A[i + (i64)j * lda] *= (1.0 / d); }
+        else A[i + (i64)j * lda] *= d;
     }
 }
 
@@ -698,16 +714,15 @@ static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double*
     double* W2p = (double*)ws_alloc(s, sizeof(double) * ldw * nb);
     double* W1u = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));    // trailing-update scratch
     double* W2u = (double*)ws_alloc(s, sizeof(double) * ldw * max(n, nb));
-    unsigned long long* amax_bits = (unsigned long long*)ws_alloc(s, 64);
-    double* scale = (double*)(amax_bits + 2);
+    double* dcol = (double*)ws_alloc(s, sizeof(double) * (size_t)n + 64);
+    int* any_scaled = (int*)(dcol + n);
 
-    // exact power-of-two pre-scaling against over/underflow in the fused norm reduction
-    LB_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 8, s));
-    amax_kernel<<<min(n, 4 * num_sms()), 256, 0, s>>>(m, n, A, lda, amax_bits);
-    decide_scale_kernel<<<1, 1, 0, s>>>(amax_bits, scale);
+    // exact power-of-two pre-scaling of out-of-range columns (see col_scale_decide_kernel)
+    LB_CUDA_CHECK(cudaMemsetAsync(any_scaled, 0, sizeof(int), s));
+    col_scale_decide_kernel<<<ceil_div(n, 8), 256, 0, s>>>(m, n, A, lda, dcol, any_scaled);
     dim3 sgrid(ceil_div(m, 256), (unsigned)min(n, 4096));
-    scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 0, 0);
-    count_launch(3);
+    col_scale_apply_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, dcol, any_scaled, 0);
+    count_launch(2);
 
     Aux& ax = aux();
     cudaStream_t sp = la ? ax.panel_stream : s;
@@ -754,11 +769,11 @@ static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double*
         LB_CUDA_CHECK(cudaEventRecord(ev_next, sp));
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_next, 0));
     }
-    scale_by_dev_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, scale, 1, 1);   // un-scale R only
+    col_scale_apply_kernel<<<sgrid, 256, 0, s>>>(m, n, A, lda, dcol, any_scaled, 1);   // un-scale R only
     count_launch();
     ws_free(s, Vc[0]); ws_free(s, T[0]);
     if (la) { ws_free(s, Vc[1]); ws_free(s, T[1]); }
-    ws_free(s, W1p); ws_free(s, W2p); ws_free(s, W1u); ws_free(s, W2u); ws_free(s, amax_bits);
+    ws_free(s, W1p); ws_free(s, W2p); ws_free(s, W1u); ws_free(s, W2u); ws_free(s, dcol);
     LB_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -129,5 +129,7 @@ struct Aux {
 Aux& aux();
 
 int num_sms();
+const int* kernel_guard();                 // see runtime.cu: device INFO word that disables queued Level-3 kernels once non-zero
+void set_kernel_guard(const int* p);
 
 }  // namespace lb

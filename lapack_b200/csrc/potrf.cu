@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(PL* PL) potrf_leaf_kernel(int n, double* __res
     __shared__ int s_fail;
     const int i = threadIdx.x, j = threadIdx.y;     // element (i,j) of the lower triangle, i >= j
     const bool mine = (i < n && j < n && i >= j);
+    if (*info != 0) return;                         // an earlier leaf failed: the factorization has been abandoned (dpotrf.f:239-240)
     if (mine) L[i][j] = upper ? A[j + (i64)i * lda] : A[i + (i64)j * lda];
     if (i == 0 && j == 0) s_fail = 0;
     __syncthreads();
@@ -90,9 +91,16 @@ static void potrf_rec(cudaStream_t s, bool upper, int n, double* A, i64 lda, int
 
 static std::mutex g_po_mutex;
 
+// every Level-3 kernel queued by the Cholesky drivers carries the INFO word as a guard (runtime.cu)
+struct GuardScope {
+    explicit GuardScope(const int* p) { set_kernel_guard(p); }
+    ~GuardScope() { set_kernel_guard(nullptr); }
+};
+
 void potrf2(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
     std::lock_guard<std::mutex> lock(g_po_mutex);
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
+    GuardScope guard(info);
     potrf_rec(s, uplo == 'U' || uplo == 'u', n, A, lda, info, 0);
 }
 
@@ -100,6 +108,7 @@ void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
     std::lock_guard<std::mutex> lock(g_po_mutex);
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     if (n <= 0) return;
+    GuardScope guard(info);
     const bool upper = (uplo == 'U' || uplo == 'u');
     const int nb = g_po_nb;
     if (nb >= n) { potrf_rec(s, upper, n, A, lda, info, 0); return; }

@@ -18,6 +18,14 @@ void clear_cuda_error() {
     (void)cudaGetLastError();
 }
 
+// Device word that turns the Level-3 kernels launched while it is set into no-ops once it becomes non-zero: DPOTRF aborts at
+// the first non-positive leading minor (dpotrf.f:219-220,239-240), so everything queued behind the failing leaf must not run
+// on the unfactored block (it would spread Inf/NaN over the trailing matrix).  Set / cleared by the Cholesky drivers under
+// the library mutex.
+static thread_local const int* g_kernel_guard = nullptr;   // per host thread: concurrent callers must not see each other's guard
+const int* kernel_guard() { return g_kernel_guard; }
+void set_kernel_guard(const int* p) { g_kernel_guard = p; }
+
 StreamOut*& stream_out() {
     static StreamOut* so = nullptr;
     return so;

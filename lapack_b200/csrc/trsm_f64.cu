@@ -34,8 +34,9 @@ __device__ __forceinline__ void load_leaf_tri(double (*T)[TB + 1], const double*
 template <bool LOWER>
 __global__ void __launch_bounds__(128) trsm_left_leaf_kernel(int nb, int n, const double* __restrict__ A, i64 lda,
                                                              bool a_upper, bool trans, bool unit, double* __restrict__ B,
-                                                             i64 ldb) {
+                                                             i64 ldb, const int* guard) {
     __shared__ double T[TB][TB + 1];
+    if (guard && *guard != 0) return;
     load_leaf_tri(T, A, lda, nb, a_upper, trans);
     __syncthreads();
     int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -74,8 +75,9 @@ __global__ void __launch_bounds__(128) trsm_left_leaf_kernel(int nb, int n, cons
 template <bool UPPER_T>
 __global__ void __launch_bounds__(128) trsm_right_leaf_kernel(int m, int nb, const double* __restrict__ A, i64 lda,
                                                               bool a_upper, bool trans, bool unit, double* __restrict__ B,
-                                                              i64 ldb) {
+                                                              i64 ldb, const int* guard) {
     __shared__ double T[TB][TB + 1];
+    if (guard && *guard != 0) return;
     load_leaf_tri(T, A, lda, nb, a_upper, trans);
     __syncthreads();
     int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,8 +206,8 @@ static void trsm_left_rec(cudaStream_t s, bool upper, bool trans, bool unit, int
     const bool eff_lower = (upper == trans);   // (L,N) or (U,T)
     if (m <= TB) {
         int threads = 128;
-        if (eff_lower) trsm_left_leaf_kernel<true><<<ceil_div(n, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb);
-        else trsm_left_leaf_kernel<false><<<ceil_div(n, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb);
+        if (eff_lower) trsm_left_leaf_kernel<true><<<ceil_div(n, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
+        else trsm_left_leaf_kernel<false><<<ceil_div(n, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
         count_launch();
         return;
     }
@@ -234,8 +236,8 @@ static void trsm_right_rec(cudaStream_t s, bool upper, bool trans, bool unit, in
     const bool eff_upper = (upper != trans);   // (U,N) or (L,T)
     if (n <= TB) {
         int threads = 128;
-        if (eff_upper) trsm_right_leaf_kernel<true><<<ceil_div(m, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb);
-        else trsm_right_leaf_kernel<false><<<ceil_div(m, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb);
+        if (eff_upper) trsm_right_leaf_kernel<true><<<ceil_div(m, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
+        else trsm_right_leaf_kernel<false><<<ceil_div(m, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
         count_launch();
         return;
     }

@@ -468,6 +468,32 @@ def test_dpotrf_not_positive_definite(lb):
     assert lb.f77.potrf("L", b.copy(order="F")) == 41              # NaN on the diagonal (dpotrf2.f:169)
 
 
+def test_dpotrf_abort_leaves_finite_matrix(lb):
+    """dpotrf.f:219-220,239-240: the factorization stops at the first non-positive leading minor.  Everything queued behind the
+    failing block (DTRSM / DSYRK / later panels, block-column downloads of the streamed host path) must not run on the unfactored
+    block: no Inf/NaN may appear, and the block columns finished before the failure are the oracle's."""
+    n, izero = 2600, 1301
+    s, _ = O.spd_matrix(n, SEED)
+    s[izero - 1, :] = 0.0
+    s[:, izero - 1] = 0.0
+    ref = s.copy(order="F")
+    assert O.dpotrf("L", ref) == izero
+    nb = 512
+    done = ((izero - 1) // nb) * nb                                 # block columns completely factored before the failure
+    for pinned in (False, True):
+        if pinned:
+            buf = torch.empty((n, n), dtype=torch.float64).pin_memory()
+            got = buf.numpy().T                                     # column-major view of pinned memory
+            got[:, :] = s
+        else:
+            got = s.copy(order="F")
+        assert lb.f77.dpotrf("L", n, got if not pinned else buf.data_ptr(), n) == izero
+        g = np.tril(got)
+        assert np.all(np.isfinite(g)), pinned
+        assert np.max(np.abs(g[:, :done] - np.tril(ref)[:, :done])) < 1e-10 * np.max(np.abs(ref))
+        assert np.array_equal(np.triu(got, 1), np.triu(s, 1))       # the other triangle is never touched
+
+
 def test_dposv_dpotrs_solution(lb):
     for uplo in "LU":
         for (n, nrhs) in ((1, 1), (150, 3), (900, 1)):
@@ -526,6 +552,27 @@ def test_dgeqrf_scaled_inputs(lb):
         assert info == 0 and np.all(np.isfinite(got))
         res = O.dqrt01(b, got, tau)
         assert res[0] < O.THRESH and res[1] < O.THRESH
+
+
+def test_dgeqrf_graded_columns(lb):
+    """Columns of wildly different magnitude inside one matrix: a column of entries ~1e-200 next to O(1) columns must
+    keep its relative accuracy -- the reference gets it from DNRM2's scaled sum and DLARFG's rescaling loop (dlarfg.f:159-176)."""
+    m, n = 150, 90
+    a, _ = O.random_matrix(m, n, SEED)
+    d = 10.0 ** np.where(np.arange(n) % 3 == 0, -200.0, np.where(np.arange(n) % 3 == 1, 0.0, 180.0))
+    b = np.asfortranarray(a * d[None, :])
+    ref = b.copy(order="F")
+    tau_ref, _, _ = O.dgeqrf(ref)
+    got = b.copy(order="F")
+    tau, info, _ = lb.f77.geqrf(got)
+    assert info == 0 and np.all(np.isfinite(got))
+    assert np.max(np.abs(tau - tau_ref)) < 1e-12
+    v_got, v_ref = np.tril(got, -1), np.tril(ref, -1)
+    assert np.max(np.abs(v_got - v_ref)) < 1e-11                              # reflectors are scale-free
+    r_got, r_ref = np.triu(got[:n]), np.triu(ref[:n])
+    colmax = np.max(np.abs(r_ref), axis=0)
+    assert np.all(colmax > 0)
+    assert np.max(np.abs(r_got - r_ref) / colmax[None, :]) < 1e-11           # every column of R to ITS OWN scale
 
 
 def test_dlarft_dlarfb_vs_oracle(lb):
