@@ -244,6 +244,67 @@ def run_dist(args, rank, world, local_rank):
             assert ok, msg
         torch.cuda.empty_cache()
 
+    # ---- SURVEY 8e second row on the driver's hardware: distributed Cholesky / QR (block-column cyclic, lapack_b200/dist.py):
+    # factors against the single-GPU factorization at n=8192, then one timed run each at n_dist/2
+    other = {}
+    if not args.no_check:
+        from lapack_b200.dist import BlockCyclic1D, GpuOps, fill_local_random, ppotrf, pgeqrf
+        ops1 = GpuOps(dev)
+        for which in ("dpotrf", "dgeqrf"):
+            nc = 8192
+            d1 = BlockCyclic1D(nc, 512 if which == "dpotrf" else 256, world, rank)
+            cols = torch.tensor([d1.global_col(c) for c in range(d1.local_cols())], device=dev, dtype=torch.long)
+            full = lb.dev.larnv_matrix(nc, nc, device=dev)
+            if which == "dpotrf":
+                lb.dev.make_spd(full, float(nc))
+            aloc = lb.dev.colmajor(nc, len(cols), device=dev)
+            aloc.copy_(full[:, cols])
+            if which == "dpotrf":
+                info_d = ppotrf(ops1, dist, d1, aloc)
+                info_1 = int(lb.dev.potrf("L", full).item())
+                low = (torch.arange(nc, device=dev).unsqueeze(1) >= cols.unsqueeze(0))
+                diff = ((full[:, cols] - aloc).abs() * low).max().item()
+                ok = info_d == 0 and info_1 == 0 and diff < 1e-9
+            else:
+                tau_d = pgeqrf(ops1, dist, d1, aloc)
+                tau_1 = lb.dev.geqrf(full).cpu().numpy()
+                diff = (full[:, cols] - aloc).abs().max().item() / full.abs().max().item()
+                ok = diff < 1e-10 and float(np.max(np.abs(tau_d - tau_1))) < 1e-10
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            checks[f"n8192_p{which}_equals_single_gpu"] = bool(flag.item())
+            assert flag.item() == 1, (which, diff)
+            del full, aloc
+            torch.cuda.empty_cache()
+            # timing at n_dist / 2 (the matrix of the LU leg would not leave room for a second copy)
+            nt = n // 2
+            d2 = BlockCyclic1D(nt, 512 if which == "dpotrf" else 256, world, rank)
+            a2 = fill_local_random(ops1, d2, device=dev)
+            if which == "dpotrf":
+                c2 = torch.tensor([d2.global_col(c) for c in range(d2.local_cols())], device=dev, dtype=torch.long)
+                a2[c2, torch.arange(len(c2), device=dev)] += float(nt)         # diagonally dominant; only the lower triangle is read
+            w2 = a2.clone()
+            ts = []
+            for rep in range(2):
+                w2.copy_(a2)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                if which == "dpotrf":
+                    ppotrf(ops1, dist, d2, w2)
+                else:
+                    pgeqrf(ops1, dist, d2, w2)
+                e1.record()
+                torch.cuda.synchronize()
+                tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                ts.append(tt.item())
+            fl2 = flops_potrf(nt) if which == "dpotrf" else flops_geqrf(nt, nt)
+            other[f"p{which}"] = {"n": nt, "ms": min(ts), "tflops": fl2 / (min(ts) * 1e-3) * 1e-12,
+                                  "tflops_per_gpu": fl2 / (min(ts) * 1e-3) * 1e-12 / world, "layout": f"block-column cyclic 1x{world}"}
+            del a2, w2
+            torch.cuda.empty_cache()
+
     a0 = fill_local_random_2d(desc, device=dev)
     a = lb.dev.colmajor(desc.mloc, desc.nloc, device=dev)
     fl = flops_getrf(n)
@@ -301,6 +362,7 @@ def run_dist(args, rank, world, local_rank):
                     "note": "the distributed matrix is generated on the devices (128 GiB does not pass through one host buffer); only IPIV/INFO return to the host"},
             "gpu_launches": int(lt.item()), "clocks": clocks,
             "checks": dict(checks, randomized_residual_ratio=resid, info=int(info)),
+            "distributed_cholesky_qr": other,
             "t1_single_gpu_same_n": t1,
             "parallel_efficiency_vs_t1": (t1["ms"] / (world * ms / args.steps)) if (t1 and t1.get("n") == n) else None,
             "batched_dgetrf_32x32": batched,

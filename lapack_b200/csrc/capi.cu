@@ -24,8 +24,9 @@ void trsm_set_fewrhs_mode(int mode);
 }  // namespace lb
 
 static inline cudaStream_t S(void* s) { return (cudaStream_t)s; }
+// return code of ONE call: only errors raised since the previous lb200_* call returned are reported, and they are consumed
 static inline int rc() {
-    int e = lb::last_cuda_error();
+    const int e = lb::take_cuda_error();
     return e ? -1000 - e : 0;
 }
 

@@ -183,8 +183,8 @@ struct Ctx {
         for (auto& it : items) lb::ws_free(s, it.dev);
         if (dinfo) lb::ws_free(s, dinfo);
         LB_CUDA_CHECK(cudaStreamSynchronize(s));
-        int e = lb::last_cuda_error();
-        if (e) { lb::clear_cuda_error(); return -1001 - e; }
+        int e = lb::take_cuda_error();
+        if (e) return -1001 - e;
         return hinfo;
     }
 };
@@ -448,8 +448,8 @@ static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
     lb::ws_free(s, dp);
     lb::ws_free(s, dinfo);
     LB_CUDA_CHECK(cudaStreamSynchronize(s));
-    int e = lb::last_cuda_error();
-    if (e) { lb::clear_cuda_error(); return -1001 - e; }
+    int e = lb::take_cuda_error();
+    if (e) return -1001 - e;
     return hinfo;
 }
 
@@ -668,7 +668,7 @@ static int potrf_host_streamed(bool upper, int n, double* A, int lda, int nrhs =
     LB_CUDA_CHECK(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (nrhs > 0) {
         LB_CUDA_CHECK(cudaStreamSynchronize(s));               // INFO decides whether the solve happens
-        if (hinfo == 0 && lb::last_cuda_error() == 0) {
+        if (hinfo == 0 && lb::pending_cuda_error() == 0) {
             LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
             lb::potrs(s, ul, n, nrhs, dA, ldd, dB, ldd);
             LB_CUDA_CHECK(cudaMemcpy2DAsync(B, (size_t)ldb * 8, dB, ldd * 8, (size_t)n * 8, nrhs, cudaMemcpyDeviceToHost, s));
@@ -680,8 +680,8 @@ static int potrf_host_streamed(bool upper, int n, double* A, int lda, int nrhs =
     if (dB) lb::ws_free(s, dB);
     lb::ws_free(s, dinfo);
     LB_CUDA_CHECK(cudaStreamSynchronize(s));
-    int e = lb::last_cuda_error();
-    if (e) { lb::clear_cuda_error(); return -1001 - e; }
+    int e = lb::take_cuda_error();
+    if (e) return -1001 - e;
     return hinfo;
 }
 

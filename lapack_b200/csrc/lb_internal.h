@@ -25,6 +25,8 @@ typedef long long i64;
 
 void record_cuda_error(cudaError_t e);
 int last_cuda_error();        // 0 if none since last clear
+int take_cuda_error();        // error raised since the last take (0 if none); consumes it
+int pending_cuda_error();     // same without consuming
 void clear_cuda_error();
 
 inline __host__ __device__ i64 idx2(i64 i, i64 j, i64 ld) { return i + j * ld; }

@@ -7,14 +7,24 @@
 
 namespace lb {
 
-static std::atomic<int> g_cuda_err{0};
+// Two latches: `pending` is consumed by the call that reports it (so one failed call does not poison the return codes of
+// later, successful calls); `last` stays readable through lb200_last_cuda_error() until lb200_clear_cuda_error().
+static std::atomic<int> g_cuda_err{0}, g_cuda_err_last{0};
 void record_cuda_error(cudaError_t e) {
     int expected = 0;
     g_cuda_err.compare_exchange_strong(expected, (int)e);
+    g_cuda_err_last.store((int)e);
 }
-int last_cuda_error() { return g_cuda_err.load(); }
+int last_cuda_error() { int e = g_cuda_err.load(); return e ? e : g_cuda_err_last.load(); }
+int pending_cuda_error() { return g_cuda_err.load(); }
+int take_cuda_error() {
+    const int e = g_cuda_err.exchange(0);
+    if (e) (void)cudaGetLastError();
+    return e;
+}
 void clear_cuda_error() {
     g_cuda_err.store(0);
+    g_cuda_err_last.store(0);
     (void)cudaGetLastError();
 }
 
