@@ -629,6 +629,14 @@ def run_ours(args, rank, world, local_rank):
               "x_rel_err_vs_oracle": float(np.max(np.abs(sol1 - keep["x"])) / np.max(np.abs(keep["x"]))) if "x" in keep else None,
               "x_rel_err_vs_xact": float(np.max(np.abs(sol1 - x1)) / np.max(np.abs(x1)))}
     gemm_tf = (gfl.value / (gms.value * 1e-3) * 1e-12) if gms.value > 0 else None
+    traffic, traffic_note = None, "no ncu capture found under profiles/"
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
+        traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of ONE representative trailing-update launch (m=n={tr['m']}, k={tr['k']}; "
+                        f"algorithmic {tr['algorithmic_bytes']:.3e} B), read from profiles/r02_gemm_traffic.json ({tr['source']})")
+    except Exception:
+        pass
     hbm = 6650.0
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", hbm)
@@ -662,8 +670,7 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
                      "peak_cublas": peak_cublas, "frac_of_cublas": (gemm_tf / peak_cublas) if gemm_tf else None,
                      "peak_cublas_note": "cuBLAS DGEMM 8192^3 via torch.matmul timed in this run (independent denominator, checker only)",
-                     "traffic": 5.41e9, "traffic_note": "dram read+write bytes of ONE representative trailing-update launch "
-                     "(m=n=16384, k=512; algorithmic 4.43e9 B) from profiles/r01_gemm_cfg8_ncu_full_16384x16384x512.txt",
+                     "traffic": traffic, "traffic_note": traffic_note,
                      "launches_timed": int(gcnt.value),
                      "peak_source": "FP64 DMMA.8x8x4 issue-rate peak measured in this run by lb200_fp64_peak_tflops "
                                     "(MEASURED_PEAKS.json carries HBM and bf16 only)"},
