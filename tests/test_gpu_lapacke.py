@@ -192,3 +192,93 @@ def test_lapacke_dgelqf_dormlq(libs, layout):
                               tau.ctypes.data_as(dp), cbuf.ctypes.data_as(dp), nc if layout == ROW else n)
         assert rc == 0, name
         assert np.max(np.abs(cbuf - c_ref)) < 1e-12, name
+
+
+def _ref_lapacke(libs):
+    for name, L in libs:
+        if name == "reference-lapacke":
+            return L
+    pytest.skip("oracle/_ref/liblapacke_ref.so not built")
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_reference_lapacke_dgecon_dgeequ_on_our_symbols(libs, layout):
+    """The reference's OWN LAPACKE_dgecon / LAPACKE_dgeequ (LAPACKE/src/lapacke_dgecon.c, lapacke_dgeequ.c), compiled in place, call our
+    dgecon_ / dgeequ_ (row-major goes through their transposition): same RCOND as the oracle's DGECON."""
+    L = _ref_lapacke(libs)
+    L.LAPACKE_dgecon.argtypes = [C.c_int, C.c_char, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    n = 260
+    a, _ = O.random_matrix(n, n, SEED)
+    lu = a.copy(order="F")
+    O.dgetrf(lu)
+    buf = np.array(lu, order="C" if layout == ROW else "F", copy=True)
+    for norm in (b"1", b"I"):
+        anorm = float(np.linalg.norm(a, 1 if norm == b"1" else np.inf))
+        rc_ref, _ = O.dgecon(norm.decode(), lu, anorm)
+        rcond = C.c_double(0.0)
+        assert L.LAPACKE_dgecon(layout, norm, n, vp(buf), n, anorm, C.byref(rcond)) == 0
+        assert abs(rcond.value - rc_ref) <= 1e-9 * rc_ref
+    m2, n2 = 70, 50
+    b = np.asfortranarray(np.random.default_rng(4).uniform(-1, 1, (m2, n2)) * (10.0 ** np.linspace(-4, 4, m2))[:, None])
+    want = O.dgeequ(b)
+    bb = np.array(b, order="C" if layout == ROW else "F", copy=True)
+    r, c = np.zeros(m2), np.zeros(n2)
+    rowcnd, colcnd, amax = C.c_double(0), C.c_double(0), C.c_double(0)
+    assert L.LAPACKE_dgeequ(layout, m2, n2, vp(bb), n2 if layout == ROW else m2, vp(r), vp(c), C.byref(rowcnd), C.byref(colcnd), C.byref(amax)) == 0
+    assert np.allclose(r, want[0], rtol=1e-15) and np.allclose(c, want[1], rtol=1e-15)
+    assert (rowcnd.value, colcnd.value, amax.value) == pytest.approx(want[2:5], rel=1e-15)
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_reference_lapacke_dgesvx_dgerfs_on_our_symbols(libs, layout):
+    L = _ref_lapacke(libs)
+    n, nrhs = 180, 2
+    a0, seed = O.random_matrix(n, n, SEED)
+    a0 *= (10.0 ** np.linspace(-4, 4, n))[:, None]
+    xact, _ = O.random_matrix(n, nrhs, seed)
+    b0 = np.asfortranarray(a0 @ xact)
+    order = "C" if layout == ROW else "F"
+    a, b = np.array(a0, order=order, copy=True), np.array(b0, order=order, copy=True)
+    af, x = np.zeros((n, n), order=order), np.zeros((n, nrhs), order=order)
+    ipiv, r, c = np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros(n)
+    ferr, berr, rpiv = np.zeros(nrhs), np.zeros(nrhs), np.zeros(1)
+    equed, rcond = C.create_string_buffer(b"N", 2), C.c_double(0.0)
+    ldb = nrhs if layout == ROW else n
+    L.LAPACKE_dgesvx.argtypes = [C.c_int, C.c_char, C.c_char, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]
+    info = L.LAPACKE_dgesvx(layout, b"E", b"N", n, nrhs, vp(a), n, vp(af), n, vp(ipiv), equed, vp(r), vp(c), vp(b), ldb, vp(x), ldb,
+                            C.byref(rcond), vp(ferr), vp(berr), vp(rpiv))
+    a2, b2 = a0.copy(order="F"), b0.copy(order="F")
+    af2, ipiv2, r2, c2 = np.zeros((n, n), order="F"), np.zeros(n, dtype=np.int32), np.zeros(n), np.zeros(n)
+    ref = O.dgesvx("E", "N", a2, af2, ipiv2, "N", r2, c2, b2)
+    assert info == ref["info"] == 0 and equed.value.decode()[:1] == ref["equed"]
+    assert np.array_equal(ipiv, ipiv2)
+    assert abs(rcond.value - ref["rcond"]) <= 1e-8 * ref["rcond"]
+    assert abs(rpiv[0] - ref["rpvgrw"]) <= 1e-11 * ref["rpvgrw"]
+    assert np.max(np.abs(x - xact)) / np.max(np.abs(xact)) <= max(1e-9, 2 * np.max(ferr))
+    assert np.all(berr <= 4 * 2.0 ** -53 * (n + 1))
+    # LAPACKE_dgerfs on the equilibrated system returned above.  The reference's row-major wrapper writes the scaled B back only for
+    # FACT = 'F' (lapacke_dgesvx_work.c:124-128), so the equilibrated right-hand side is formed here for both layouts.
+    b = np.array(b0 * r[:, None] if ref["equed"] in "RB" else b0, order=order, copy=True)
+    xs = x / c[:, None] if ref["equed"] in "CB" else x            # DGESVX returned x scaled back; refine in the equilibrated variables
+    x3 = np.array(xs * (1 + 1e-8), order=order, copy=True)
+    L.LAPACKE_dgerfs.argtypes = [C.c_int, C.c_char, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.LAPACKE_dgerfs(layout, b"N", n, nrhs, vp(a), n, vp(af), n, vp(ipiv), vp(b), ldb, vp(x3), ldb, vp(ferr), vp(berr)) == 0
+    assert np.max(np.abs(x3 - xs)) / np.max(np.abs(xs)) <= max(1e-9, 2 * np.max(ferr))
+    assert np.all(berr <= 4 * 2.0 ** -53 * (n + 1))
+
+
+@pytest.mark.parametrize("layout", [COL, ROW])
+def test_reference_lapacke_dgeqrt3_on_our_symbols(libs, layout):
+    L = _ref_lapacke(libs)
+    m, n = 150, 60
+    a, _ = O.random_matrix(m, n, SEED)
+    ref = a.copy(order="F")
+    t_ref, _ = O.dgeqrt(ref, n)
+    order = "C" if layout == ROW else "F"
+    buf, t = np.array(a, order=order, copy=True), np.zeros((n, n), order=order)
+    assert L.LAPACKE_dgeqrt3(layout, m, n, vp(buf), n if layout == ROW else m, vp(t), n) == 0
+    assert np.max(np.abs(buf - ref)) < 1e-11
+    assert np.max(np.abs(np.triu(t) - np.triu(t_ref[:n, :n]))) < 1e-11
