@@ -40,6 +40,8 @@ void lb200_set_getrf_cluster_max(int ctas);
 void lb200_set_getrf_big_leaf(int rows4);
 /* rows per CTA (1024 default / 2048 / 4096) of the leaf kernel for panels too tall for one cluster: fewer, fatter CTAs hold fewer SMs */
 void lb200_set_getrf_tall_rows(int rows_per_cta);
+/* 1: panels of 16385..32768 rows are factored by ONE thread-block cluster of <= 16 CTAs with 8 rows per thread (measured neutral: 852 vs 850 ms) */
+void lb200_set_getrf_cluster_fat(int on);
 /* batched 32x32 DGETRF: 0 (default) = one-shot kernel (one matrix per warp), 1 = persistent software-pipelined kernel (measured slower) */
 void lb200_set_batched_mode(int mode);
 void lb200_set_geqrf_cluster_max(int ctas);

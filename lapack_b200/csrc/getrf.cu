@@ -36,6 +36,8 @@ int getrf_block() { return min(g_nb, 2048); }
 void getrf_set_cluster_max(int c) { g_cluster_max = c < 0 ? 0 : (c > 16 ? 16 : c); }
 static int g_big_leaf_rows4 = 1;    // panels too tall for a cluster: 1 = 256 threads x 4 rows kernel, 0 = 1024 x 1 row kernel
 void getrf_set_big_leaf(int v) { g_big_leaf_rows4 = v ? 1 : 0; }
+static int g_cluster_fat = 0;       // 1: panels of 16385..32768 rows use ONE cluster of <= 16 CTAs with 8 rows per thread (2048 rows per CTA)
+void getrf_set_cluster_fat(int v) { g_cluster_fat = v ? 1 : 0; }
 static int g_tall_rows = 1024;      // rows per CTA of the global-packet leaf for panels too tall for one cluster: 1024 / 2048 / 4096
 void getrf_set_tall_rows(int r) { g_tall_rows = (r == 2048 || r == 4096) ? r : 1024; }
 void getrf_set_params(int nb, int leaf, int lookahead) {
@@ -682,6 +684,29 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
             LB_CUDA_CHECK(cudaGetLastError());
             return;
         }
+    }
+    if (g_cluster_fat && p.G > min(g_cluster_max, cluster_hw_max()) && ceil_div(m, 2048) <= min(g_cluster_max, cluster_hw_max())) {
+        // fat cluster leaf: 8 rows per thread, 2048 rows per CTA, DSMEM exchange -- half the SMs of the global-packet leaf
+        auto kern = getrf_leaf_cluster_kernel<LEAF_W, CL_THREADS, 8, true>;
+        static bool attr = false;
+        if (!attr) { (void)cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); (void)cudaGetLastError(); attr = true; }
+        p.G = ceil_div(m, 2048);
+        const bool outside = pc.width > n;
+        int nclusters = 1;
+        if (outside) nclusters += ceil_div(ceil_div(pc.width, CL_THREADS), p.G);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(p.G * nclusters));
+        cfg.blockDim = dim3(CL_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)p.G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        LB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
+        count_launch();
+        w.epoch += (unsigned)min(m, n);
+        return;
     }
     if (p.G <= g_cluster_max && p.G <= cluster_hw_max()) {
         // one cluster of G work CTAs (+ clusters of interchange CTAs when the panel is wider than the leaf)

@@ -17,6 +17,11 @@ def run(tag):
     print(f"{tag}: {best:.1f} ms  {(2*n**3/3)/best*1e-9:.2f} TFLOP/s", flush=True)
     return piv.clone()
 p0 = run("default")
+L.lb200_set_getrf_cluster_fat(1)
+p = run("cluster_fat (8 rows/thread, one 16-CTA cluster up to 32768 rows)")
+print("  ipiv equal:", bool((p == p0).all()))
+L.lb200_set_getrf_cluster_fat(0)
+if len(sys.argv) > 2: sys.exit(0)
 for rows in (2048, 4096):
     L.lb200_set_getrf_tall_rows(rows)
     p = run(f"tall_rows={rows}")
