@@ -61,6 +61,9 @@ void dgels_(const char* trans, const int* m, const int* n, const int* nrhs, doub
 /* SRC/dgeqrt.f:139 DGEQRT(M,N,NB,A,LDA,T,LDT,WORK,INFO); SRC/dgemqrt.f:166 DGEMQRT(SIDE,TRANS,M,N,K,NB,V,LDV,T,LDT,C,LDC,WORK,INFO) */
 void dgeqrt_(const int* m, const int* n, const int* nb, double* A, const int* lda, double* T, const int* ldt, double* work,
              int* info);
+/* SRC/dlatsqr.f:170 DLATSQR(M,N,MB,NB,A,LDA,T,LDT,WORK,LWORK,INFO) (LAPACKE/include/lapack.h dlatsqr_) */
+void dlatsqr_(const int* m, const int* n, const int* mb, const int* nb, double* A, const int* lda, double* T, const int* ldt,
+              double* work, const int* lwork, int* info);
 /* SRC/dgeqrt3.f:129 DGEQRT3(M,N,A,LDA,T,LDT,INFO) (LAPACKE/include/lapack.h dgeqrt3_) */
 void dgeqrt3_(const int* m, const int* n, double* A, const int* lda, double* T, const int* ldt, int* info);
 void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, const int* k, const int* nb, const double* V,

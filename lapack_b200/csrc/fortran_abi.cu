@@ -991,6 +991,36 @@ void dgeqrt3_(const int* m, const int* n, double* A, const int* lda, double* T, 
     if (r) *info = r;
 }
 
+// SRC/dlatsqr.f:170 DLATSQR(M,N,MB,NB,A,LDA,T,LDT,WORK,LWORK,INFO); WORK is not used (device scratch), WORK(1) = N*NB
+void dlatsqr_(const int* m, const int* n, const int* mb, const int* nb, double* A, const int* lda, double* T, const int* ldt,
+              double* work, const int* lwork, int* info) {
+    *info = 0;
+    const bool lquery = (*lwork == -1);
+    const int minmn = imin(*m, *n);
+    const int lwmin = (minmn == 0) ? 1 : *n * *nb;
+    if (*m < 0) *info = -1;
+    else if (*n < 0 || *m < *n) *info = -2;
+    else if (*mb < 1) *info = -3;
+    else if (*nb < 1 || (*nb > *n && *n > 0)) *info = -4;
+    else if (*lda < imax(1, *m)) *info = -6;
+    else if (*ldt < *nb) *info = -8;
+    else if (*lwork < lwmin && !lquery) *info = -10;
+    if (*info == 0 && ptr_kind(work) != PK_DEVICE) work[0] = (double)lwmin;
+    if (*info != 0) { call_xerbla("DLATSQR", -*info); return; }
+    if (lquery || minmn == 0) return;
+    if (!device_ok(info)) return;
+    std::lock_guard<std::mutex> lock(g_abi_mutex);
+    int tcols = *n;
+    if (!(*mb <= *n || *mb >= *m)) tcols = *n * ((*m - *n + (*mb - *n) - 1) / (*mb - *n));     // dlatsqr.f:100-104
+    Ctx c; c.scan({A, T});
+    lb::i64 la, lt;
+    double* dA = c.mat(A, *m, *n, *lda, true, true, &la);
+    double* dT = c.mat(T, *nb, tcols, *ldt, true, true, &lt);
+    lb::latsqr(c.s, *m, *n, *mb, *nb, dA, la, dT, lt);
+    int r = c.finish();
+    if (r) *info = r;
+}
+
 void dgemqrt_(const char* side, const char* trans, const int* m, const int* n, const int* k, const int* nb, const double* V,
               const int* ldv, const double* T, const int* ldt, double* C, const int* ldc, double* work, int* info, size_t, size_t) {
     (void)work;

@@ -1016,6 +1016,33 @@ void geqrt(cudaStream_t s, int m, int n, int nb, double* A, i64 lda, double* T, 
     ws_free(s, tau);
 }
 
+// DLATSQR (SRC/dlatsqr.f:185-290): tall-skinny QR by row blocks of MB rows.  After DGEQRT of the first block
+// every further block B (MB-N rows) is combined with the current R by DTPQRT(L = 0) -- the QR factorization of the stacked matrix
+// [R; B].  Because the rows of R below the diagonal are exactly zero, Householder QR of the stacked (N + rows) x N matrix produces
+// precisely DTPQRT's reflectors (v = [e_i; b_i], dtpqrt2.f:214-232), the same T blocks and the same updated R, so each step is
+// the blocked DGEQRT path of this file on a stacked scratch copy; R goes back to A(1:N,1:N), the reflector block to the rows of A,
+// the T blocks to T(1, CTR*N+1).
+void latsqr(cudaStream_t s, int m, int n, int mb, int nb, double* A, i64 lda, double* T, i64 ldt) {
+    if (min(m, n) <= 0) return;
+    if (mb <= n || mb >= m) { geqrt(s, m, n, nb, A, lda, T, ldt); return; }          // dlatsqr.f:252-255
+    const int kk = (m - n) % (mb - n), ii = m - kk;
+    geqrt(s, mb, n, nb, A, lda, T, ldt);                                             // dlatsqr.f:261
+    const i64 lds = ((i64)mb + 1) & ~1LL;
+    double* S = (double*)ws_alloc(s, sizeof(double) * (size_t)lds * n);
+    auto tp = [&](int i, int rows, int ctr) {
+        laset(s, 'A', n, n, 0.0, 0.0, S, lds);
+        lacpy(s, 'U', n, n, A, lda, S, lds);
+        lacpy(s, 'A', rows, n, A + i, lda, S + n, lds);
+        geqrt(s, n + rows, n, nb, S, lds, T + (i64)ctr * n * ldt, ldt);              // == DTPQRT(rows, N, 0, NB, ...)
+        lacpy(s, 'U', n, n, S, lds, A, lda);
+        lacpy(s, 'A', rows, n, S + n, lds, A + i, lda);
+    };
+    int ctr = 1;
+    for (int i = mb; i <= ii - mb + n; i += mb - n) tp(i, mb - n, ctr++);            // dlatsqr.f:264-269
+    if (ii < m) tp(ii, kk, ctr);                                                     // dlatsqr.f:273-277
+    ws_free(s, S);
+}
+
 void gemqrt(cudaStream_t s, char side, char trans, int m, int n, int k, int nb, const double* V, i64 ldv, const double* T,
             i64 ldt, double* C, i64 ldc) {
     if (m <= 0 || n <= 0 || k <= 0) return;

@@ -82,6 +82,7 @@ void larft_general(cudaStream_t s, bool backward, bool rowwise, int n, int k, co
 void larfb_general(cudaStream_t s, char side, char trans, bool backward, bool rowwise, int m, int n, int k, const double* V, i64 ldv,
                    const double* T, i64 ldt, double* C, i64 ldc);
 void geqrt(cudaStream_t s, int m, int n, int nb, double* A, i64 lda, double* T, i64 ldt);
+void latsqr(cudaStream_t s, int m, int n, int mb, int nb, double* A, i64 lda, double* T, i64 ldt);
 void gemqrt(cudaStream_t s, char side, char trans, int m, int n, int k, int nb, const double* V, i64 ldv, const double* T,
             i64 ldt, double* C, i64 ldc);
 void gelqf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau);

@@ -223,6 +223,12 @@ def dgeqrt(m, n, nb, a, lda, t, ldt, work):
     return info.value
 
 
+def dlatsqr(m, n, mb, nb, a, lda, t, ldt, work, lwork):
+    info = _i(0)
+    lib().dlatsqr_(_r(m), _r(n), _r(mb), _r(nb), _p(a), _r(lda), _p(t), _r(ldt), _p(work), _r(lwork), C.byref(info))
+    return info.value
+
+
 def dgeqrt3(m, n, a, lda, t, ldt):
     info = _i(0)
     lib().dgeqrt3_(_r(m), _r(n), _p(a), _r(lda), _p(t), _r(ldt), C.byref(info))

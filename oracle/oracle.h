@@ -102,6 +102,12 @@ void ora_dorml2(char side, char trans, int m, int n, int k, const double *a, int
                 double *work, int *info);
 void ora_dgels(char trans, int m, int n, int nrhs, double *a, int lda, double *b, int ldb, double *work, int lwork, int *info);
 void ora_dlacn2(int n, double *v, double *x, int *isgn, double *est, int *kase, int *isave);
+/* ---- tall-skinny QR, L = 0 forms of the triangular-pentagonal kernels ---- */
+void ora_dtpqrt2_l0(int m, int n, double *a, int lda, double *b, int ldb, double *t, int ldt);
+void ora_dtprfb_ltfc_l0(int m, int n, int k, const double *v, int ldv, const double *t, int ldt, double *a, int lda, double *b,
+                        int ldb, double *work, int ldwork);
+void ora_dtpqrt_l0(int m, int n, int nb, double *a, int lda, double *b, int ldb, double *t, int ldt, double *work, int *info);
+void ora_dlatsqr(int m, int n, int mb, int nb, double *a, int lda, double *t, int ldt, double *work, int *info);
 /* ---- condition estimation / expert driver ---- */
 void ora_dtrsv(char uplo, char trans, char diag, int n, const double *a, int lda, double *x);
 void ora_drscl(int n, double sa, double *x);

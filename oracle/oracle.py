@@ -278,6 +278,23 @@ def dgerfs(trans, a, af, ipiv, b, x):
     return ferr[:nrhs], berr[:nrhs], info.value
 
 
+def latsqr_tcols(m, n, mb):
+    """number of columns of DLATSQR's T array: N * ceil((M-N)/(MB-N)) (dlatsqr.f:100-104), N when a single DGEQRT is used"""
+    if mb <= n or mb >= m:
+        return max(1, n)
+    return n * (-(-(m - n) // (mb - n)))
+
+
+def dlatsqr(a, mb, nb):
+    """tall-skinny QR (SRC/dlatsqr.f); returns (t [nb x N*blocks], info)"""
+    m, n = a.shape
+    t = fmat(nb, latsqr_tcols(m, n, mb))
+    work = np.zeros(max(1, nb * n))
+    info = C.c_int(0)
+    lib().ora_dlatsqr(m, n, mb, nb, _d(a), _ld(a), _d(t), _ld(t), _d(work), C.byref(info))
+    return t, info.value
+
+
 def dlatrs(uplo, trans, diag, normin, a, x, cnorm):
     """SRC/dlatrs.f: x (1-D) := solution of op(A) x = scale*b; returns (scale, info); cnorm is in/out"""
     n = a.shape[0]

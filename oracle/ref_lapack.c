@@ -1611,3 +1611,82 @@ void ora_dgesvx(char fact, char trans, int n, int nrhs, double *a, int lda, doub
     work[0] = rpvgrw;
     if (*rcond < ora_dlamch('E')) *info = n + 1;
 }
+
+/* ======================================================================================================================
+ * Tall-skinny QR: DLATSQR and the triangular-pentagonal kernels it calls, restated for L = 0 -- the only
+ * value DLATSQR passes (dlatsqr.f:265-277): the pentagonal block B is then a plain M x N rectangle under the N x N triangle A.
+ * ====================================================================================================================== */
+#define B_(i, j) b[(size_t)(i) + (size_t)(j) * ldb]
+#define T_(i, j) t[(size_t)(i) + (size_t)(j) * ldt]
+
+/* SRC/dtpqrt2.f:214-300 with L = 0 */
+void ora_dtpqrt2_l0(int m, int n, double *a, int lda, double *b, int ldb, double *t, int ldt)
+{
+    if (n == 0 || m == 0) return;
+    for (int i = 0; i < n; ++i) {
+        /* generate H(i) to annihilate B(:,i) (dtpqrt2.f:221) */
+        ora_dlarfg(m + 1, &A_(i, i), &B_(0, i), 1, &T_(i, 0));
+        if (i < n - 1) {
+            for (int j = 0; j < n - i - 1; ++j) T_(j, n - 1) = A_(i, i + 1 + j);
+            ora_dgemv('T', m, n - i - 1, 1.0, &B_(0, i + 1), ldb, &B_(0, i), 1, 1.0, &T_(0, n - 1), 1);
+            double alpha = -T_(i, 0);
+            for (int j = 0; j < n - i - 1; ++j) A_(i, i + 1 + j) = A_(i, i + 1 + j) + alpha * T_(j, n - 1);
+            ora_dger(m, n - i - 1, alpha, &B_(0, i), 1, &T_(0, n - 1), 1, &B_(0, i + 1), ldb);
+        }
+    }
+    for (int i = 1; i < n; ++i) {
+        double alpha = -T_(i, 0);
+        for (int j = 0; j < i; ++j) T_(j, i) = 0.0;
+        /* P = 0: no triangular part of B2; the rectangular part of B2 has L = 0 rows: y := 0 (dtpqrt2.f:271-285) */
+        ora_dgemv('T', m, i, alpha, b, ldb, &B_(0, i), 1, 1.0, &T_(0, i), 1);                  /* B1 (dtpqrt2.f:289) */
+        ora_dtrmv('U', 'N', 'N', i, t, ldt, &T_(0, i), 1);                                     /* dtpqrt2.f:294 */
+        T_(i, i) = T_(i, 0);
+        T_(i, 0) = 0.0;
+    }
+}
+
+/* SRC/dtprfb.f:322-383 ('L','T','F','C') with L = 0: [A; B] := H^T [A; B], H = I - W T W^T, W = [I; V] */
+void ora_dtprfb_ltfc_l0(int m, int n, int k, const double *v, int ldv, const double *t, int ldt, double *a, int lda, double *b,
+                        int ldb, double *work, int ldwork)
+{
+    if (m <= 0 || n <= 0 || k <= 0) return;
+    ora_dgemm('T', 'N', k, n, m, 1.0, v, ldv, b, ldb, 0.0, work, ldwork);
+    for (int j = 0; j < n; ++j) for (int i = 0; i < k; ++i) work[i + (size_t)j * ldwork] += A_(i, j);
+    ora_dtrmm('L', 'U', 'T', 'N', k, n, 1.0, t, ldt, work, ldwork);
+    for (int j = 0; j < n; ++j) for (int i = 0; i < k; ++i) A_(i, j) -= work[i + (size_t)j * ldwork];
+    ora_dgemm('N', 'N', m, n, k, -1.0, v, ldv, work, ldwork, 1.0, b, ldb);
+}
+
+/* SRC/dtpqrt.f:200-270 with L = 0.  work: nb*n doubles */
+void ora_dtpqrt_l0(int m, int n, int nb, double *a, int lda, double *b, int ldb, double *t, int ldt, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0) *info = -2; else if (nb < 1 || (nb > n && n > 0)) *info = -4;
+    else if (lda < imax(1, n)) *info = -6; else if (ldb < imax(1, m)) *info = -8; else if (ldt < nb) *info = -10;
+    if (*info != 0 || m == 0 || n == 0) return;
+    for (int i = 0; i < n; i += nb) {
+        const int ib = imin(n - i, nb);
+        ora_dtpqrt2_l0(m, ib, &A_(i, i), lda, &B_(0, i), ldb, &T_(0, i), ldt);
+        if (i + ib < n)
+            ora_dtprfb_ltfc_l0(m, n - i - ib, ib, &B_(0, i), ldb, &T_(0, i), ldt, &A_(i, i + ib), lda, &B_(0, i + ib), ldb, work, ib);
+    }
+}
+
+/* SRC/dlatsqr.f:185-290.  t: nb x n*ceil((m-n)/(mb-n)) ; work: nb*n doubles */
+void ora_dlatsqr(int m, int n, int mb, int nb, double *a, int lda, double *t, int ldt, double *work, int *info)
+{
+    *info = 0;
+    if (m < 0) *info = -1; else if (n < 0 || m < n) *info = -2; else if (mb < 1) *info = -3;
+    else if (nb < 1 || (nb > n && n > 0)) *info = -4; else if (lda < imax(1, m)) *info = -6; else if (ldt < nb) *info = -8;
+    if (*info != 0) return;
+    if (imin(m, n) == 0) return;
+    if (mb <= n || mb >= m) { ora_dgeqrt(m, n, nb, a, lda, t, ldt, work, info); return; }
+    const int kk = (m - n) % (mb - n), ii = m - kk;                       /* ii: 0-based first row of the last block */
+    ora_dgeqrt(mb, n, nb, a, lda, t, ldt, work, info);
+    int ctr = 1;
+    for (int i = mb; i <= ii - mb + n; i += mb - n) {                    /* DO I = MB+1, II-MB+N, MB-N (1-based; II = ii+1) */
+        ora_dtpqrt_l0(mb - n, n, nb, a, lda, &A_(i, 0), lda, &T_(0, ctr * n), ldt, work, info);
+        ++ctr;
+    }
+    if (ii < m) ora_dtpqrt_l0(kk, n, nb, a, lda, &A_(ii, 0), lda, &T_(0, ctr * n), ldt, work, info);
+}

@@ -177,3 +177,33 @@ def test_dgeqrt3_vs_oracle(lb):
         assert np.max(np.abs(np.triu(t[:n]) - np.triu(t_ref[:n, :n]))) < 1e-11
         assert np.all(t[n] == 4.5e77) and np.all(t[:n][np.tril_indices(n, -1)] == 4.5e77)       # below the diagonal: not used
     assert lb.f77.dgeqrt3(3, 5, np.zeros((3, 5), order="F"), 3, np.zeros((5, 5), order="F"), 5) == -1   # M < N (dgeqrt3.f:162)
+
+
+def test_dlatsqr_vs_netlib_golden(lb):
+    """DLATSQR (SRC/dlatsqr.f:185-290): R, the reflector blocks and every T block against netlib's DLATSQR on the same DLARNV input;
+    Q^T A = R checked through the stored blocks for the largest case."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "netlib_golden_latsqr.npz"))
+    for k, (m, n, mb, nb) in enumerate(g["cases"]):
+        m, n, mb, nb = int(m), int(n), int(mb), int(nb)
+        a, _ = O.random_matrix(m, n, SEED)
+        tc = O.latsqr_tcols(m, n, mb)
+        t = np.zeros((nb, tc), order="F")
+        wq = np.zeros(1)
+        assert lb.f77.dlatsqr(m, n, mb, nb, a, m, t, nb, wq, -1) == 0 and wq[0] == n * nb          # workspace query (dlatsqr.f:213-217)
+        work = np.zeros(n * nb)
+        assert lb.f77.dlatsqr(m, n, mb, nb, a, m, t, nb, work, n * nb) == 0
+        ref_a, ref_t = g[f"a{k}"], g[f"t{k}"]
+        assert np.max(np.abs(a - ref_a)) < 1e-11 * max(1.0, np.max(np.abs(ref_a))), (m, n, mb, nb)
+        for g0 in range(0, tc, n):
+            for i in range(0, n, nb):
+                w = min(nb, n - i)
+                c0 = g0 + i
+                assert np.max(np.abs(np.triu(t[:w, c0:c0 + w]) - np.triu(ref_t[:w, c0:c0 + w]))) < 1e-11, (m, n, mb, nb, c0)
+    # error exits (dlatsqr.f:222-238)
+    a = np.zeros((10, 4), order="F"); t = np.zeros((2, 8), order="F"); w = np.zeros(8)
+    assert lb.f77.dlatsqr(3, 4, 6, 2, a, 10, t, 2, w, 8) == -2        # M < N
+    assert lb.f77.dlatsqr(10, 4, 0, 2, a, 10, t, 2, w, 8) == -3
+    assert lb.f77.dlatsqr(10, 4, 6, 5, a, 10, t, 5, w, 20) == -4      # NB > N
+    assert lb.f77.dlatsqr(10, 4, 6, 2, a, 9, t, 2, w, 8) == -6
+    assert lb.f77.dlatsqr(10, 4, 6, 2, a, 10, t, 1, w, 8) == -8
+    assert lb.f77.dlatsqr(10, 4, 6, 2, a, 10, t, 2, w, 7) == -10

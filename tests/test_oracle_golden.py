@@ -478,3 +478,21 @@ def test_dlaswp_long_lists_match_netlib(golden_large):
         O.dlaswp(a, k1, k2, g[f"swp{k}_ipiv"], incx)                    # SRC/dlaswp.f:138-183 (32-column strips + remainder)
         assert np.array_equal(a[:, 0], g[f"swp{k}_col0"])
         assert np.array_equal(a, a[:, :1] + np.arange(ncol)[None, :])
+
+
+# ------------------------------------------------------------------------------------------- DLATSQR
+def test_dlatsqr_matches_netlib():
+    """SRC/dlatsqr.f:185-290 with DTPQRT / DTPQRT2 / DTPRFB (L = 0): A (R and the reflector blocks) and every T block to rounding"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "netlib_golden_latsqr.npz"))
+    for k, (m, n, mb, nb) in enumerate(g["cases"]):
+        a, _ = O.random_matrix(int(m), int(n), (1988, 1989, 1990, 1991))
+        t, info = O.dlatsqr(a, int(mb), int(nb))
+        assert info == 0
+        assert np.max(np.abs(a - g[f"a{k}"])) < 1e-12 * max(1.0, np.max(np.abs(g[f"a{k}"])))
+        ref_t = g[f"t{k}"]
+        n, nb = int(n), int(nb)
+        for g0 in range(0, ref_t.shape[1], n):                         # one N-wide group of T blocks per row block (dlatsqr.f:100-104)
+            for i in range(0, n, nb):                                  # only the upper triangle of every IB x IB block is defined
+                w = min(nb, n - i)
+                c0 = g0 + i
+                assert np.max(np.abs(np.triu(t[:w, c0:c0 + w]) - np.triu(ref_t[:w, c0:c0 + w]))) < 1e-12
