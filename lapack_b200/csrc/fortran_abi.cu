@@ -104,6 +104,9 @@ std::mutex g_abi_mutex;     // one Fortran-ABI call at a time (the reference is 
 // this every cudaMemcpyAsync from it degrades to a synchronous staged copy.  LAPACK_B200_HOST_REGISTER=0 disables it.
 struct TempPin {
     void* base = nullptr;
+    // ONE registration for the whole matrix.  Measured (tools/hostreg_probe.py, 8 GiB, pages already touched): cudaHostRegister
+    // 179 ms + cudaHostUnregister 140 ms on one thread; splitting the range over 2 / 4 / 8 / 16 threads is SLOWER (532 / 225 / 851 /
+    // 1951 ms) and a 2-D copy that spans two registrations is rejected (cudaErrorInvalidValue), so the range is never split.
     TempPin(const void* p, size_t bytes, size_t min_bytes = (size_t)256 << 20) {
         static int enabled = -1;
         if (enabled < 0) { const char* e = getenv("LAPACK_B200_HOST_REGISTER"); enabled = (e && e[0] == '0') ? 0 : 1; }
