@@ -680,7 +680,9 @@ __global__ void col_scale_apply_kernel(int m, int n, double* __restrict__ A, i64
     }
 }
 
-static std::mutex g_qr_mutex;
+// one mutex for every driver that uses the look-ahead streams / events of lb::aux() (runtime.cu): concurrent host threads calling
+// different factorizations through the device API must not interleave their event joins
+static std::recursive_mutex& g_qr_mutex = driver_mutex();
 
 // C := (I - V T^T V^T) C for the m x nc block C, V/T given as clean copies  (dlarfb.f:248-304 as three GEMMs)
 static void apply_block_reflector(cudaStream_t s, int m, int nc, int k, const double* Vc, i64 ldvc, const double* T, i64 ldt,
@@ -778,12 +780,12 @@ static void geqrf_impl(cudaStream_t s, int m, int n, double* A, i64 lda, double*
 }
 
 void geqrf(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
-    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_qr_mutex);
     geqrf_impl(s, m, n, A, lda, tau, g_qr_nb, g_qr_lookahead != 0);
 }
 // DGEQR2: same factorization, panel-only code path (one recursive panel per 64 columns)
 void geqr2(cudaStream_t s, int m, int n, double* A, i64 lda, double* tau) {
-    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_qr_mutex);
     geqrf_impl(s, m, n, A, lda, tau, 64, false);
 }
 
@@ -1010,7 +1012,7 @@ void orgqr(cudaStream_t s, int m, int n, int k, double* A, i64 lda, const double
 void geqrt(cudaStream_t s, int m, int n, int nb, double* A, i64 lda, double* T, i64 ldt) {
     const int k = min(m, n);
     if (k <= 0) return;
-    std::lock_guard<std::mutex> lock(g_qr_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_qr_mutex);
     double* tau = (double*)ws_alloc(s, sizeof(double) * (size_t)k);
     geqrf_impl(s, m, n, A, lda, tau, nb, g_qr_lookahead != 0, T, ldt);
     ws_free(s, tau);

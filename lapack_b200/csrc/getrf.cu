@@ -772,10 +772,12 @@ static void getrf_panel(cudaStream_t s, int m, int n, double* A, i64 lda, int* i
     getrf_panel_rec(s, pc, 0, m, n, A, lda, ipiv, info, info_off);
 }
 
-static std::mutex g_lib_mutex;
+// one mutex for every driver that uses the look-ahead streams / events of lb::aux() (runtime.cu): concurrent host threads calling
+// different factorizations through the device API must not interleave their event joins
+static std::recursive_mutex& g_lib_mutex = driver_mutex();
 
 void getrf2(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
-    std::lock_guard<std::mutex> lock(g_lib_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_lib_mutex);
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     getrf_panel(s, m, n, A, lda, ipiv, info, 0);
 }
@@ -812,7 +814,7 @@ struct LuTrace {
 };
 
 void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
-    std::lock_guard<std::mutex> lock(g_lib_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_lib_mutex);
     static const bool trace_on = getenv("LB200_TRACE_LU") != nullptr;
     LuTrace trace;
     LuTrace* tr = trace_on ? &trace : nullptr;

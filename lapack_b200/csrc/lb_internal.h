@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #define LB_CUDA_CHECK(expr)                                                                       \
     do {                                                                                          \
@@ -132,6 +133,7 @@ struct Aux {
 Aux& aux();
 
 int num_sms();
+std::recursive_mutex& driver_mutex();    // serialises the drivers that share lb::aux()'s streams and events
 const int* kernel_guard();                 // see runtime.cu: device INFO word that disables queued Level-3 kernels once non-zero
 void set_kernel_guard(const int* p);
 

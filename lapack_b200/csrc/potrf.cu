@@ -89,7 +89,9 @@ static void potrf_rec(cudaStream_t s, bool upper, int n, double* A, i64 lda, int
     potrf_rec(s, upper, n2, A22, lda, info, info_off + n1);
 }
 
-static std::mutex g_po_mutex;
+// one mutex for every driver that uses the look-ahead streams / events of lb::aux() (runtime.cu): concurrent host threads calling
+// different factorizations through the device API must not interleave their event joins
+static std::recursive_mutex& g_po_mutex = driver_mutex();
 
 // every Level-3 kernel queued by the Cholesky drivers carries the INFO word as a guard (runtime.cu)
 struct GuardScope {
@@ -98,14 +100,14 @@ struct GuardScope {
 };
 
 void potrf2(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
-    std::lock_guard<std::mutex> lock(g_po_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_po_mutex);
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     GuardScope guard(info);
     potrf_rec(s, uplo == 'U' || uplo == 'u', n, A, lda, info, 0);
 }
 
 void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
-    std::lock_guard<std::mutex> lock(g_po_mutex);
+    std::lock_guard<std::recursive_mutex> lock(g_po_mutex);
     LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     if (n <= 0) return;
     GuardScope guard(info);

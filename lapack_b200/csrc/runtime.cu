@@ -36,6 +36,11 @@ static thread_local const int* g_kernel_guard = nullptr;   // per host thread: c
 const int* kernel_guard() { return g_kernel_guard; }
 void set_kernel_guard(const int* p) { g_kernel_guard = p; }
 
+std::recursive_mutex& driver_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
+
 StreamOut*& stream_out() {
     static StreamOut* so = nullptr;
     return so;
