@@ -119,6 +119,23 @@ def cpu_reference_sample(n, nrhs=1, keep=None):
     return t, flops_getrf(n) + flops_getrs(n, nrhs), info, err
 
 
+def cpu_reference_mix(n, nrhs=1):
+    """The SAME routine mix as the GPU step, on the oracle port: DPOTRF('L') + DPOTRS of the n x n SPD matrix, then DGETRF of the
+    n x n U(-1,1) matrix (SURVEY 8d inputs); returns (seconds, flops, infos)."""
+    import numpy as np
+    from oracle import oracle as O
+    s, seed = O.spd_matrix(n, SEED)
+    xact, _ = O.random_matrix(n, nrhs, seed)
+    b = np.asfortranarray(s @ xact)
+    a, _ = O.random_matrix(n, n, SEED)
+    t0 = time.perf_counter()
+    i1 = O.dpotrf("L", s)
+    O.dpotrs("L", s, b)
+    _, i2 = O.dgetrf(a)
+    t = time.perf_counter() - t0
+    return t, flops_potrf(n) + flops_potrs(n, nrhs) + flops_getrf(n), (i1, i2)
+
+
 def pick_cpu_sample(budget_s, steps):
     """Largest n in a fixed ladder whose estimated total time fits the budget (calibrated on n=768)."""
     t, fl, _, _ = cpu_reference_sample(768)
@@ -133,21 +150,30 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = args.steps + args.warmup
-    n = pick_cpu_sample(150.0, steps)
+    # same routine mix as the GPU arm's step (DPOTRF + DPOTRS + DGETRF), at the largest order of a fixed ladder that fits ~150 s
+    t, fl, _ = cpu_reference_mix(768)
+    rate = fl / t
+    n = 1024
+    for cand in (4096, 3072, 2048, 1536, 1024):
+        if ((flops_potrf(cand) + flops_getrf(cand)) / rate) * steps <= 150.0:
+            n = cand
+            break
     ts = []
-    fl = 0.0
     for i in range(steps):
-        t, fl, info, err = cpu_reference_sample(n)
+        t, fl, infos = cpu_reference_mix(n)
+        assert infos == (0, 0), infos
         if i >= args.warmup:
             ts.append(t)
     tmean = sum(ts) / len(ts)
     val = fl / tmean * 1e-12
-    sample = f"DGESV n={n} nrhs=1: reference DGETRF (NB=64, recursive DGETRF2 panel) + DGETRS on reference BLAS loops (oracle port), 1 thread"
+    sample = (f"DPOTRF('L')+DPOTRS(1 rhs)+DGETRF at n={n} (the GPU arm's routine mix at a bounded order; its n={args.n} would take hours): "
+              "reference blocked algorithms (NB=64, recursive panels) on reference BLAS loops (oracle port), 1 thread -- the reference "
+              "has no threading on this path")
     line = {
         "impl": "reference", "metric": "DGETRF/DPOTRF FP64 TFLOP/s", "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tmean * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"bounded CPU sample of the n={args.n} factorization workload: " + sample},
+        "config": {"workload": "bounded CPU sample of the GPU arm's step: " + sample, "n": n},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
