@@ -44,6 +44,8 @@ void lb200_set_getrf_tall_rows(int rows_per_cta);
 void lb200_set_getrf_cluster_fat(int on);
 /* batched 32x32 DGETRF: 0 (default) = one-shot kernel (one matrix per warp), 1 = persistent software-pipelined kernel (measured slower) */
 void lb200_set_batched_mode(int mode);
+/* DLASWP apply kernel: 1 = scattered row reads as 16-byte cp.async.bulk copies instead of LDG (experiment) */
+void lb200_set_laswp_bulk(int on);
 void lb200_set_geqrf_cluster_max(int ctas);
 void lb200_set_potrf_params(int nb, int lookahead);
 void lb200_set_geqrf_params(int nb, int lookahead);

@@ -53,6 +53,7 @@ def _declare(L):
     L.lb200_set_getrf_tall_rows.argtypes = [i]
     L.lb200_set_getrf_cluster_fat.argtypes = [i]
     L.lb200_set_batched_mode.argtypes = [i]
+    L.lb200_set_laswp_bulk.argtypes = [i]
     L.lb200_set_geqrf_cluster_max.argtypes = [i]
     L.lb200_set_potrf_params.argtypes = [i, i]
     L.lb200_set_geqrf_params.argtypes = [i, i]

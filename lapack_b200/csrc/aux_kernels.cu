@@ -1,6 +1,7 @@
 // aux_kernels.cu -- memory-bound helper kernels: row interchanges (DLASWP), copies, transposes,
 // the DLARNV/DLARUV generator with jump-ahead, and small integer fix-ups for IPIV/INFO.
 #include "lb_internal.h"
+#include <cstdint>
 
 namespace lb {
 
@@ -187,6 +188,79 @@ __global__ void __launch_bounds__(256) laswp_apply_kernel(int n, double* __restr
     }
 }
 
+// Variant with the SCATTERED reads issued as 16-byte bulk copies (cp.async.bulk, SASS UBLKCP: the TMA engine's linear mode) into a
+// shared-memory stage, completion counted on one mbarrier.  Motivation (profiles/r02_laswp_ncu.txt): an LDG that misses L2 on an
+// LDA-strided row is filled as a full 128-byte line, 16x the 8 useful bytes; the bulk-copy path fetches the 16-byte pair it asks for.
+// Needs 16-byte aligned pairs: A 16-byte aligned and lda even (else the LDG kernel above is used).
+__device__ __forceinline__ unsigned swp_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(256) laswp_apply_bulk_kernel(int n, double* __restrict__ A, i64 lda, const SwapPlan* __restrict__ pl, int cw) {
+    extern __shared__ __align__(16) double sval[];         // [cw][np] 16-byte slots (group 1), then [cw][nout] doubles (group 2)
+    __shared__ __align__(8) unsigned long long mbar;
+    const int np = pl->np, nout = pl->nout, k1 = pl->k1;
+    if (pl->nmoved == 0 && nout == 0) return;
+    const int* __restrict__ srcA = pl->data;
+    const int2* __restrict__ pairs = reinterpret_cast<const int2*>(pl->data + np + (np & 1));
+    const int c0 = blockIdx.x * cw;
+    const int nc = min(cw, n - c0);
+    double* Ac = A + (i64)c0 * lda;
+    double2* s1 = reinterpret_cast<double2*>(sval);
+    double* s2 = sval + (size_t)2 * np * cw;
+    const unsigned bar = swp_smem_u32(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)pl->nmoved * (unsigned)nc * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+    }
+    // group 1: block row k1-1+q <- row srcA[q]; one 16-byte bulk copy of the aligned row pair per (move, column)
+    for (int q = threadIdx.x; q < np; q += 256) {
+        const int src = srcA[q];
+        if (src != k1 - 1 + q) {
+            const double* g = Ac + (src & ~1);
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) {
+                const unsigned dst = swp_smem_u32(s1 + (size_t)c * np + q);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 16, [%2];\n"
+                             ::"r"(dst), "l"(g + (i64)c * lda), "r"(bar) : "memory");
+            }
+        }
+    }
+    // group 2: outside row <- (mostly) block row: sources contiguous, plain loads
+    for (int q = threadIdx.x; q < nout; q += 256) {
+        const int src = pairs[q].y;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) s2[(size_t)c * nout + q] = Ac[(i64)c * lda + src];
+    }
+    {   // wait for the bulk copies (phase 0)
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(bar), "r"(0) : "memory");
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < np; q += 256) {
+        const int src = srcA[q], dst = k1 - 1 + q;
+        if (src != dst) {
+#pragma unroll 4
+            for (int c = 0; c < nc; ++c) {
+                const double2 v = s1[(size_t)c * np + q];
+                Ac[(i64)c * lda + dst] = (src & 1) ? v.y : v.x;
+            }
+        }
+    }
+    for (int q = threadIdx.x; q < nout; q += 256) {
+        const int dst = pairs[q].x;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) Ac[(i64)c * lda + dst] = s2[(size_t)c * nout + q];
+    }
+}
+static int g_laswp_bulk = 0;     // 1: scattered reads through cp.async.bulk (experiment knob, lb200_set_laswp_bulk)
+void laswp_set_bulk(int on) { g_laswp_bulk = on; }
+
 static size_t swap_plan_bytes(int np) { return sizeof(SwapPlan) + sizeof(int) * ((size_t)np + 1 + 4 * (size_t)np + 2); }
 static void laswp_attr() {
     static bool attr = false;
@@ -212,6 +286,18 @@ static void swap_plan_apply(cudaStream_t s, int n, double* A, i64 lda, const Swa
     int cw = (int)((size_t)(2 * LASWP_MAX_PIV * 4) / (size_t)(2 * npiv));
     cw = max(1, min(8, cw));
     while (cw > 1 && ceil_div(n, cw) < 2 * num_sms()) cw >>= 1;
+    if (g_laswp_bulk && (lda & 1) == 0 && (((uintptr_t)A) & 15) == 0) {
+        // 16-byte slots for group 1 + 8-byte slots for group 2: (2 np + np) * cw doubles
+        int cwb = max(1, min(cw, (int)((size_t)(2 * LASWP_MAX_PIV * 4) / (size_t)(3 * npiv))));
+        static bool attr = false;
+        if (!attr) {
+            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAX_PIV * 4 * 8));
+            attr = true;
+        }
+        laswp_apply_bulk_kernel<<<ceil_div(n, cwb), 256, (size_t)3 * npiv * cwb * sizeof(double), s>>>(n, A, lda, pl, cwb);
+        count_launch();
+        return;
+    }
     laswp_apply_kernel<<<ceil_div(n, cw), 256, (size_t)2 * npiv * cw * sizeof(double), s>>>(n, A, lda, pl, cw);
     count_launch();
 }

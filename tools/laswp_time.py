@@ -4,6 +4,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import lapack_b200 as lb
+if os.environ.get('BULK'): lb.lib().lb200_set_laswp_bulk(int(os.environ['BULK']))
 if os.environ.get('L2G'): print('L2 fetch granularity ->', os.environ['L2G'], lb.lib().lb200_set_l2_fetch_granularity(int(os.environ['L2G'])))
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
