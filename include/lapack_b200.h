@@ -31,6 +31,7 @@ void lb200_profile_gemm(int enable);
 void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* launches);
 
 /* tuning knobs (testing / benchmarking; defaults are chosen per problem size) */
+void lb200_set_gemm_splitk_balance(int on);   /* 1 (default): long-K GEMMs whose tile count leaves a partly filled last wave are split along K */
 void lb200_set_gemm_config(int cfg);   /* -1 auto, 0/1/2 force a cp.async tile shape, 3 force the TMA kernel */
 void lb200_set_gemm_tma(int on);       /* 0 disables the TMA fast path (falls back to cp.async) */
 void lb200_set_getrf_params(int nb, int leaf, int lookahead);
@@ -42,6 +43,8 @@ void lb200_set_getrf_big_leaf(int rows4);
 void lb200_set_getrf_tall_rows(int rows_per_cta);
 /* 1: panels of 16385..32768 rows are factored by ONE thread-block cluster of <= 16 CTAs with 8 rows per thread (measured neutral: 852 vs 850 ms) */
 void lb200_set_getrf_cluster_fat(int on);
+/* thin LU leaves for panels taller than min_rows: 0 = off, 1 = 128 threads x 2 rows per CTA, 2 = 64 threads x 4 rows (one GEMM-CTA slot each) */
+void lb200_set_getrf_thin(int mode, int min_rows);
 /* batched 32x32 DGETRF: 0 (default) = one-shot kernel (one matrix per warp), 1 = persistent software-pipelined kernel (measured slower) */
 void lb200_set_batched_mode(int mode);
 /* DLASWP apply kernel: 1 = scattered row reads as 16-byte cp.async.bulk copies instead of LDG (experiment) */

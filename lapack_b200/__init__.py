@@ -47,11 +47,13 @@ def _declare(L):
     L.lb200_fp64_peak_tflops.restype = d
     L.lb200_fp64_peak_tflops.argtypes = [VP, i, i, i, i]
     L.lb200_set_gemm_config.argtypes = [i]
+    L.lb200_set_gemm_splitk_balance.argtypes = [i]
     L.lb200_set_getrf_params.argtypes = [i, i, i]
     L.lb200_set_getrf_cluster_max.argtypes = [i]
     L.lb200_set_getrf_big_leaf.argtypes = [i]
     L.lb200_set_getrf_tall_rows.argtypes = [i]
     L.lb200_set_getrf_cluster_fat.argtypes = [i]
+    L.lb200_set_getrf_thin.argtypes = [i, i]
     L.lb200_set_batched_mode.argtypes = [i]
     L.lb200_set_laswp_bulk.argtypes = [i]
     L.lb200_set_geqrf_cluster_max.argtypes = [i]

@@ -9,6 +9,7 @@
 namespace lb {
 double fp64_peak(cudaStream_t s, int kind, int warps_per_cta, int ctas_per_sm, int iters);
 void gemm_set_config(int cfg);
+void gemm_set_splitk_balance(int on);
 void gemm_set_tma(int on);
 void gemm_profile(int enable);
 void gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
@@ -17,6 +18,7 @@ void getrf_set_cluster_max(int c);
 void getrf_set_big_leaf(int v);
 void getrf_set_tall_rows(int r);
 void getrf_set_cluster_fat(int v);
+void getrf_set_thin(int mode, int min_rows);
 void batched_set_mode(int m);
 void laswp_set_bulk(int on);
 void geqrf_set_cluster_max(int c);
@@ -44,6 +46,7 @@ double lb200_fp64_peak_tflops(void* stream, int kind, int warps_per_cta, int cta
     return lb::fp64_peak(S(stream), kind, warps_per_cta, ctas_per_sm, iters);
 }
 void lb200_set_gemm_config(int cfg) { lb::gemm_set_config(cfg); }
+void lb200_set_gemm_splitk_balance(int on) { lb::gemm_set_splitk_balance(on); }
 void lb200_set_gemm_tma(int on) { lb::gemm_set_tma(on); }
 void lb200_profile_gemm(int enable) { lb::gemm_profile(enable); }
 void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* launches) {
@@ -55,6 +58,7 @@ void lb200_set_getrf_cluster_max(int ctas) { lb::getrf_set_cluster_max(ctas); }
 void lb200_set_getrf_big_leaf(int rows4) { lb::getrf_set_big_leaf(rows4); }
 void lb200_set_getrf_tall_rows(int rows_per_cta) { lb::getrf_set_tall_rows(rows_per_cta); }
 void lb200_set_getrf_cluster_fat(int on) { lb::getrf_set_cluster_fat(on); }
+void lb200_set_getrf_thin(int mode, int min_rows) { lb::getrf_set_thin(mode, min_rows); }
 void lb200_set_batched_mode(int mode) { lb::batched_set_mode(mode); }
 void lb200_set_laswp_bulk(int on) { lb::laswp_set_bulk(on); }
 void lb200_set_geqrf_cluster_max(int ctas) { lb::geqrf_set_cluster_max(ctas); }

@@ -122,7 +122,40 @@ struct TileLoader {
     }
 };
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, bool AL16, int STAGES, int BK = 16>
+// Loader for INTERIOR tiles (no M/N/K edge, 16-byte aligned operands): the chunks of one thread are a fixed stride apart in global and
+// in shared memory, so a k-tile costs N LDGSTS + N pointer additions and no predicates (the general loader above spends ~150 integer
+// instructions per k-tile on clamping).
+template <int EXT, bool KMAJ, int NTHREADS, int BK = 16>
+struct LeanLoader {
+    static constexpr int N = (EXT * BK / 2) / NTHREADS;
+    static constexpr int PER = KMAJ ? NTHREADS / (BK / 2) : NTHREADS / (EXT / 2);        // e (KMAJ) or k (MN-major) distance between chunks
+    static constexpr int SSTRIDE = KMAJ ? PER * (BK + PAD) : PER * (EXT + PAD);           // shared distance (doubles)
+    static_assert(KMAJ ? (NTHREADS % (BK / 2) == 0) : (NTHREADS % (EXT / 2) == 0), "lean loader: thread count");
+    const double* g;       // chunk 0 of the next k-tile
+    i64 gstride, kstep;
+    int s0;
+    __device__ __forceinline__ void init(const double* __restrict__ gbase, i64 ld, int e0, int tid) {
+        int e, k;
+        if (KMAJ) { e = tid / (BK / 2); k = 2 * (tid % (BK / 2)); }
+        else { k = tid / (EXT / 2); e = 2 * (tid % (EXT / 2)); }
+        s0 = KMAJ ? e * (BK + PAD) + k : k * (EXT + PAD) + e;
+        g = KMAJ ? gbase + (i64)(e0 + e) * ld + k : gbase + (i64)k * ld + (e0 + e);
+        gstride = (i64)PER * ld;
+        kstep = KMAJ ? (i64)BK : (i64)BK * ld;
+    }
+    __device__ __forceinline__ void issue(double* sm) {
+        const double* q = g;
+        double* d = sm + s0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            cp_async16(d + i * SSTRIDE, q, 16);
+            q += gstride;
+        }
+        g += kstep;
+    }
+};
+
+template <int BM, int BN, int WARPS_M, int WARPS_N, bool A_KMAJ, bool B_KMAJ, bool AL16, int STAGES, int BK = 16, int VAR = 0>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
                                   ((BM / WARPS_M) * (BN / WARPS_N) <= 1024) ? (512 / (WARPS_M * WARPS_N * 32) > 0 ? 512 / (WARPS_M * WARPS_N * 32) : 1)
                                                                             : ((WARPS_M * WARPS_N <= 4) ? 2 : 1))
@@ -182,6 +215,56 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
         for (int b = 0; b < NT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
     const int KT = (p.K + BK - 1) / BK;
+    // fragment offsets inside a stage (k added per step)
+    int aoff[MT], boff[NT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a) aoff[a] = LA::off(warp_m * WM + a * 8 + g4, t4);
+#pragma unroll
+    for (int b = 0; b < NT; ++b) boff[b] = LB::off(warp_n * WN + b * 8 + g4, t4);
+    constexpr int AKS = A_KMAJ ? 1 : (BM + PAD);     // shared stride of one k step
+    constexpr int BKS = B_KMAJ ? 1 : (BN + PAD);
+    auto compute = [&](const double* sa, const double* sb) {
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            double af[MT], bf[NT];
+#pragma unroll
+            for (int a = 0; a < MT; ++a) af[a] = sa[aoff[a] + kk * AKS];
+#pragma unroll
+            for (int b = 0; b < NT; ++b) bf[b] = sb[boff[b] + kk * BKS];
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) dmma884(acc[a][b][0], acc[a][b][1], bf[b], af[a]);
+        }
+    };
+
+    const bool lean = (VAR == 1) && AL16 && (m0 + BM <= p.M) && (n0 + BN <= p.N) && (p.K % BK == 0) && (KT >= STAGES);
+    if (lean) {
+        LeanLoader<BM, A_KMAJ, NTHREADS, BK> la;
+        LeanLoader<BN, B_KMAJ, NTHREADS, BK> lb_;
+        la.init(p.A, p.lda, m0, tid);
+        lb_.init(p.B, p.ldb, n0, tid);
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            la.issue(smem + s * STAGE_ELEMS);
+            lb_.issue(smem + s * STAGE_ELEMS + LA::ELEMS);
+            cp_async_commit();
+        }
+        int st_c = 0, st_l = STAGES - 1;             // stage computed / stage loaded next
+        for (int kt = 0; kt < KT; ++kt) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            if (kt + STAGES - 1 < KT) {
+                la.issue(smem + st_l * STAGE_ELEMS);
+                lb_.issue(smem + st_l * STAGE_ELEMS + LA::ELEMS);
+            }
+            cp_async_commit();
+            const double* sa = smem + st_c * STAGE_ELEMS;
+            compute(sa, sa + LA::ELEMS);
+            st_c = (st_c + 1 == STAGES) ? 0 : st_c + 1;
+            st_l = (st_l + 1 == STAGES) ? 0 : st_l + 1;
+        }
+    } else {
     TileLoader<BM, A_KMAJ, AL16, NTHREADS, BK> ldA;
     TileLoader<BN, B_KMAJ, AL16, NTHREADS, BK> ldB;
     ldA.init(p.A, p.lda, m0, p.M, tid);
@@ -199,33 +282,13 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) issue(s);
 
-    // fragment offsets inside a stage (k added per step)
-    int aoff[MT], boff[NT];
-#pragma unroll
-    for (int a = 0; a < MT; ++a) aoff[a] = LA::off(warp_m * WM + a * 8 + g4, t4);
-#pragma unroll
-    for (int b = 0; b < NT; ++b) boff[b] = LB::off(warp_n * WN + b * 8 + g4, t4);
-    constexpr int AKS = A_KMAJ ? 1 : (BM + PAD);     // shared stride of one k step
-    constexpr int BKS = B_KMAJ ? 1 : (BN + PAD);
-
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         issue(kt + STAGES - 1);
         const double* sa = smem + (kt % STAGES) * STAGE_ELEMS;
-        const double* sb = sa + LA::ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[MT], bf[NT];
-#pragma unroll
-            for (int a = 0; a < MT; ++a) af[a] = sa[aoff[a] + kk * AKS];
-#pragma unroll
-            for (int b = 0; b < NT; ++b) bf[b] = sb[boff[b] + kk * BKS];
-#pragma unroll
-            for (int a = 0; a < MT; ++a)
-#pragma unroll
-                for (int b = 0; b < NT; ++b) dmma884(acc[a][b][0], acc[a][b][1], bf[b], af[a]);
-        }
+        compute(sa, sa + LA::ELEMS);
+    }
     }
     cp_async_wait<0>();
 
@@ -313,9 +376,11 @@ __global__ void splitk_reduce_kernel(int m, int n, int nz, double alpha, double 
     }
 }
 
+static int g_splitk_balance = 1;   // wave-balancing split-K of long-K GEMMs (lb200_set_gemm_splitk_balance)
+void gemm_set_splitk_balance(int on) { g_splitk_balance = on; }
 static int g_gemm_cfg = -1;   // -1 auto, 0 = 128x128x8w, 1 = 128x64x4w, 2 = 64x64 (2 warps)
 
-template <int BM, int BN, int WMW, int WNW, int STAGES, int BKT = 16>
+template <int BM, int BN, int WMW, int WNW, int STAGES, int BKT = 16, int VAR = 0>
 static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const GemmParams& p0) {
     GemmParams p = p0;
     p.tiles_m = ceil_div(p.M, BM);
@@ -325,7 +390,7 @@ static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const Gemm
     dim3 grid((unsigned)((i64)p.tiles_m * p.tiles_n), (unsigned)ceil_div(p.K, p.kchunk));
 #define LB_LAUNCH(AK, BKM, AL)                                                                                  \
     {                                                                                                           \
-        auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES, BKT>;                             \
+        auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES, BKT, VAR>;                             \
         smem = sizeof(double) * STAGES * (TileLayout<BM, AK, BKT>::ELEMS + TileLayout<BN, BKM, BKT>::ELEMS);     \
         static bool attr_set = false;                                                                           \
         if (!attr_set) {                                                                                        \
@@ -442,19 +507,50 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
             }
         }
     }
+    // Long-K products with few output tiles per wave (W = V^T C of DLARFB: 8 tile rows, K = panel height): the launch is a handful
+    // of waves of 4 x #SMs CTAs and the last, partly filled wave costs up to 15%.  Split K so that the CTA count fills whole waves;
+    // slices are summed in a fixed order (deterministic).  K = NB updates of LU / Cholesky never take this path (k >= 2048).
+    if (g_splitk_balance && k >= 2048 && cfg < 0) {
+        const i64 t64 = (i64)ceil_div(m, 64) * ceil_div(n, 64);
+        const i64 slots = 4 * (i64)num_sms();
+        auto eff = [&](int z) {
+            const i64 tot = t64 * z, wv = (tot + slots - 1) / slots;
+            return (double)tot / (double)(wv * slots) - 0.004 * (z - 1);
+        };
+        int best = 1;
+        double be = eff(1);
+        if (be < 0.95 && t64 <= 16 * slots)
+            for (int z = 2; z <= min(8, k / 512); ++z)
+                if (eff(z) > be + 0.01) { best = z; be = eff(z); }
+        if (best > 1) {
+            int kchunk = ceil_div(ceil_div(k, best), BK) * BK;
+            const int nz = ceil_div(k, kchunk);
+            double* P = (double*)ws_alloc(s, sizeof(double) * (size_t)m * n * nz);
+            GemmParams q = p;
+            q.alpha = 1.0; q.beta = 0.0; q.C = P; q.ldc = m; q.tri = 0;
+            q.kchunk = kchunk; q.c_zstride = (i64)m * n;
+            launch_cfg<64, 64, 2, 2, 2, 16, 1>(s, a_k, b_k, al16, q);
+            dim3 rgrid(ceil_div(m, 128), (unsigned)min(n, 4096));
+            splitk_reduce_kernel<<<rgrid, 128, 0, s>>>(m, n, nz, alpha, beta, P, C, ldc, tri);
+            count_launch();
+            ws_free(s, P);
+            return;
+        }
+    }
     if (cfg == 3) {
         // persistent warp-specialised TMA kernel (gemm_tma.cu): one CTA per SM for the whole GEMM, so it must not
         // be used while a look-ahead panel needs SMs; measured 31.3 TFLOP/s at K=512 vs 33.6 for the default below.
         if (k >= 32 && gemm_tma_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri)) return;
         cfg = -1;
     }
-    // default: 64x64 tiles, 4 warps of 32x32, 2-stage cp.async ring, 4 CTAs per SM (measured best on B200:
-    // 33.6 TFLOP/s = 90% of the DMMA peak at K=512; profiles/r01_gemm_config_sweep.txt)
+    // default: 64x64 tiles, 4 warps of 32x32, 2-stage cp.async ring, 4 CTAs per SM, interior tiles through the lean loader
+    // (measured on B200: 34.8 TFLOP/s at K=512, 35.6 at 8192^3, against 33.8 / 34.4 for the general loader alone -- cfg 8 -- and
+    // 34.9 / 35.5 for cuBLAS; profiles/r02_gemm_lean_ab.txt)
     if (cfg == 12) {   // 64x64 TMA-fed kernel (same tile shape as cfg 8, operands moved by cp.async.bulk.tensor)
         if (k >= 16 && gemm_tma64_try(s, a_k, b_k, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, tri)) return;
         cfg = -1;
     }
-    if (cfg < 0) cfg = 8;
+    if (cfg < 0) cfg = 13;
     if (cfg == 4) launch_cfg<128, 64, 4, 2, 3>(s, a_k, b_k, al16, p);          // 8 warps of 32x32, 2 CTAs/SM
     else if (cfg == 5) launch_cfg<128, 128, 4, 4, 4>(s, a_k, b_k, al16, p);     // 16 warps of 32x32, 1 CTA/SM
     else if (cfg == 6) launch_cfg<64, 64, 2, 2, 4>(s, a_k, b_k, al16, p);       // 4 warps of 32x32, 2 CTAs/SM (smem)
@@ -463,6 +559,8 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
     else if (cfg == 9) launch_cfg<64, 64, 2, 2, 3, 32>(s, a_k, b_k, al16, p);   // BK=32
     else if (cfg == 10) launch_cfg<64, 128, 2, 2, 3>(s, a_k, b_k, al16, p);     // 4 warps of 32x64
     else if (cfg == 11) launch_cfg<128, 64, 2, 2, 3, 32>(s, a_k, b_k, al16, p); // cfg1 with BK=32
+    else if (cfg == 13) launch_cfg<64, 64, 2, 2, 2, 16, 1>(s, a_k, b_k, al16, p);   // cfg 8 + lean interior loader
+    else if (cfg == 14) launch_cfg<64, 64, 2, 2, 3, 16, 1>(s, a_k, b_k, al16, p);   // same with 3 stages (3 CTAs/SM)
     else if (cfg == 0) launch_cfg<128, 128, 2, 4, 4>(s, a_k, b_k, al16, p);
     else if (cfg == 1) launch_cfg<128, 64, 2, 2, 3>(s, a_k, b_k, al16, p);
     else launch_cfg<64, 64, 1, 2, 4>(s, a_k, b_k, al16, p);

@@ -40,6 +40,10 @@ static int g_cluster_fat = 0;       // 1: panels of 16385..32768 rows use ONE cl
 void getrf_set_cluster_fat(int v) { g_cluster_fat = v ? 1 : 0; }
 static int g_tall_rows = 1024;      // rows per CTA of the global-packet leaf for panels too tall for one cluster: 1024 / 2048 / 4096
 void getrf_set_tall_rows(int r) { g_tall_rows = (r == 2048 || r == 4096) ? r : 1024; }
+// Thin leaves (see getrf_leaf_cluster_kernel, MINB): 0 = off, 1 = 128 threads x 2 rows, 2 = 64 threads x 4 rows (256 rows per CTA either
+// way, one GEMM-CTA slot each); used for panels of more than g_thin_min_rows rows, i.e. while the panel is hidden behind the update.
+static int g_thin_mode = 0, g_thin_min_rows = 16384;
+void getrf_set_thin(int mode, int min_rows) { g_thin_mode = mode; if (min_rows >= 0) g_thin_min_rows = min_rows; }
 void getrf_set_params(int nb, int leaf, int lookahead) {
     (void)leaf;
     if (nb > 0) g_nb = nb;
@@ -328,8 +332,11 @@ __device__ __forceinline__ void warp_argmax(double& key, int& krow) {
 // R rows per thread (row = g*R*THREADS + r*THREADS + tid): the per-step bookkeeping (reductions, barriers, the
 // pull of the pivot row) is paid once per thread, so few fat threads beat many thin ones -- the kernel is bound
 // by instruction issue, not by latency.
-template <int W, int THREADS, int R, bool CLUSTER>
-__global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafParams p) {
+// MINB > 1 ("thin" leaves): the CTA is sized to fit into the resources ONE trailing-update GEMM CTA gives back (128 threads x 128
+// registers, or 64 x 255), so a look-ahead panel launched next to a running update is placed as GEMM CTAs retire instead of waiting
+// for whole SMs to drain (the block scheduler holds back every lower-priority CTA while a higher-priority one is pending).
+template <int W, int THREADS, int R, bool CLUSTER, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) getrf_leaf_cluster_kernel(LeafParams p) {
     constexpr int NWARP = THREADS / 32;
     constexpr int ROWS = THREADS * R;
     __shared__ double s_key[NWARP];
@@ -489,12 +496,32 @@ __global__ void __launch_bounds__(THREADS, 1) getrf_leaf_cluster_kernel(LeafPara
         if (warp == 0) {
             double k2 = -3.0;
             int r2 = 0x7fffffff, g2 = 0;
-            for (int q = lane; q < p.G; q += 32) {
-                const LeafPacket* cp = p.cand + slot * p.G + q;
-                unsigned long long tag = poll_tag(&cp->tag, epoch);
-                double ck = __ldcg(&cp->key);
-                int cr = (int)(unsigned)(tag & 0xffffffffu);
-                if (cand_better(ck, cr, k2, r2)) { k2 = ck; r2 = cr; g2 = q; }
+            // up to four packets per lane are polled together (their loads overlap): thin leaves have up to 256 work CTAs
+            for (int q0 = 0; q0 < p.G; q0 += 128) {
+                unsigned long long tg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + lane + 32 * i;
+                    tg[i] = (q < p.G) ? ld_acquire_u64(&p.cand[slot * p.G + q].tag) : 0ull;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + lane + 32 * i;
+                    if (q < p.G)
+                        while ((unsigned)(tg[i] >> 32) != epoch) tg[i] = ld_acquire_u64(&p.cand[slot * p.G + q].tag);
+                }
+                double ck[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + lane + 32 * i;
+                    ck[i] = (q < p.G) ? __ldcg(&p.cand[slot * p.G + q].key) : -3.0;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = q0 + lane + 32 * i;
+                    const int cr = (int)(unsigned)(tg[i] & 0xffffffffu);
+                    if (q < p.G && cand_better(ck[i], cr, k2, r2)) { k2 = ck[i]; r2 = cr; g2 = q; }
+                }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -661,6 +688,20 @@ static void getrf_leaf(cudaStream_t s, const PanelCtx& pc, int off, int m, int n
     p.sw_left = off;
     p.sw_right = pc.width - off - n;
     const int S = ceil_div(pc.width, LEAF_THREADS);
+    if (g_thin_mode && m > g_thin_min_rows) {
+        const int thr = (g_thin_mode == 1) ? 128 : 64;
+        const int Gt = ceil_div(m, 256);
+        const int St = (pc.width > n) ? ceil_div(pc.width, thr) : 0;
+        if (Gt <= w.maxG && Gt + St <= 4 * num_sms() - 16) {
+            p.G = Gt;
+            if (g_thin_mode == 1) getrf_leaf_cluster_kernel<LEAF_W, 128, 2, false, 4><<<Gt + St, 128, 0, s>>>(p);
+            else getrf_leaf_cluster_kernel<LEAF_W, 64, 4, false, 4><<<Gt + St, 64, 0, s>>>(p);
+            count_launch();
+            w.epoch += (unsigned)min(m, n);
+            LB_CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+    }
     // All work CTAs of a leaf must be co-resident (they spin on each other's packets).  Panels taller than
     // (#SMs - interchange CTAs) x 1024 rows use 8 or 16 rows per thread -- slower (the row window spills to local
     // memory) but the same algorithm and results; 256 x 16 x 146 = 598,016 rows is the limit.
@@ -839,8 +880,9 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     cudaStream_t su = la ? ax.update_stream : s;
     cudaStream_t sl = la ? ax.side_stream : s;
     cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2], ev_plan = ax.ev[8], ev_left = ax.ev[9];
-    cudaEvent_t ev_gemm = ax.ev[10], ev_g1 = ax.ev[15];
+    cudaEvent_t ev_gemm = ax.ev[10];
     cudaEvent_t ev_prep[4] = {ax.ev[11], ax.ev[12], ax.ev[13], ax.ev[14]};
+    cudaEvent_t ev_upd[4] = {ax.ev[16], ax.ev[17], ax.ev[18], ax.ev[19]};      // recorded after the GEMM of chunk q
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
@@ -851,16 +893,14 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     // first panel
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
-    bool gemm_recorded = false, g1_recorded = false;
-    int g1_end = 0;              // last column (exclusive) covered by the previous step's chunk-1 GEMM
+    bool gemm_recorded = false;
+    int pc_lo[4], pc_hi[4], npc = 0;     // column ranges of the previous step's GEMM chunks (their completion = ev_upd[q])
 
     for (int j = 0; j < mn; j += nb) {
         const int jb = min(nb, mn - j);
         const int jn = j + jb;                       // first column after this panel
         double* Ajj = A + j + (i64)j * lda;
         const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
-        bool g1_now = false;
-        int g1_end_now = 0;
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
         // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel),
         // [c[1],c[2]) = the panel after that, then a quarter of the rest, then the remainder
@@ -884,27 +924,26 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 if (h1 < rest) c[++nchunk] = n;
             }
         }
-        if (la) {
-            LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
-            // chunk 0 of this step was (part of) chunk 1 of the previous step: its preparation may start as soon as
-            // THAT GEMM is done, while the big chunks of update j-1 are still running
-            if (g1_recorded && nchunk >= 1 && c[1] <= g1_end) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_g1, 0));
-            else if (gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));
-        }
+        if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
         // one plan for this panel's interchanges (dgetrf.f:193,199), applied to all column ranges
         void* plan = laswp_plan(sq, j + 1, jn, piv, 1);
         // preparation on sq: interchanges + block row of U for every chunk, in order
         for (int q = 0; q < nchunk; ++q) {
             const int w = c[q + 1] - c[q];
-            // every chunk but the first also needs the whole update j-1 (its columns were in the big chunks)
-            if (q == 1 && la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));
+            // the columns of this chunk must have received update j-1: wait for exactly the GEMM chunks of the previous step that
+            // cover them (chunk 0 here was chunk 1 there, chunk 1 here lies inside chunk 2 there, ...), so that the preparation
+            // of the first chunks of step j overlaps with the big GEMMs of step j-1
+            if (la)
+                for (int r = 0; r < npc; ++r)
+                    if (pc_lo[r] < c[q + 1] && c[q] < pc_hi[r]) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_upd[r], 0));
             if (tr) tr->mark(sq, j / nb, 4 + q, true);
             laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);                              // dgetrf.f:199
             trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);         // dgetrf.f:204
             if (tr) tr->mark(sq, j / nb, 4 + q, false);
             if (la) LB_CUDA_CHECK(cudaEventRecord(ev_prep[q], sq));
         }
-        if (nchunk <= 1 && la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));   // keep sq ordered after update j-1
+        // the interchanges left of the panel (below) and the next step's work on sq come after the whole update j-1
+        if (la && gemm_recorded) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_gemm, 0));
         if (la) LB_CUDA_CHECK(cudaEventRecord(ev_plan, sq));
         if (so && la && jn < n) {
             // block row j of U (rows j..jn, columns jn..n) is final once every chunk has been prepared: start its
@@ -923,7 +962,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 gemm(su, 'N', 'N', m - jn, w, jb, -1.0, A + jn + (i64)j * lda, lda, A + j + (i64)c[q] * lda, lda, 1.0,
                      A + jn + (i64)c[q] * lda, lda);                                                   // dgetrf.f:212
             if (tr) tr->mark(su, j / nb, q, false);
-            if (q == 1 && la) { LB_CUDA_CHECK(cudaEventRecord(ev_g1, su)); g1_now = true; g1_end_now = c[2]; }
+            if (la) LB_CUDA_CHECK(cudaEventRecord(ev_upd[q], su));
             if (q == 0 && jb2 > 0) {
                 if (la) {
                     LB_CUDA_CHECK(cudaEventRecord(ev_next, su));
@@ -938,8 +977,8 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
             }
         }
         if (la) { LB_CUDA_CHECK(cudaEventRecord(ev_gemm, su)); gemm_recorded = true; }
-        g1_recorded = g1_now;
-        g1_end = g1_end_now;
+        npc = nchunk;
+        for (int q = 0; q < nchunk; ++q) { pc_lo[q] = c[q]; pc_hi[q] = c[q + 1]; }
         // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns whose only
         // remaining reader was the trailing GEMM of the previous step (sq waited for it above), so they run on
         // a low-priority side stream concurrently with this step's trailing update.

@@ -127,7 +127,7 @@ struct Aux {
     cudaStream_t update_stream = nullptr;
     cudaStream_t side_stream = nullptr;    // low priority: work that is off the critical path (left-of-panel interchanges)
     cudaStream_t prep_stream = nullptr;    // medium priority: memory-bound preparation (interchanges + U12 solve) of the next chunk
-    cudaEvent_t ev[16];
+    cudaEvent_t ev[32];
     bool ready = false;
 };
 Aux& aux();

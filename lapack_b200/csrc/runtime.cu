@@ -97,7 +97,7 @@ Aux& aux() {
         LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.update_stream, cudaStreamNonBlocking, lo));
         LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.side_stream, cudaStreamNonBlocking, lo));
         LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, (hi + 1 <= lo) ? hi + 1 : hi));
-        for (int i = 0; i < 16; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
+        for (int i = 0; i < 32; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
         a.ready = true;
     }
     return a;
