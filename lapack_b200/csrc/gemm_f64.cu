@@ -122,6 +122,21 @@ struct TileLoader {
     }
 };
 
+// Tile columns [c0, c0+nc) that a group of tile rows [first_m, first_m+gsz) needs when only one triangle of C is computed
+// (tri 1: lower, tiles with some m >= n; tri 2: upper, tiles with some m <= n).
+constexpr int TRI_GROUP = 16;
+__host__ __device__ __forceinline__ void tri_group_cols(int tri, int first_m, int gsz, int bm, int bn, int tiles_n, int& c0, int& nc) {
+    if (tri == 1) {
+        c0 = 0;
+        const int last = ((first_m + gsz) * bm - 1) / bn;        // last tile column touched by the lowest row of the group
+        nc = (last + 1 < tiles_n) ? last + 1 : tiles_n;
+    } else {
+        c0 = (first_m * bm) / bn;                                 // first tile column touched by the top row of the group
+        if (c0 > tiles_n) c0 = tiles_n;
+        nc = tiles_n - c0;
+    }
+}
+
 // Loader for INTERIOR tiles (no M/N/K edge, 16-byte aligned operands): the chunks of one thread are a fixed stride apart in global and
 // in shared memory, so a k-tile costs N LDGSTS + N pointer additions and no predicates (the general loader above spends ~150 integer
 // instructions per k-tile on clamping).
@@ -170,14 +185,31 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32,
     extern __shared__ __align__(16) double smem[];
 
     // grouped rasterisation: 16 tile-rows at a time so that a wave of CTAs covers a squarish patch of C
-    constexpr int GROUP = 16;
+    constexpr int GROUP = TRI_GROUP;
     int pid = blockIdx.x;
-    int width = GROUP * p.tiles_n;
-    int group_id = pid / width;
-    int first_m = group_id * GROUP;
-    int gsz = min(p.tiles_m - first_m, GROUP);
-    int pid_m = first_m + (pid % width) % gsz;
-    int pid_n = (pid % width) / gsz;
+    int pid_m, pid_n;
+    if (p.tri == 0) {
+        int width = GROUP * p.tiles_n;
+        int group_id = pid / width;
+        int first_m = group_id * GROUP;
+        int gsz = min(p.tiles_m - first_m, GROUP);
+        pid_m = first_m + (pid % width) % gsz;
+        pid_n = (pid % width) / gsz;
+    } else {
+        // one triangle of C (DSYRK and the look-ahead block column of DPOTRF): the grid holds, per group of tile rows, only the tile
+        // columns that can touch the triangle (tri_group_cols, same formula on the host), not tiles_m x tiles_n CTAs of which half
+        // exit at once
+        int first_m = 0, gsz, c0, nc;
+        for (;;) {
+            gsz = min(p.tiles_m - first_m, GROUP);
+            tri_group_cols(p.tri, first_m, gsz, BM, BN, p.tiles_n, c0, nc);
+            if (pid < gsz * nc) break;
+            pid -= gsz * nc;
+            first_m += GROUP;
+        }
+        pid_m = first_m + pid % gsz;
+        pid_n = c0 + pid / gsz;
+    }
     const int m0 = pid_m * BM, n0 = pid_n * BN;
     if (p.guard && *p.guard != 0) return;
     if (p.tri == 1 && m0 + BM - 1 < n0) return;       // tile strictly above the diagonal
@@ -387,7 +419,18 @@ static void launch_cfg(cudaStream_t s, bool a_k, bool b_k, bool al16, const Gemm
     p.tiles_n = ceil_div(p.N, BN);
     constexpr int NTH = WMW * WNW * 32;
     size_t smem = 0;
-    dim3 grid((unsigned)((i64)p.tiles_m * p.tiles_n), (unsigned)ceil_div(p.K, p.kchunk));
+    i64 nctas = (i64)p.tiles_m * p.tiles_n;
+    if (p.tri != 0) {
+        nctas = 0;
+        for (int first_m = 0; first_m < p.tiles_m; first_m += TRI_GROUP) {
+            const int gsz = min(p.tiles_m - first_m, TRI_GROUP);
+            int c0, nc;
+            tri_group_cols(p.tri, first_m, gsz, BM, BN, p.tiles_n, c0, nc);
+            nctas += (i64)gsz * nc;
+        }
+        if (nctas == 0) return;
+    }
+    dim3 grid((unsigned)nctas, (unsigned)ceil_div(p.K, p.kchunk));
 #define LB_LAUNCH(AK, BKM, AL)                                                                                  \
     {                                                                                                           \
         auto kern = gemm_f64_dmma_kernel<BM, BN, WMW, WNW, AK, BKM, AL, STAGES, BKT, VAR>;                             \
@@ -510,9 +553,9 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
     // Long-K products with few output tiles per wave (W = V^T C of DLARFB: 8 tile rows, K = panel height): the launch is a handful
     // of waves of 4 x #SMs CTAs and the last, partly filled wave costs up to 15%.  Split K so that the CTA count fills whole waves;
     // slices are summed in a fixed order (deterministic).  K = NB updates of LU / Cholesky never take this path (k >= 2048).
-    if (g_splitk_balance && k >= 2048 && cfg < 0) {
+    if (g_splitk_balance && k >= 2048 && (cfg < 0 || cfg == 13 || cfg == 14)) {
         const i64 t64 = (i64)ceil_div(m, 64) * ceil_div(n, 64);
-        const i64 slots = 4 * (i64)num_sms();
+        const i64 slots = (cfg == 14 ? 3 : 4) * (i64)num_sms();
         auto eff = [&](int z) {
             const i64 tot = t64 * z, wv = (tot + slots - 1) / slots;
             return (double)tot / (double)(wv * slots) - 0.004 * (z - 1);
@@ -529,7 +572,8 @@ static void gemm_impl(cudaStream_t s, char transa, char transb, int m, int n, in
             GemmParams q = p;
             q.alpha = 1.0; q.beta = 0.0; q.C = P; q.ldc = m; q.tri = 0;
             q.kchunk = kchunk; q.c_zstride = (i64)m * n;
-            launch_cfg<64, 64, 2, 2, 2, 16, 1>(s, a_k, b_k, al16, q);
+            if (cfg == 14) launch_cfg<64, 64, 2, 2, 3, 16, 1>(s, a_k, b_k, al16, q);
+            else launch_cfg<64, 64, 2, 2, 2, 16, 1>(s, a_k, b_k, al16, q);
             dim3 rgrid(ceil_div(m, 128), (unsigned)min(n, 4096));
             splitk_reduce_kernel<<<rgrid, 128, 0, s>>>(m, n, nz, alpha, beta, P, C, ldc, tri);
             count_launch();

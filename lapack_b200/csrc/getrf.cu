@@ -826,7 +826,7 @@ void getrf2(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* in
 // Optional timeline of the blocked driver (LB200_TRACE_LU=1): timing events around every chunk GEMM and every panel;
 // after the factorization the per-step intervals are printed to stderr (the call becomes synchronous).
 struct LuTrace {
-    struct Rec { int step, kind; cudaEvent_t e0, e1; };     // kind 0..3 = GEMM chunk, 4..7 = preparation of chunk, 8 = panel
+    struct Rec { int step, kind; cudaEvent_t e0, e1; };     // kind 0..4 = GEMM chunk, 10..14 = preparation of chunk, 20 = panel
     std::vector<Rec> recs;
     cudaEvent_t origin = nullptr;
     void mark(cudaStream_t st, int step, int kind, bool begin) {
@@ -871,8 +871,8 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     StreamOut* so = stream_out();
     // Streams (look-ahead on): sp = panel (highest priority), sq = memory-bound preparation of the trailing
     // columns (interchanges + U12 solve, medium priority), su = trailing GEMMs (low priority), sl = interchanges
-    // left of the panel (low priority, off the critical path).  The trailing columns are processed in four
-    // chunks -- the next panel's columns, the panel after that, a quarter of the rest, the remainder -- so that the
+    // left of the panel (low priority, off the critical path).  The trailing columns are processed in up to five
+    // chunks -- the next panel's columns, the panel after that, 2048 more, a quarter of the rest, the remainder -- so that the
     // preparation of chunk c+1 overlaps with the GEMM of chunk c, and the preparation of the NEXT step's first chunk
     // (this step's chunk 1) can start while this step's big chunks are still running.
     cudaStream_t sp = la ? ax.panel_stream : s;
@@ -881,8 +881,8 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     cudaStream_t sl = la ? ax.side_stream : s;
     cudaEvent_t ev_panel = ax.ev[0], ev_next = ax.ev[1], ev_join = ax.ev[2], ev_plan = ax.ev[8], ev_left = ax.ev[9];
     cudaEvent_t ev_gemm = ax.ev[10];
-    cudaEvent_t ev_prep[4] = {ax.ev[11], ax.ev[12], ax.ev[13], ax.ev[14]};
-    cudaEvent_t ev_upd[4] = {ax.ev[16], ax.ev[17], ax.ev[18], ax.ev[19]};      // recorded after the GEMM of chunk q
+    cudaEvent_t ev_prep[5] = {ax.ev[11], ax.ev[12], ax.ev[13], ax.ev[14], ax.ev[15]};
+    cudaEvent_t ev_upd[5] = {ax.ev[16], ax.ev[17], ax.ev[18], ax.ev[19], ax.ev[20]};      // recorded after the GEMM of chunk q
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_join, s));
         LB_CUDA_CHECK(cudaStreamWaitEvent(sp, ev_join, 0));
@@ -894,7 +894,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
     bool gemm_recorded = false;
-    int pc_lo[4], pc_hi[4], npc = 0;     // column ranges of the previous step's GEMM chunks (their completion = ev_upd[q])
+    int pc_lo[5], pc_hi[5], npc = 0;     // column ranges of the previous step's GEMM chunks (their completion = ev_upd[q])
 
     for (int j = 0; j < mn; j += nb) {
         const int jb = min(nb, mn - j);
@@ -903,8 +903,9 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
         // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel),
-        // [c[1],c[2]) = the panel after that, then a quarter of the rest, then the remainder
-        int c[5];
+        // [c[1],c[2]) = the panel after that, a narrow third chunk (its preparation can only start after the whole update j-1 and
+        // must be finished when the GEMMs of the first two chunks are), then a quarter of the rest, then the remainder
+        int c[6];
         int nchunk = 0;
         c[0] = jn;
         if (jn < n) {
@@ -916,6 +917,11 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 c[nchunk + 1] = c[nchunk] + w2;
                 ++nchunk;
                 rest -= w2;
+            }
+            if (rest >= 8192) {
+                c[nchunk + 1] = c[nchunk] + 2048;
+                ++nchunk;
+                rest -= 2048;
             }
             if (rest > 0) {
                 int h1 = (rest >= 4096) ? ((rest / 4 + 63) / 64) * 64 : rest;
@@ -936,10 +942,10 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
             if (la)
                 for (int r = 0; r < npc; ++r)
                     if (pc_lo[r] < c[q + 1] && c[q] < pc_hi[r]) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_upd[r], 0));
-            if (tr) tr->mark(sq, j / nb, 4 + q, true);
+            if (tr) tr->mark(sq, j / nb, 10 + q, true);
             laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);                              // dgetrf.f:199
             trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);         // dgetrf.f:204
-            if (tr) tr->mark(sq, j / nb, 4 + q, false);
+            if (tr) tr->mark(sq, j / nb, 10 + q, false);
             if (la) LB_CUDA_CHECK(cudaEventRecord(ev_prep[q], sq));
         }
         // the interchanges left of the panel (below) and the next step's work on sq come after the whole update j-1
@@ -970,9 +976,9 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 }
                 // factor the next panel (overlaps with the rest of this update when look-ahead is on)
                 // the leaves write absolute pivot rows (dgetrf.f:187-189 shift applied at the source)
-                if (tr) tr->mark(sp, j / nb, 8, true);
+                if (tr) tr->mark(sp, j / nb, 20, true);
                 getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
-                if (tr) tr->mark(sp, j / nb, 8, false);
+                if (tr) tr->mark(sp, j / nb, 20, false);
                 if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
             }
         }
