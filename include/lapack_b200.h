@@ -45,7 +45,7 @@ void lb200_set_getrf_tall_rows(int rows_per_cta);
 void lb200_set_getrf_cluster_fat(int on);
 /* thin LU leaves for panels taller than min_rows: 0 = off, 1 = 128 threads x 2 rows per CTA, 2 = 64 threads x 4 rows (one GEMM-CTA slot each) */
 void lb200_set_getrf_thin(int mode, int min_rows);
-/* batched 32x32 DGETRF: 0 (default) = one-shot kernel (one matrix per warp), 1 = persistent software-pipelined kernel (measured slower) */
+/* batched 32x32 DGETRF: 2 (default) = two matrices per warp, 0 = one matrix per warp, 1 = persistent software-pipelined one-matrix kernel (measured slower) */
 void lb200_set_batched_mode(int mode);
 /* DLASWP apply kernel: 1 = scattered row reads as 16-byte cp.async.bulk copies instead of LDG (experiment) */
 void lb200_set_laswp_bulk(int on);

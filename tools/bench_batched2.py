@@ -18,4 +18,4 @@ for mode in (0, 1):
     res[mode] = (a.clone(), ipiv.clone(), info.clone())
     print(f"mode {mode}: {best:.3f} ms  {batch * 16512 / best * 1e-6:.0f} GB/s", flush=True)
 print("identical results:", bool(torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])))
-L.lb200_set_batched_mode(0)
+L.lb200_set_batched_mode(2)

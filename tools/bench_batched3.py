@@ -47,4 +47,4 @@ for mode in modes:
     print(f"mode {mode}: {ms:.3f} ms  {batch * 16512 / ms * 1e-6:.0f} GB/s = {batch * 16512 / ms * 1e-6 / 6454.3:.3f} of HBM peak", flush=True)
     if ref is None: ref = (a, ipiv, info)
     else: print(f"   identical to mode {modes[0]}: factors {same(a, ref[0])} ipiv {same(ipiv, ref[1])} info {same(info, ref[2])}", flush=True)
-L.lb200_set_batched_mode(0)
+L.lb200_set_batched_mode(2)
