@@ -657,10 +657,10 @@ def run_ours(args, rank, world, local_rank):
     gemm_tf = (gfl.value / (gms.value * 1e-3) * 1e-12) if gms.value > 0 else None
     traffic, traffic_note = None, "no ncu capture found under profiles/"
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02b_gemm_traffic.json")))
         traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of ONE representative trailing-update launch (m=n={tr['m']}, k={tr['k']}; "
-                        f"algorithmic {tr['algorithmic_bytes']:.3e} B), read from profiles/r02_gemm_traffic.json ({tr['source']})")
+                        f"algorithmic {tr['algorithmic_bytes']:.3e} B), read from profiles/r02b_gemm_traffic.json ({tr['source']})")
     except Exception:
         pass
     hbm = 6650.0
@@ -692,7 +692,7 @@ def run_ours(args, rank, world, local_rank):
         "dgeqrf_32768": {"workload": f"DGEQRF {n}x{n} (BASELINE configs[3]), DLARNV(2) seed 1988-1991", "ms": t_qr * 1e3,
                          "tflops": flops_geqrf(n, n) / t_qr * 1e-12, "flops": flops_geqrf(n, n), "checks": qr_checks},
         "dgesv_4096": c1,
-        "roofline": {"bound": "tensor", "kernel": "gemm_f64_dmma_kernel<64,64,2,2,...,STAGES=2,BK=16> (trailing updates, DMMA.8x8x4)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_f64_dmma_kernel<64,64,2,2,...,STAGES=2,BK=16,VAR=1> (trailing updates, DMMA.8x8x4; interior tiles through the lean cp.async loader)",
                      "achieved": gemm_tf, "peak": peak, "unit": "TFLOP/s", "frac": (gemm_tf / peak) if gemm_tf else None,
                      "peak_cublas": peak_cublas, "frac_of_cublas": (gemm_tf / peak_cublas) if gemm_tf else None,
                      "peak_cublas_note": "cuBLAS DGEMM 8192^3 via torch.matmul timed in this run (independent denominator, checker only)",
