@@ -32,6 +32,7 @@ void lb200_profile_gemm_read(double* total_ms, double* total_flops, long long* l
 
 /* tuning knobs (testing / benchmarking; defaults are chosen per problem size) */
 void lb200_set_gemm_splitk_balance(int on);   /* 1 (default): long-K GEMMs whose tile count leaves a partly filled last wave are split along K */
+void lb200_set_trsm_inverse(int on);   /* 1 (default): the panel solve inside DPOTRF uses inverted 32x32 diagonal blocks (DMMA leaves; 377.5 -> 373.9 ms at n=32768); 0: substitution leaves everywhere */
 void lb200_set_gemm_config(int cfg);   /* -1 auto, 0/1/2 force a cp.async tile shape, 3 force the TMA kernel */
 void lb200_set_gemm_tma(int on);       /* 0 disables the TMA fast path (falls back to cp.async) */
 void lb200_set_getrf_params(int nb, int leaf, int lookahead);

@@ -47,6 +47,7 @@ def _declare(L):
     L.lb200_fp64_peak_tflops.restype = d
     L.lb200_fp64_peak_tflops.argtypes = [VP, i, i, i, i]
     L.lb200_set_gemm_config.argtypes = [i]
+    L.lb200_set_trsm_inverse.argtypes = [i]
     L.lb200_set_gemm_splitk_balance.argtypes = [i]
     L.lb200_set_getrf_params.argtypes = [i, i, i]
     L.lb200_set_getrf_cluster_max.argtypes = [i]

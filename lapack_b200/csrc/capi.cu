@@ -9,6 +9,7 @@
 namespace lb {
 double fp64_peak(cudaStream_t s, int kind, int warps_per_cta, int ctas_per_sm, int iters);
 void gemm_set_config(int cfg);
+void trsm_set_inverse_enabled(int on);
 void gemm_set_splitk_balance(int on);
 void gemm_set_tma(int on);
 void gemm_profile(int enable);
@@ -46,6 +47,7 @@ double lb200_fp64_peak_tflops(void* stream, int kind, int warps_per_cta, int cta
     return lb::fp64_peak(S(stream), kind, warps_per_cta, ctas_per_sm, iters);
 }
 void lb200_set_gemm_config(int cfg) { lb::gemm_set_config(cfg); }
+void lb200_set_trsm_inverse(int on) { lb::trsm_set_inverse_enabled(on); }
 void lb200_set_gemm_splitk_balance(int on) { lb::gemm_set_splitk_balance(on); }
 void lb200_set_gemm_tma(int on) { lb::gemm_set_tma(on); }
 void lb200_profile_gemm(int enable) { lb::gemm_profile(enable); }

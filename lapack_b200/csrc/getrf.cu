@@ -857,6 +857,9 @@ struct LuTrace {
 void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
     std::lock_guard<std::recursive_mutex> lock(g_lib_mutex);
     static const bool trace_on = getenv("LB200_TRACE_LU") != nullptr;
+    // Profiling aid (WRONG RESULTS, timing only): LB200_ABLATE bit 0 = skip the interchanges left of the panel, bit 1 = skip the
+    // interchanges of the trailing columns, bit 2 = skip the U12 solve -- measures what each memory-bound stage costs the update GEMMs.
+    static const int ablate = getenv("LB200_ABLATE") ? atoi(getenv("LB200_ABLATE")) : 0;
     LuTrace trace;
     LuTrace* tr = trace_on ? &trace : nullptr;
     if (tr) { cudaEventCreate(&tr->origin); cudaEventRecord(tr->origin, s); }
@@ -943,8 +946,9 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 for (int r = 0; r < npc; ++r)
                     if (pc_lo[r] < c[q + 1] && c[q] < pc_hi[r]) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_upd[r], 0));
             if (tr) tr->mark(sq, j / nb, 10 + q, true);
-            laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);                              // dgetrf.f:199
-            trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);         // dgetrf.f:204
+            if (!(ablate & 2)) laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);           // dgetrf.f:199
+            // (inverted 32 x 32 diagonal blocks -- trsm_set_inverse_leaves, used by DPOTRF -- were measured neutral here: 806 vs 807 ms)
+            if (!(ablate & 4)) trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);   // dgetrf.f:204
             if (tr) tr->mark(sq, j / nb, 10 + q, false);
             if (la) LB_CUDA_CHECK(cudaEventRecord(ev_prep[q], sq));
         }
@@ -989,7 +993,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         // remaining reader was the trailing GEMM of the previous step (sq waited for it above), so they run on
         // a low-priority side stream concurrently with this step's trailing update.
         if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
-        if (j > 0) laswp_apply_plan(sl, j, A, lda, plan, jb);
+        if (j > 0 && !(ablate & 1)) laswp_apply_plan(sl, j, A, lda, plan, jb);
         laswp_plan_free(sl, plan);
     }
     if (la) {

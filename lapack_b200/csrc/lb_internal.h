@@ -43,6 +43,9 @@ void syrk(cudaStream_t s, char uplo, char trans, int n, int k, double alpha, con
 // op(A)*X = alpha*B or X*op(A) = alpha*B, X overwrites B.
 void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, double alpha,
           const double* A, i64 lda, double* B, i64 ldb);
+// Drivers' large solves only (thread-local switch): 32 x 32 leaves as in-place DMMA products with the inverted diagonal blocks.
+void trsm_set_inverse_leaves(int on);
+int trsm_inverse_enabled();                 // library-wide knob (lb200_set_trsm_inverse), default 1
 // B := alpha*op(A)*B or alpha*B*op(A), A triangular.  Needs a scratch copy of B (from the pool).
 void trmm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, int n, double alpha,
           const double* A, i64 lda, double* B, i64 ldb);

@@ -132,8 +132,10 @@ void potrf(cudaStream_t s, char uplo, int n, double* A, i64 lda, int* info) {
         potrf_rec(sp, upper, jb, Ajj, lda, info, j);
         const int rest = n - j - jb;
         if (rest > 0) {
+            trsm_set_inverse_leaves(1);          // panel solve with DMMA leaves (diagonal blocks of a Cholesky factor)
             if (upper) trsm(sp, 'L', 'U', 'T', 'N', jb, rest, 1.0, Ajj, lda, A + j + (i64)(j + jb) * lda, lda);
             else trsm(sp, 'R', 'L', 'T', 'N', rest, jb, 1.0, Ajj, lda, A + (j + jb) + (i64)j * lda, lda);
+            trsm_set_inverse_leaves(0);
         }
         if (so) {
             // block column j (lower) / block row j (upper) of the factor is final: start its download now

@@ -194,6 +194,55 @@ void scale_matrix(cudaStream_t s, int m, int n, double alpha, double* B, i64 ldb
 
 static inline bool is(char c, char u) { return c == u || c == (char)(u + 32); }
 
+// ----------------------------------------------------------------------------------------------
+// Inverted diagonal blocks (opt-in, used by DPOTRF for its panel solve; measured neutral for U12 = inv(L11) A12 of DGETRF, where
+// it is therefore not used).  The 32 x 32 substitution leaves above are latency-bound CUDA-core kernels that take SM slots from the concurrent
+// trailing GEMM; with the inverse of every 32 x 32 diagonal block formed once per triangle (one small launch), a leaf becomes the
+// in-place DMMA product B := inv(T_kk) B (or B inv(T_kk)), K = 32, which only streams B.  The blocks are diagonal blocks of a Cholesky factor, so inv(T_kk) is benign (factor difference against the
+// substitution leaves at n = 32768: 6e-18 absolute); the public DTRSM keeps
+// the substitution leaves (dtrsm.f semantics entry by entry).
+struct InvBlocks { const double* base = nullptr; int blk0 = 0; };       // 32 x 32 dense blocks, ld 32; blk0 = block index of A(0,0)
+static thread_local int g_trsm_inverse_leaves = 0;
+static int g_trsm_inverse_enabled = 1;
+void trsm_set_inverse_leaves(int on) { g_trsm_inverse_leaves = on && g_trsm_inverse_enabled; }
+int trsm_inverse_enabled() { return g_trsm_inverse_enabled; }
+void trsm_set_inverse_enabled(int on) { g_trsm_inverse_enabled = on; }
+
+// one CTA (32 threads) per diagonal block: thread j solves T x = e_j by substitution; partial last block padded with the identity
+__global__ void __launch_bounds__(32) trtri32_blocks_kernel(int n, const double* __restrict__ A, i64 lda, bool upper, bool unit,
+                                                            double* __restrict__ Tinv, const int* guard) {
+    __shared__ double T[TB][TB + 1];
+    if (guard && *guard != 0) return;
+    const int b = blockIdx.x, r0 = b * TB, nb = min(TB, n - r0), j = threadIdx.x;
+    for (int i = 0; i < TB; ++i) {
+        double v = (i == j) ? 1.0 : 0.0;
+        if (i < nb && j < nb && (upper ? i <= j : i >= j) && !(unit && i == j)) v = A[(r0 + i) + (i64)(r0 + j) * lda];
+        T[i][j] = v;
+    }
+    __syncwarp();
+    double x[TB];
+#pragma unroll
+    for (int i = 0; i < TB; ++i) x[i] = (i == j) ? 1.0 : 0.0;
+    if (!upper) {
+#pragma unroll
+        for (int k = 0; k < TB; ++k) {
+            x[k] = x[k] / T[k][k];
+#pragma unroll
+            for (int i = k + 1; i < TB; ++i) x[i] = fma(-x[k], T[i][k], x[i]);
+        }
+    } else {
+#pragma unroll
+        for (int k = TB - 1; k >= 0; --k) {
+            x[k] = x[k] / T[k][k];
+#pragma unroll
+            for (int i = 0; i < k; ++i) x[i] = fma(-x[k], T[i][k], x[i]);
+        }
+    }
+    double* out = Tinv + (size_t)b * TB * TB + (size_t)j * TB;
+#pragma unroll
+    for (int i = 0; i < TB; ++i) out[i] = x[i];
+}
+
 // split point: largest multiple of TB (power-of-two times TB preferred) not exceeding half, at least TB
 static int split_point(int n) {
     int h = TB;
@@ -202,8 +251,13 @@ static int split_point(int n) {
 }
 
 static void trsm_left_rec(cudaStream_t s, bool upper, bool trans, bool unit, int m, int n, const double* A, i64 lda,
-                          double* B, i64 ldb) {
+                          double* B, i64 ldb, InvBlocks iv = InvBlocks()) {
     const bool eff_lower = (upper == trans);   // (L,N) or (U,T)
+    if (m <= TB && iv.base) {
+        // B := op(inv(T_kk)) B in place: a CTA's 64-column output tile reads exactly its own columns of B, all of them before it writes
+        gemm(s, trans ? 'T' : 'N', 'N', m, n, m, 1.0, iv.base + (size_t)iv.blk0 * TB * TB, TB, B, ldb, 0.0, B, ldb);
+        return;
+    }
     if (m <= TB) {
         int threads = 128;
         if (eff_lower) trsm_left_leaf_kernel<true><<<ceil_div(n, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
@@ -218,22 +272,29 @@ static void trsm_left_rec(cudaStream_t s, bool upper, bool trans, bool unit, int
     const double* A12 = A + (i64)m1 * lda;         // stored (m1 x m2) block right of the diagonal
     double* B1 = B;
     double* B2 = B + m1;
+    InvBlocks iv2 = iv;
+    iv2.blk0 = iv.blk0 + m1 / TB;
     if (eff_lower) {
-        trsm_left_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb);
+        trsm_left_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb, iv);
         if (!trans) gemm(s, 'N', 'N', m2, n, m1, -1.0, A21, lda, B1, ldb, 1.0, B2, ldb);
         else gemm(s, 'T', 'N', m2, n, m1, -1.0, A12, lda, B1, ldb, 1.0, B2, ldb);
-        trsm_left_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb);
+        trsm_left_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb, iv2);
     } else {
-        trsm_left_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb);
+        trsm_left_rec(s, upper, trans, unit, m2, n, A22, lda, B2, ldb, iv2);
         if (!trans) gemm(s, 'N', 'N', m1, n, m2, -1.0, A12, lda, B2, ldb, 1.0, B1, ldb);
         else gemm(s, 'T', 'N', m1, n, m2, -1.0, A21, lda, B2, ldb, 1.0, B1, ldb);
-        trsm_left_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb);
+        trsm_left_rec(s, upper, trans, unit, m1, n, A11, lda, B1, ldb, iv);
     }
 }
 
 static void trsm_right_rec(cudaStream_t s, bool upper, bool trans, bool unit, int m, int n, const double* A, i64 lda,
-                           double* B, i64 ldb) {
+                           double* B, i64 ldb, InvBlocks iv = InvBlocks()) {
     const bool eff_upper = (upper != trans);   // (U,N) or (L,T)
+    if (n <= TB && iv.base) {
+        // B := B op(inv(T_kk)) in place: a CTA's 64-row output tile reads exactly its own rows of B, all of them before it writes
+        gemm(s, 'N', trans ? 'T' : 'N', m, n, n, 1.0, B, ldb, iv.base + (size_t)iv.blk0 * TB * TB, TB, 0.0, B, ldb);
+        return;
+    }
     if (n <= TB) {
         int threads = 128;
         if (eff_upper) trsm_right_leaf_kernel<true><<<ceil_div(m, threads), threads, 0, s>>>(m, n, A, lda, upper, trans, unit, B, ldb, kernel_guard());
@@ -248,16 +309,18 @@ static void trsm_right_rec(cudaStream_t s, bool upper, bool trans, bool unit, in
     const double* A12 = A + (i64)n1 * lda;
     double* B1 = B;
     double* B2 = B + (i64)n1 * ldb;
+    InvBlocks iv2 = iv;
+    iv2.blk0 = iv.blk0 + n1 / TB;
     if (eff_upper) {
-        trsm_right_rec(s, upper, trans, unit, m, n1, A11, lda, B1, ldb);
+        trsm_right_rec(s, upper, trans, unit, m, n1, A11, lda, B1, ldb, iv);
         if (!trans) gemm(s, 'N', 'N', m, n2, n1, -1.0, B1, ldb, A12, lda, 1.0, B2, ldb);
         else gemm(s, 'N', 'T', m, n2, n1, -1.0, B1, ldb, A21, lda, 1.0, B2, ldb);
-        trsm_right_rec(s, upper, trans, unit, m, n2, A22, lda, B2, ldb);
+        trsm_right_rec(s, upper, trans, unit, m, n2, A22, lda, B2, ldb, iv2);
     } else {
-        trsm_right_rec(s, upper, trans, unit, m, n2, A22, lda, B2, ldb);
+        trsm_right_rec(s, upper, trans, unit, m, n2, A22, lda, B2, ldb, iv2);
         if (!trans) gemm(s, 'N', 'N', m, n1, n2, -1.0, B2, ldb, A21, lda, 1.0, B1, ldb);
         else gemm(s, 'N', 'T', m, n1, n2, -1.0, B2, ldb, A12, lda, 1.0, B1, ldb);
-        trsm_right_rec(s, upper, trans, unit, m, n1, A11, lda, B1, ldb);
+        trsm_right_rec(s, upper, trans, unit, m, n1, A11, lda, B1, ldb, iv);
     }
 }
 
@@ -519,8 +582,21 @@ void trsm(cudaStream_t s, char side, char uplo, char trans, char diag, int m, in
     } else if (left && n <= FR_MAXRHS && m > FR_LEAF) {
         if (g_fewrhs_mode == 1) trsv_stream(s, upper, tr, unit, m, n, A, lda, B, ldb);
         else trsm_left_fewrhs_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
-    } else if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
-    else trsm_right_rec(s, upper, tr, unit, m, n, A, lda, B, ldb);
+    } else {
+        const int nt = left ? m : n;                       // order of the triangle
+        InvBlocks iv;
+        double* scratch = nullptr;
+        if (g_trsm_inverse_leaves && nt >= 2 * TB && (left ? n : m) >= 1024) {
+            const int nblk = ceil_div(nt, TB);
+            scratch = (double*)ws_alloc(s, sizeof(double) * (size_t)nblk * TB * TB);
+            trtri32_blocks_kernel<<<nblk, 32, 0, s>>>(nt, A, lda, upper, unit, scratch, kernel_guard());
+            count_launch();
+            iv.base = scratch;
+        }
+        if (left) trsm_left_rec(s, upper, tr, unit, m, n, A, lda, B, ldb, iv);
+        else trsm_right_rec(s, upper, tr, unit, m, n, A, lda, B, ldb, iv);
+        if (scratch) ws_free(s, scratch);
+    }
     LB_CUDA_CHECK(cudaGetLastError());
 }
 
