@@ -400,6 +400,79 @@ void laswp(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int*
 }
 // Plan once, apply to several column ranges (the blocked LU driver applies one panel's interchanges to the
 // look-ahead slab, the rest of the trailing matrix and the columns on the left).  k2-k1+1 <= LASWP_MAX_PIV.
+// ---- deferred interchanges left of the panels (getrf.cu): the plans of D consecutive panels, plan d to be applied to the columns
+// [0, (d+1)*nb), are COMPOSED per block column -- block column b receives plans b .. D-1 in that order -- into one row permutation
+// sigma_b (new row i <- old row sigma_b(i)), and every column is then permuted ONCE: gathered through its permutation (scattered
+// 8-byte reads, but of a column that one CTA is streaming through L2 anyway) and written back.  DRAM traffic ~ the touched part of
+// the columns once, instead of one 128-byte line fill per moved element and panel (profiles/r02_laswp_ncu.txt).
+//   compose: one CTA; t = the current plan's map tau in shared memory (identity elsewhere), sig <- tau(sig), from the last plan
+//   to the first: sigma_b(i) = tau_{b}(sigma_{b+1}(i)).
+constexpr int LASWP_CHAIN_MAX = 120;
+struct SwapPlanList { const SwapPlan* p[LASWP_CHAIN_MAX]; };
+__global__ void __launch_bounds__(1024) laswp_chain_compose_kernel(int m, int nplans, const SwapPlanList plans, int* __restrict__ sigma) {
+    extern __shared__ int tmap[];                    // [m]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m; i += 1024) tmap[i] = i;
+    __syncthreads();
+    for (int d = nplans - 1; d >= 0; --d) {
+        const SwapPlan* pl = plans.p[d];
+        const int np = pl->np, nout = pl->nout, k1 = pl->k1;
+        const int* srcA = pl->data;
+        const int2* pairs = reinterpret_cast<const int2*>(pl->data + np + (np & 1));
+        for (int q = tid; q < np; q += 1024) tmap[k1 - 1 + q] = srcA[q];
+        for (int q = tid; q < nout; q += 1024) tmap[pairs[q].x] = pairs[q].y;
+        __syncthreads();
+        int* sig = sigma + (size_t)d * m;
+        const int* prev = (d + 1 < nplans) ? sigma + (size_t)(d + 1) * m : nullptr;
+        for (int i = tid; i < m; i += 1024) sig[i] = tmap[prev ? prev[i] : i];
+        __syncthreads();
+        for (int q = tid; q < np; q += 1024) tmap[k1 - 1 + q] = k1 - 1 + q;
+        for (int q = tid; q < nout; q += 1024) tmap[pairs[q].x] = pairs[q].x;
+        __syncthreads();
+    }
+}
+// persistent CTAs, one column at a time: gather the moved rows into this CTA's scratch column, then write them back
+__global__ void __launch_bounds__(1024) laswp_chain_apply_kernel(int m, int nb, int ncols, double* __restrict__ A, i64 lda,
+                                                                 const int* __restrict__ sigma, double* __restrict__ W) {
+    double* w = W + (size_t)blockIdx.x * m;
+    for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
+        const int b = c / nb;
+        const int r0 = (b + 1) * nb;                 // rows above belong to earlier panels: untouched by plans b ..
+        const int* sig = sigma + (size_t)b * m;
+        double* col = A + (i64)c * lda;
+        for (int i = r0 + threadIdx.x; i < m; i += 1024) {
+            const int src = sig[i];
+            if (src != i) w[i] = col[src];
+        }
+        __syncthreads();
+        for (int i = r0 + threadIdx.x; i < m; i += 1024)
+            if (sig[i] != i) col[i] = w[i];
+        __syncthreads();
+    }
+}
+// plans[d] (device SwapPlan pointers, host array) applies to columns [0, (d+1)*nb); false = not applicable (caller falls back)
+bool laswp_apply_chain(cudaStream_t s, int m, int nb, int nplans, void* const* plans_host, double* A, i64 lda) {
+    if (nplans <= 0) return true;
+    const size_t smem = sizeof(int) * (size_t)m;
+    if (smem > 200 * 1024 || nplans > LASWP_CHAIN_MAX) return false;
+    static bool attr = false;
+    if (!attr) {
+        LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_chain_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    const int grid = 2 * num_sms();
+    SwapPlanList list;
+    for (int d = 0; d < nplans; ++d) list.p[d] = (const SwapPlan*)plans_host[d];
+    int* sigma = (int*)ws_alloc(s, sizeof(int) * (size_t)nplans * m);
+    double* W = (double*)ws_alloc(s, sizeof(double) * (size_t)grid * m);
+    laswp_chain_compose_kernel<<<1, 1024, smem, s>>>(m, nplans, list, sigma);
+    laswp_chain_apply_kernel<<<grid, 1024, 0, s>>>(m, nb, nplans * nb, A, lda, sigma, W);
+    count_launch(2);
+    ws_free(s, W); ws_free(s, sigma);
+    LB_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
 void* laswp_plan(cudaStream_t s, int k1, int k2, const int* ipiv, int incx) {
     const int cnt = k2 - k1 + 1;
     if (cnt <= 0 || cnt > LASWP_MAX_PIV) return nullptr;

@@ -29,6 +29,7 @@ void laswp_rows(cudaStream_t s, int n, int rows, double* A, i64 lda, int k1, int
 void* laswp_plan(cudaStream_t s, int k1, int k2, const int* ipiv, int incx);
 void laswp_apply_plan(cudaStream_t s, int n, double* A, i64 lda, const void* plan, int npiv);
 void laswp_plan_free(cudaStream_t s, void* plan);
+bool laswp_apply_chain(cudaStream_t s, int m, int nb, int nplans, void* const* plans_host, double* A, i64 lda);
 
 static int g_nb = 512, g_lookahead = 1;
 static int g_cluster_max = 16;      // panels of up to this many 1024-row CTAs use the cluster leaf (0 = never)
@@ -42,6 +43,8 @@ static int g_tall_rows = 1024;      // rows per CTA of the global-packet leaf fo
 void getrf_set_tall_rows(int r) { g_tall_rows = (r == 2048 || r == 4096) ? r : 1024; }
 // Thin leaves (see getrf_leaf_cluster_kernel, MINB): 0 = off, 1 = 128 threads x 2 rows, 2 = 64 threads x 4 rows (256 rows per CTA either
 // way, one GEMM-CTA slot each); used for panels of more than g_thin_min_rows rows, i.e. while the panel is hidden behind the update.
+static int g_defer_left = 1, g_defer_tail_rows = 512;     // deferred interchanges left of the panel: 0 off, 1 composed streaming pass, 2 plan by plan
+void getrf_set_defer_left(int on, int tail_rows) { g_defer_left = on; if (tail_rows > 0) g_defer_tail_rows = tail_rows; }
 static int g_thin_mode = 0, g_thin_min_rows = 16384;
 void getrf_set_thin(int mode, int min_rows) { g_thin_mode = mode; if (min_rows >= 0) g_thin_min_rows = min_rows; }
 void getrf_set_params(int nb, int leaf, int lookahead) {
@@ -897,6 +900,23 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
     getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
     bool gemm_recorded = false;
+    struct DeferredSwap { void* plan; int ncols, npiv; };
+    std::vector<DeferredSwap> deferred;          // interchanges left of the panel that wait for the tail (see below)
+    // deferred[d] is the plan of panel d+1 and applies to the columns [0, (d+1)*nb): composed per block column and applied in one
+    // streaming pass (laswp_apply_chain); plan by plan when the composition is not applicable (uneven panels, very tall matrices)
+    auto flush_deferred = [&]() {
+        if (deferred.empty()) return;
+        bool chain_ok = g_defer_left == 1;
+        std::vector<void*> pl;
+        for (size_t d = 0; d < deferred.size(); ++d) {
+            pl.push_back(deferred[d].plan);
+            if (deferred[d].ncols != (int)(d + 1) * nb || deferred[d].npiv != nb) chain_ok = false;
+        }
+        if (!(chain_ok && laswp_apply_chain(sl, m, nb, (int)pl.size(), pl.data(), A, lda)))
+            for (const DeferredSwap& d : deferred) laswp_apply_plan(sl, d.ncols, A, lda, d.plan, d.npiv);
+        for (const DeferredSwap& d : deferred) laswp_plan_free(sl, d.plan);
+        deferred.clear();
+    };
     int pc_lo[5], pc_hi[5], npc = 0;     // column ranges of the previous step's GEMM chunks (their completion = ev_upd[q])
 
     for (int j = 0; j < mn; j += nb) {
@@ -992,9 +1012,25 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         // interchanges to the left of the panel (dgetrf.f:193).  Those columns are final L columns whose only
         // remaining reader was the trailing GEMM of the previous step (sq waited for it above), so they run on
         // a low-priority side stream concurrently with this step's trailing update.
+        // These interchanges are scattered DRAM accesses (one 128-byte line fill per moved element) that slow the concurrent GEMMs
+        // down by about their own duration (LB200_ABLATE=1: 809 -> 791 ms at n = 32768), and moving them into the tail of the
+        // factorization does not hide them either (808 ms).  So they are DEFERRED and COMPOSED: the plans are kept until the trailing
+        // matrix is down to g_defer_tail_rows rows (default: the last panel), then every block column receives its whole chain of
+        // interchanges as ONE row permutation in a streaming pass (laswp_apply_chain): 809 -> 793 ms, bit-identical results.
+        const bool defer = la && g_defer_left && (m - jn) > g_defer_tail_rows && jn < mn;
+        if (defer) {
+            if (j > 0 && !(ablate & 1)) deferred.push_back(DeferredSwap{plan, j, jb});
+            else laswp_plan_free(sl, plan);
+        } else {
+            if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
+            flush_deferred();
+            if (j > 0 && !(ablate & 1)) laswp_apply_plan(sl, j, A, lda, plan, jb);
+            laswp_plan_free(sl, plan);
+        }
+    }
+    if (!deferred.empty()) {        // (not reached: the last step is never deferred)
         if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
-        if (j > 0 && !(ablate & 1)) laswp_apply_plan(sl, j, A, lda, plan, jb);
-        laswp_plan_free(sl, plan);
+        flush_deferred();
     }
     if (la) {
         LB_CUDA_CHECK(cudaEventRecord(ev_left, sl));

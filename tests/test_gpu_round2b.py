@@ -164,3 +164,30 @@ def test_batched_two_per_warp_equals_one_row_kernel(lb):
         if info_ref == 0 and b >= 64:
             assert np.array_equal(ipiv[b], ipiv_ref), b
             assert np.max(np.abs(out[b].T - r)) < 1e-11 * np.max(np.abs(r)), b
+
+
+@pytest.mark.parametrize("shape", [(3000, 3000), (4100, 2300), (2300, 4100), (2600, 300)])
+def test_dgetrf_deferred_composed_interchanges(lb, shape):
+    """the interchanges left of the panels are kept, composed per block column and applied in one streaming pass at the end:
+    IPIV and factors bit-identical to the immediate plan-by-plan application and to the plan-by-plan deferred one, and DGET01 passes"""
+    m, n = shape
+    L = lb.lib()
+    a0 = lb.dev.larnv_matrix(m, n, SEED)
+    outs = []
+    try:
+        L.lb200_set_getrf_params(128, 0, 1)
+        for mode, tail in ((0, 512), (1, 128), (1, 1024), (2, 128)):
+            L.lb200_set_getrf_defer_left(mode, tail)
+            a = a0.clone()
+            piv, info = lb.dev.getrf(a)
+            torch.cuda.synchronize()
+            assert int(info) == 0
+            outs.append((piv.clone(), a))
+    finally:
+        L.lb200_set_getrf_params(512, 0, 1)
+        L.lb200_set_getrf_defer_left(1, 512)
+    for piv, a in outs[1:]:
+        assert torch.equal(piv, outs[0][0]) and _bits_equal(a, outs[0][1])
+    x = np.asfortranarray(a0.cpu().numpy())
+    got = np.asfortranarray(outs[1][1].cpu().numpy())
+    assert O.dget01(x, got, outs[1][0].cpu().numpy()) < O.THRESH
