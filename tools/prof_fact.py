@@ -3,6 +3,7 @@ import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import lapack_b200 as lb
+if os.environ.get("LB200_GEMM_CFG"): lb.lib().lb200_set_gemm_config(int(os.environ["LB200_GEMM_CFG"]))
 which, n = sys.argv[1], int(sys.argv[2])
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 a0 = lb.dev.larnv_matrix(n, 512 if which == "panel" else n)

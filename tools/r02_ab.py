@@ -1,4 +1,5 @@
-"""One-call A/B of the round-2 experiments: lean-loader / staggered GEMM (cfg 13, 14) and thin LU leaves.  python tools/r02_ab.py [n]"""
+"""One-call A/B of the round-2 experiments: general vs lean GEMM loader (cfg 8 / 13 / 14) and thin LU leaves.  python tools/r02_ab.py [n]
+(the first-wave skew knob that the log profiles/r02_gemm_lean_ab.txt mentions was dropped from the library after this run)"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,8 +21,8 @@ if "nogemm" not in sys.argv:
         ar, ac = (m, k) if ta == "N" else (k, m); br, bc = (k, nn) if tb == "N" else (nn, k)
         A = lb.dev.colmajor(ar, ac); A.normal_(); B = lb.dev.colmajor(br, bc); B.normal_(); C0 = lb.dev.colmajor(m, nn); C0.normal_()
         ref = None
-        for cfg, stg in ((8, 0), (13, 0), (13, 16000), (13, 33000), (13, 50000), (14, 0), (14, 33000)):
-            L.lb200_set_gemm_config(cfg); L.lb200_set_gemm_stagger(stg)
+        for cfg, stg in ((8, 0), (13, 0), (14, 0)):
+            L.lb200_set_gemm_config(cfg)
             C = C0.clone()
             lb.dev.gemm(ta, tb, -1.0, A, B, 1.0, C); torch.cuda.synchronize()
             if ref is None: ref = C.clone()
@@ -29,7 +30,7 @@ if "nogemm" not in sys.argv:
             ms = t(lambda: lb.dev.gemm(ta, tb, -1.0, A, B, 1.0, C))
             print(f"gemm {ta}{tb} {m}x{nn}x{k} cfg {cfg} stagger {stg}: {ms:.3f} ms {2*m*nn*k/ms*1e-9:.2f} TF/s  bitwise==cfg8: {same}", flush=True)
         del A, B, C, C0, ref
-    L.lb200_set_gemm_config(-1); L.lb200_set_gemm_stagger(0)
+    L.lb200_set_gemm_config(-1)
 
 a0 = lb.dev.larnv_matrix(n, n)
 a = a0.clone()
@@ -43,11 +44,11 @@ def run(tag, reps=2):
     print(f"LU n={n} {tag}: {best:.1f} ms  {(2*n**3/3)/best*1e-9:.2f} TFLOP/s", flush=True)
     return piv.clone(), a.clone()
 p0, f0 = run("default", 3)
-for cfg, stg in ((13, 0), (13, 33000)):
-    L.lb200_set_gemm_config(cfg); L.lb200_set_gemm_stagger(stg)
+for cfg, stg in ((8, 0), (14, 0)):
+    L.lb200_set_gemm_config(cfg)
     p, f = run(f"gemm cfg {cfg} stagger {stg}")
     print("  ipiv equal:", bool((p == p0).all()), " factors bitwise equal:", bool(torch.equal(f, f0)))
-L.lb200_set_gemm_config(-1); L.lb200_set_gemm_stagger(0)
+L.lb200_set_gemm_config(-1)
 for mode in (1, 2):
     for mr in (16384, 12288, 8192, 4096):
         L.lb200_set_getrf_thin(mode, mr)
