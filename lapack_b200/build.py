@@ -10,16 +10,14 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblapack_b200.so")
 OBJ = os.path.join(HERE, "build")
 
+# never --use_fast_math: FP64 parity with the reference
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=default", "--use_fast_math=false"]
-NVCC_FLAGS.remove("--use_fast_math=false")   # never fast-math: FP64 parity
+              "-Xcompiler", "-fPIC,-fvisibility=default"]
 
 
 def sources(minimal: bool = False):
     if minimal:
         return ["gemm_f64.cu", "gemm_tma.cu", "runtime.cu", "capi.cu"]
-    if minimal:
-        return ["gemm_f64.cu", "runtime.cu", "capi.cu"]
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
