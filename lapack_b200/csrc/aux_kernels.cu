@@ -345,6 +345,7 @@ __global__ void laswp_long_copy_kernel(int rows, int n, const double* __restrict
     for (int c = blockIdx.y; c < n; c += gridDim.y) A[r + (i64)c * lda] = W[r + (i64)c * rows];
 }
 
+static void laswp_stream_permute(cudaStream_t s, int rows, int rmin, int n, double* A, i64 lda, const int* src);
 static void laswp_impl(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2, const int* ipiv, int incx,
                        int rows_hint) {
     if (n <= 0 || incx == 0 || k2 < k1) return;
@@ -366,6 +367,24 @@ static void laswp_impl(cudaStream_t s, int n, double* A, i64 lda, int k1, int k2
         count_launch(3);
         ws_free(s, src);
         ws_free(s, W);
+        LB_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    if (rows_hint > 0 && rows_hint <= LASWP_LONG_MAX && np_all >= 2 * LASWP_MAX_PIV && n > 64) {
+        // many columns AND a long pivot list (the two interchange sweeps of the recursive host-streamed DGETRF, DGETRS with many
+        // right-hand sides): compose the whole sequence once, then stream every column through its permutation (one pass over the
+        // touched rows instead of np/2048 plans of scattered line fills each)
+        static bool attr = false;
+        if (!attr) {
+            LB_CUDA_CHECK(cudaFuncSetAttribute(laswp_long_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (LASWP_LONG_MAX + LASWP_LONG_TILE) * 4));
+            attr = true;
+        }
+        int* src = (int*)ws_alloc(s, sizeof(int) * (size_t)rows_hint);
+        laswp_long_build_kernel<<<1, 256, (size_t)(rows_hint + LASWP_LONG_TILE) * sizeof(int), s>>>(rows_hint, k1, k2, ipiv, incx, src);
+        count_launch();
+        laswp_stream_permute(s, rows_hint, k1 - 1, n, A, lda, src);
+        ws_free(s, src);
         LB_CUDA_CHECK(cudaGetLastError());
         return;
     }
@@ -432,12 +451,14 @@ __global__ void __launch_bounds__(1024) laswp_chain_compose_kernel(int m, int np
     }
 }
 // persistent CTAs, one column at a time: gather the moved rows into this CTA's scratch column, then write them back
+// nb > 0: column c belongs to block column b = c / nb with its own permutation sigma + b*m, rows below (b+1)*nb;
+// nb == 0: one permutation for all columns, rows from rmin on (long pivot sequences, laswp_impl)
 __global__ void __launch_bounds__(1024) laswp_chain_apply_kernel(int m, int nb, int ncols, double* __restrict__ A, i64 lda,
-                                                                 const int* __restrict__ sigma, double* __restrict__ W) {
+                                                                 const int* __restrict__ sigma, double* __restrict__ W, int rmin) {
     double* w = W + (size_t)blockIdx.x * m;
     for (int c = blockIdx.x; c < ncols; c += gridDim.x) {
-        const int b = c / nb;
-        const int r0 = (b + 1) * nb;                 // rows above belong to earlier panels: untouched by plans b ..
+        const int b = nb > 0 ? c / nb : 0;
+        const int r0 = nb > 0 ? (b + 1) * nb : rmin; // rows above belong to earlier panels: untouched by plans b ..
         const int* sig = sigma + (size_t)b * m;
         double* col = A + (i64)c * lda;
         for (int i = r0 + threadIdx.x; i < m; i += 1024) {
@@ -449,6 +470,13 @@ __global__ void __launch_bounds__(1024) laswp_chain_apply_kernel(int m, int nb, 
             if (sig[i] != i) col[i] = w[i];
         __syncthreads();
     }
+}
+static void laswp_stream_permute(cudaStream_t s, int rows, int rmin, int n, double* A, i64 lda, const int* src) {
+    const int grid = min(2 * num_sms(), n);
+    double* W = (double*)ws_alloc(s, sizeof(double) * (size_t)grid * rows);
+    laswp_chain_apply_kernel<<<grid, 1024, 0, s>>>(rows, 0, n, A, lda, src, W, rmin);
+    count_launch();
+    ws_free(s, W);
 }
 // plans[d] (device SwapPlan pointers, host array) applies to columns [0, (d+1)*nb); false = not applicable (caller falls back)
 bool laswp_apply_chain(cudaStream_t s, int m, int nb, int nplans, void* const* plans_host, double* A, i64 lda) {
@@ -466,7 +494,7 @@ bool laswp_apply_chain(cudaStream_t s, int m, int nb, int nplans, void* const* p
     int* sigma = (int*)ws_alloc(s, sizeof(int) * (size_t)nplans * m);
     double* W = (double*)ws_alloc(s, sizeof(double) * (size_t)grid * m);
     laswp_chain_compose_kernel<<<1, 1024, smem, s>>>(m, nplans, list, sigma);
-    laswp_chain_apply_kernel<<<grid, 1024, 0, s>>>(m, nb, nplans * nb, A, lda, sigma, W);
+    laswp_chain_apply_kernel<<<grid, 1024, 0, s>>>(m, nb, nplans * nb, A, lda, sigma, W, 0);
     count_launch(2);
     ws_free(s, W); ws_free(s, sigma);
     LB_CUDA_CHECK(cudaGetLastError());

@@ -409,7 +409,7 @@ static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
     LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
     LB_CUDA_CHECK(cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, ldd * 8, (size_t)n1 * 8, n1, cudaMemcpyDeviceToHost, copy_stream));
     LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_up, 0));
-    lb::laswp(s, n2, dA12, ldd, 1, n1, dp, 1);                                          // dgetrf2.f:236
+    lb::laswp_rows(s, n2, n, dA12, ldd, 1, n1, dp, 1);                                  // dgetrf2.f:236 (composed, one streaming pass)
     lb::trsm(s, 'L', 'L', 'N', 'U', n1, n2, 1.0, dA, ldd, dA12, ldd);                   // dgetrf2.f:240
     LB_CUDA_CHECK(cudaEventRecord(ev_u12, s));
     LB_CUDA_CHECK(cudaStreamWaitEvent(copy_stream, ev_u12, 0));
@@ -424,7 +424,7 @@ static int getrf_host_streamed(int n, double* A, int lda, int* ipiv) {
     lb::stream_out() = nullptr;
     lb::info_max_offset(s, dinfo, dinfo + 8, n1);                                       // dgetrf2.f:251-252
     lb::iadd(s, n2, dp + n1, n1);                                                       // dgetrf2.f:257-259
-    lb::laswp(s, n1, dA, ldd, n1 + 1, n, dp, 1);                                        // dgetrf2.f:263
+    lb::laswp_rows(s, n1, n, dA, ldd, n1 + 1, n, dp, 1);                                // dgetrf2.f:263 (composed, one streaming pass)
     // what is left of A22: the block lower trapezoids (L and the diagonal blocks), or everything if nothing was streamed
     {
         const int nb = lb::getrf_block();

@@ -191,3 +191,38 @@ def test_dgetrf_deferred_composed_interchanges(lb, shape):
     x = np.asfortranarray(a0.cpu().numpy())
     got = np.asfortranarray(outs[1][1].cpu().numpy())
     assert O.dget01(x, got, outs[1][0].cpu().numpy()) < O.THRESH
+
+
+def test_long_pivot_lists_on_many_columns(lb):
+    """DLASWP with a long pivot list on many columns is composed once and streamed (laswp_impl): the interchanges of DGETRS with
+    many right-hand sides, forward and reverse, against an independent application by the short-list path, and the two interchange
+    sweeps of the host-streamed square DGETRF (n1 >= 4096) against the device-resident driver"""
+    n, nrhs = 5000, 96
+    a = lb.dev.larnv_matrix(n, n, SEED)
+    piv, info = lb.dev.getrf(a)
+    assert int(info) == 0
+    b0 = lb.dev.larnv_matrix(n, nrhs, SEED, n * n)
+    for trans in "NT":
+        x = b0.clone()
+        lb.dev.getrs(trans, a, piv, x)                         # nrhs > 64, n pivots: composed + streamed interchanges
+        # reference: the same solve in column groups of 48 (n pivots on <= 64 columns: gather / copy-back path)
+        y = b0.clone()
+        for c0 in range(0, nrhs, 48):
+            lb.dev.getrs(trans, a, piv, y[:, c0:c0 + 48])
+        torch.cuda.synchronize()
+        # (the triangular solves may split K differently for 96 and 48 columns: agreement to rounding, not bit for bit)
+        assert float((x - y).abs().max()) < 1e-11 * float(y.abs().max()), trans
+    # host-streamed DGETRF with both sweeps long
+    n = 12288
+    a0 = lb.dev.larnv_matrix(n, n, SEED)
+    buf = torch.empty((n, n), dtype=torch.float64).pin_memory()
+    h = buf.numpy().T
+    h[:] = a0.cpu().numpy()
+    ipiv = np.zeros(n, dtype=np.int32)
+    assert lb.f77.dgetrf(n, n, h, n, ipiv) == 0
+    pd, infod = lb.dev.getrf(a0)
+    torch.cuda.synchronize()
+    assert np.array_equal(ipiv, pd.cpu().numpy())
+    got = torch.from_numpy(np.ascontiguousarray(h)).to(a0.device)
+    scale = float(a0.abs().max())
+    assert float((got - a0).abs().max()) < 1e-10 * scale
