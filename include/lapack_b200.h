@@ -46,6 +46,8 @@ void lb200_set_getrf_tall_rows(int rows_per_cta);
 void lb200_set_getrf_cluster_fat(int on);
 /* thin LU leaves for panels taller than min_rows: 0 = off, 1 = 128 threads x 2 rows per CTA, 2 = 64 threads x 4 rows (one GEMM-CTA slot each) */
 void lb200_set_getrf_thin(int mode, int min_rows);
+/* DGETRF two-level driver: outer block size (default 4096; 0 = single level); used for min(m,n) >= 3*nb, m <= 56320, device-resident callers */
+void lb200_set_getrf_super(int nb);
 /* DGETRF: 1 (default) = the interchanges left of the panel are applied in the tail of the factorization (trailing matrix <= tail_rows rows) */
 void lb200_set_getrf_defer_left(int on, int tail_rows);
 /* batched 32x32 DGETRF: 2 (default) = two matrices per warp, 0 = one matrix per warp, 1 = persistent software-pipelined one-matrix kernel (measured slower) */

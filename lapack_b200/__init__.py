@@ -55,6 +55,7 @@ def _declare(L):
     L.lb200_set_getrf_tall_rows.argtypes = [i]
     L.lb200_set_getrf_cluster_fat.argtypes = [i]
     L.lb200_set_getrf_thin.argtypes = [i, i]
+    L.lb200_set_getrf_super.argtypes = [i]
     L.lb200_set_getrf_defer_left.argtypes = [i, i]
     L.lb200_set_batched_mode.argtypes = [i]
     L.lb200_set_laswp_bulk.argtypes = [i]

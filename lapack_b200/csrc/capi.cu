@@ -20,6 +20,7 @@ void getrf_set_big_leaf(int v);
 void getrf_set_tall_rows(int r);
 void getrf_set_cluster_fat(int v);
 void getrf_set_thin(int mode, int min_rows);
+void getrf_set_super(int nb);
 void getrf_set_defer_left(int on, int tail_rows);
 void batched_set_mode(int m);
 void laswp_set_bulk(int on);
@@ -62,6 +63,7 @@ void lb200_set_getrf_big_leaf(int rows4) { lb::getrf_set_big_leaf(rows4); }
 void lb200_set_getrf_tall_rows(int rows_per_cta) { lb::getrf_set_tall_rows(rows_per_cta); }
 void lb200_set_getrf_cluster_fat(int on) { lb::getrf_set_cluster_fat(on); }
 void lb200_set_getrf_thin(int mode, int min_rows) { lb::getrf_set_thin(mode, min_rows); }
+void lb200_set_getrf_super(int nb) { lb::getrf_set_super(nb); }
 void lb200_set_getrf_defer_left(int on, int tail_rows) { lb::getrf_set_defer_left(on, tail_rows); }
 void lb200_set_batched_mode(int mode) { lb::batched_set_mode(mode); }
 void lb200_set_laswp_bulk(int on) { lb::laswp_set_bulk(on); }

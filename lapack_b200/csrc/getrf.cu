@@ -857,24 +857,40 @@ struct LuTrace {
     }
 };
 
-void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
-    std::lock_guard<std::recursive_mutex> lock(g_lib_mutex);
+// Two-level driver.  level 0 = the blocked right-looking driver described above (NB = 512, panel = recursive DGETRF2 kernels).
+// level 1 (lb200_set_getrf_super(4096); OFF by default) = the SAME driver with NB = 4096 whose "panel" is the level-0 driver on its
+// own stream set: the trailing updates then have K = 4096, the 4096 interchanges of a step are composed and streamed (laswp_rows),
+// and the level-0 factorization of the next 4096 columns runs beside the level-1 update.  Measured at n = 32768
+// (profiles/r02c_two_level_lu.txt): same IPIV, the update GEMMs drop from 735 to 598 ms as intended, but the level-0 factorization
+// beside GEMM CTAs that live 8x longer takes 154 instead of ~55 ms per block, the 4096-wide U12 solves (8% of the flops instead of
+// 1%) leave 7-8 ms gaps before every chunk, and the first block has nothing to hide behind: 832-848 ms against 794.  A is the (base, *) corner of the caller's matrix: pivots, INFO and the interchange plans use rows of the CALLER's matrix
+// (base + local row), ipiv0 is the caller's pivot array.
+static int g_super_nb = 0;                   // 0 = single level (default: the two-level driver was measured slower, see below)
+void getrf_set_super(int nb) { g_super_nb = nb; }
+static int g_driver_top_level = 0;           // level of the outermost getrf_driver call in flight (under g_lib_mutex)
+static void getrf_driver(int level, cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv0, int base, int* info) {
     static const bool trace_on = getenv("LB200_TRACE_LU") != nullptr;
     // Profiling aid (WRONG RESULTS, timing only): LB200_ABLATE bit 0 = skip the interchanges left of the panel, bit 1 = skip the
     // interchanges of the trailing columns, bit 2 = skip the U12 solve -- measures what each memory-bound stage costs the update GEMMs.
     static const int ablate = getenv("LB200_ABLATE") ? atoi(getenv("LB200_ABLATE")) : 0;
     LuTrace trace;
-    LuTrace* tr = trace_on ? &trace : nullptr;
+    LuTrace* tr = (trace_on && g_driver_top_level == level && base == 0) ? &trace : nullptr;    // the top-level call only
     if (tr) { cudaEventCreate(&tr->origin); cudaEventRecord(tr->origin, s); }
-    LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
     if (m <= 0 || n <= 0) return;
     const int mn = min(m, n);
-    const int nb = min(g_nb, 2048);
-    if (nb >= mn) { getrf_panel(s, m, n, A, lda, ipiv, info, 0); return; }
+    const int nb = level == 0 ? min(g_nb, 2048) : g_super_nb;
+    int* const ipiv = ipiv0 + base;              // pivots of the local rows
+    double* const Arow0 = A - base;              // row 0 of the caller's matrix in local column 0 (interchanges use caller rows)
+    auto factor_panel = [&](cudaStream_t st, int pm, int pn, double* P, int off) {
+        // panel at local offset (off, off): level 0 = the recursive kernels, level 1 = the level-0 driver
+        if (level == 0) getrf_panel(st, pm, pn, P, lda, ipiv + off, info, base + off);
+        else getrf_driver(0, st, pm, pn, P, lda, ipiv0, base + off, info);
+    };
+    if (nb >= mn) { factor_panel(s, m, n, A, 0); return; }
 
     const bool la = g_lookahead != 0;
-    Aux& ax = aux();
-    StreamOut* so = stream_out();
+    Aux& ax = aux(level);
+    StreamOut* so = (level == 0 && base == 0) ? stream_out() : nullptr;
     // Streams (look-ahead on): sp = panel (highest priority), sq = memory-bound preparation of the trailing
     // columns (interchanges + U12 solve, medium priority), su = trailing GEMMs (low priority), sl = interchanges
     // left of the panel (low priority, off the critical path).  The trailing columns are processed in up to five
@@ -897,7 +913,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_join, 0));
     }
     // first panel
-    getrf_panel(sp, m, min(nb, mn), A, lda, ipiv, info, 0);
+    factor_panel(sp, m, min(nb, mn), A, 0);
     if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
     bool gemm_recorded = false;
     struct DeferredSwap { void* plan; int ncols, npiv; };
@@ -912,8 +928,9 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
             pl.push_back(deferred[d].plan);
             if (deferred[d].ncols != (int)(d + 1) * nb || deferred[d].npiv != nb) chain_ok = false;
         }
-        if (!(chain_ok && laswp_apply_chain(sl, m, nb, (int)pl.size(), pl.data(), A, lda)))
-            for (const DeferredSwap& d : deferred) laswp_apply_plan(sl, d.ncols, A, lda, d.plan, d.npiv);
+        // (with base > 0 the permutations cover the caller's rows 0 .. base + m; they are the identity above base)
+        if (!(chain_ok && laswp_apply_chain(sl, base + m, nb, (int)pl.size(), pl.data(), Arow0, lda)))
+            for (const DeferredSwap& d : deferred) laswp_apply_plan(sl, d.ncols, Arow0, lda, d.plan, d.npiv);
         for (const DeferredSwap& d : deferred) laswp_plan_free(sl, d.plan);
         deferred.clear();
     };
@@ -923,7 +940,6 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         const int jb = min(nb, mn - j);
         const int jn = j + jb;                       // first column after this panel
         double* Ajj = A + j + (i64)j * lda;
-        const int* piv = ipiv;                       // absolute pivots (already shifted by j on the panel stream)
         const int jb2 = (jn < mn) ? min(nb, mn - jn) : 0;
         // chunk boundaries (columns): [c[0],c[1]) = next panel's columns (or everything if there is no next panel),
         // [c[1],c[2]) = the panel after that, a narrow third chunk (its preparation can only start after the whole update j-1 and
@@ -955,7 +971,12 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         }
         if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_panel, 0));                 // panel j is factored
         // one plan for this panel's interchanges (dgetrf.f:193,199), applied to all column ranges
-        void* plan = laswp_plan(sq, j + 1, jn, piv, 1);
+        // level 1: 4096 interchanges per step are beyond one plan; they are composed and streamed per column range (laswp_rows)
+        void* plan = (level == 0) ? laswp_plan(sq, base + j + 1, base + jn, ipiv0, 1) : nullptr;
+        auto swap_cols = [&](cudaStream_t st, int ncols, double* cols_row0) {       // cols_row0: caller row 0 of the first column
+            if (plan) laswp_apply_plan(st, ncols, cols_row0, lda, plan, jb);
+            else laswp_rows(st, ncols, base + m, cols_row0, lda, base + j + 1, base + jn, ipiv0, 1);
+        };
         // preparation on sq: interchanges + block row of U for every chunk, in order
         for (int q = 0; q < nchunk; ++q) {
             const int w = c[q + 1] - c[q];
@@ -966,7 +987,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 for (int r = 0; r < npc; ++r)
                     if (pc_lo[r] < c[q + 1] && c[q] < pc_hi[r]) LB_CUDA_CHECK(cudaStreamWaitEvent(sq, ev_upd[r], 0));
             if (tr) tr->mark(sq, j / nb, 10 + q, true);
-            if (!(ablate & 2)) laswp_apply_plan(sq, w, A + (i64)c[q] * lda, lda, plan, jb);           // dgetrf.f:199
+            if (!(ablate & 2)) swap_cols(sq, w, Arow0 + (i64)c[q] * lda);                            // dgetrf.f:199
             // (inverted 32 x 32 diagonal blocks -- trsm_set_inverse_leaves, used by DPOTRF -- were measured neutral here: 806 vs 807 ms)
             if (!(ablate & 4)) trsm(sq, 'L', 'L', 'N', 'U', jb, w, 1.0, Ajj, lda, A + j + (i64)c[q] * lda, lda);   // dgetrf.f:204
             if (tr) tr->mark(sq, j / nb, 10 + q, false);
@@ -1001,7 +1022,7 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
                 // factor the next panel (overlaps with the rest of this update when look-ahead is on)
                 // the leaves write absolute pivot rows (dgetrf.f:187-189 shift applied at the source)
                 if (tr) tr->mark(sp, j / nb, 20, true);
-                getrf_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, lda, ipiv + jn, info, jn);
+                factor_panel(sp, m - jn, jb2, A + jn + (i64)jn * lda, jn);
                 if (tr) tr->mark(sp, j / nb, 20, false);
                 if (la) LB_CUDA_CHECK(cudaEventRecord(ev_panel, sp));
             }
@@ -1017,15 +1038,15 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         // factorization does not hide them either (808 ms).  So they are DEFERRED and COMPOSED: the plans are kept until the trailing
         // matrix is down to g_defer_tail_rows rows (default: the last panel), then every block column receives its whole chain of
         // interchanges as ONE row permutation in a streaming pass (laswp_apply_chain): 809 -> 793 ms, bit-identical results.
-        const bool defer = la && g_defer_left && (m - jn) > g_defer_tail_rows && jn < mn;
+        const bool defer = la && plan && g_defer_left && (m - jn) > g_defer_tail_rows && jn < mn;
         if (defer) {
             if (j > 0 && !(ablate & 1)) deferred.push_back(DeferredSwap{plan, j, jb});
             else laswp_plan_free(sl, plan);
         } else {
             if (la) LB_CUDA_CHECK(cudaStreamWaitEvent(sl, ev_plan, 0));
             flush_deferred();
-            if (j > 0 && !(ablate & 1)) laswp_apply_plan(sl, j, A, lda, plan, jb);
-            laswp_plan_free(sl, plan);
+            if (j > 0 && !(ablate & 1)) swap_cols(sl, j, Arow0);
+            if (plan) laswp_plan_free(sl, plan);
         }
     }
     if (!deferred.empty()) {        // (not reached: the last step is never deferred)
@@ -1043,6 +1064,18 @@ void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* inf
         LB_CUDA_CHECK(cudaStreamWaitEvent(s, ev_plan, 0));
     }
     if (tr) { tr->dump(); cudaEventDestroy(tr->origin); }
+}
+
+void getrf(cudaStream_t s, int m, int n, double* A, i64 lda, int* ipiv, int* info) {
+    std::lock_guard<std::recursive_mutex> lock(g_lib_mutex);
+    LB_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), s));
+    if (m <= 0 || n <= 0) return;
+    // level 1 needs the composed long-list interchanges (rows <= 55K, laswp_impl) and is only worth it with >= 3 outer blocks;
+    // host-streamed callers (lb::StreamOut) keep the single-level driver, whose block rows of U they download as they finish
+    const bool super = g_super_nb >= 1024 && g_lookahead != 0 && min(m, n) >= 3 * g_super_nb && m <= 55 * 1024 && !stream_out() &&
+                       g_super_nb > min(g_nb, 2048);
+    g_driver_top_level = super ? 1 : 0;
+    getrf_driver(super ? 1 : 0, s, m, n, A, lda, ipiv, 0, info);
 }
 
 // DGETRS (SRC/dgetrs.f:181-218); argument checks live in the Fortran-ABI layer

@@ -133,7 +133,7 @@ struct Aux {
     cudaEvent_t ev[32];
     bool ready = false;
 };
-Aux& aux();
+Aux& aux(int level = 0);    // level 1: second stream set for the outer level of the two-level LU driver
 
 int num_sms();
 std::recursive_mutex& driver_mutex();    // serialises the drivers that share lb::aux()'s streams and events

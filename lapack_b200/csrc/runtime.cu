@@ -86,21 +86,32 @@ void ws_free(cudaStream_t s, void* p) {
     if (p) LB_CUDA_CHECK(cudaFreeAsync(p, s));
 }
 
-Aux& aux() {
-    static Aux a;
+Aux& aux(int level) {
+    static Aux a[2];
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    if (!a.ready) {
+    Aux& x = a[level ? 1 : 0];
+    if (!x.ready) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically lowest = highest priority
-        LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.panel_stream, cudaStreamNonBlocking, hi));
-        LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.update_stream, cudaStreamNonBlocking, lo));
-        LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.side_stream, cudaStreamNonBlocking, lo));
-        LB_CUDA_CHECK(cudaStreamCreateWithPriority(&a.prep_stream, cudaStreamNonBlocking, (hi + 1 <= lo) ? hi + 1 : hi));
-        for (int i = 0; i < 32; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&a.ev[i], cudaEventDisableTiming));
-        a.ready = true;
+        auto pr = [&](int steps_below_top) { const int p = hi + steps_below_top; return p > lo ? lo : p; };
+        if (level == 0) {
+            // level 0: panel on top, preparation next, updates / side work two steps above the lowest priority when the device has
+            // that many levels, so that a level-0 factorization running as the "panel" of level 1 outranks level 1's updates
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.panel_stream, cudaStreamNonBlocking, pr(0)));
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.prep_stream, cudaStreamNonBlocking, pr(1)));
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.update_stream, cudaStreamNonBlocking, pr(3)));
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.side_stream, cudaStreamNonBlocking, pr(3)));
+        } else {
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.panel_stream, cudaStreamNonBlocking, pr(2)));   // carries the level-0 driver
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.prep_stream, cudaStreamNonBlocking, pr(4)));
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.update_stream, cudaStreamNonBlocking, lo));
+            LB_CUDA_CHECK(cudaStreamCreateWithPriority(&x.side_stream, cudaStreamNonBlocking, lo));
+        }
+        for (int i = 0; i < 32; ++i) LB_CUDA_CHECK(cudaEventCreateWithFlags(&x.ev[i], cudaEventDisableTiming));
+        x.ready = true;
     }
-    return a;
+    return x;
 }
 
 // ----------------------------------------------------------------------------------------------

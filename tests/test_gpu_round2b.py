@@ -226,3 +226,27 @@ def test_long_pivot_lists_on_many_columns(lb):
     got = torch.from_numpy(np.ascontiguousarray(h)).to(a0.device)
     scale = float(a0.abs().max())
     assert float((got - a0).abs().max()) < 1e-10 * scale
+
+
+@pytest.mark.parametrize("shape", [(3300, 3300), (4200, 3100)])
+def test_dgetrf_two_level_driver(lb, shape):
+    """lb200_set_getrf_super: the outer level (NB = 1024 here) whose panel is the NB = 256 driver gives LAPACK's pivots and, up to
+    rounding (different K-blocking of the updates), the factors of the single-level driver; DGET01 passes"""
+    m, n = shape
+    L = lb.lib()
+    a0 = lb.dev.larnv_matrix(m, n, SEED)
+    try:
+        L.lb200_set_getrf_params(256, 0, 1)
+        L.lb200_set_getrf_super(0)
+        a1 = a0.clone(); p1, i1 = lb.dev.getrf(a1)
+        L.lb200_set_getrf_super(1024)
+        a2 = a0.clone(); p2, i2 = lb.dev.getrf(a2)
+        torch.cuda.synchronize()
+    finally:
+        L.lb200_set_getrf_super(0)
+        L.lb200_set_getrf_params(512, 0, 1)
+    assert int(i1) == 0 and int(i2) == 0
+    assert torch.equal(p1, p2)
+    assert float((a1 - a2).abs().max()) < 1e-11 * float(a1.abs().max())
+    x = np.asfortranarray(a0.cpu().numpy())
+    assert O.dget01(x, np.asfortranarray(a2.cpu().numpy()), p2.cpu().numpy()) < O.THRESH

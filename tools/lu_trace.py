@@ -25,6 +25,6 @@ for st in sorted(recs):
     last = [x for x in g if x][-1]
     prev_end = last[1]
     tot_gemm += sum(dur(x) for x in g); tot_gap += gap0 + gap1 + gap2 + gap3 + gap4
-    if st % 4 == 0 or st > 56:
+    if st % 4 == 0 or st > 56 or len(recs) < 20:
         print(f"{st:3d} {dur(g[0]):7.3f} {dur(g[1]):7.3f} {dur(g[2]):7.3f} {dur(g[3]):7.3f} {dur(g[4]):7.3f} {dur(r.get(20)):6.3f} {dur(r.get(10)):6.3f} {gap0:9.3f} {gap1:9.3f} {gap2:9.3f} {gap3:9.3f} {gap4:9.3f}")
 print(f"total GEMM {tot_gemm:.1f} ms, total update-stream gaps {tot_gap:.1f} ms, end {prev_end:.1f} ms")
