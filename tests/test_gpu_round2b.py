@@ -250,3 +250,28 @@ def test_dgetrf_two_level_driver(lb, shape):
     assert float((a1 - a2).abs().max()) < 1e-11 * float(a1.abs().max())
     x = np.asfortranarray(a0.cpu().numpy())
     assert O.dget01(x, np.asfortranarray(a2.cpu().numpy()), p2.cpu().numpy()) < O.THRESH
+
+
+@pytest.mark.parametrize("uplo", "LU")
+def test_dpotrf_inverted_diagonal_block_leaves(lb, uplo):
+    """DPOTRF's panel solve uses inverted 32 x 32 diagonal blocks (DMMA leaves) once the panel has >= 1024 rows / columns: both
+    triangles at a size that reaches it, against the substitution leaves (rounding-level agreement) and DPOT01"""
+    n = 2300
+    L = lb.lib()
+    a0 = lb.dev.larnv_matrix(n, n, SEED)
+    lb.dev.make_spd(a0, float(n))
+    s, _ = O.spd_matrix(n, SEED)
+    outs = []
+    try:
+        for inv in (1, 0):
+            L.lb200_set_trsm_inverse(inv)
+            a = a0.clone()
+            info = lb.dev.potrf(uplo, a)
+            torch.cuda.synchronize()
+            assert int(info) == 0
+            outs.append(a)
+    finally:
+        L.lb200_set_trsm_inverse(1)
+    tri = torch.tril if uplo == "L" else torch.triu
+    assert float((tri(outs[0]) - tri(outs[1])).abs().max()) < 1e-12 * float(tri(outs[1]).abs().max())
+    assert O.dpot01(uplo, s, np.asfortranarray(outs[0].cpu().numpy())) < O.THRESH
